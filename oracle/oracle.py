@@ -1,0 +1,259 @@
+"""ctypes binding of the CPU oracle (oracle/optimet_oracle.cpp).
+
+TEST INFRASTRUCTURE ONLY: may be imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs.  The product package
+(optimet_b200/) never imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "liboptimet_oracle.so")
+AMOS_PATH = os.path.join(HERE, "_ref", "libamos_ref.so")
+
+_lib = None
+
+
+def build(force=False):
+    """Compile the oracle (and oracle/_ref when /root/reference is present)."""
+    subprocess.check_call(["make", "-s", "-C", HERE] + (["-B"] if force else []))
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        _lib = C.CDLL(LIB_PATH)
+        _lib.orc_case_create.restype = C.c_void_p
+        _lib.orc_case_error.restype = C.c_char_p
+        _lib.orc_case_error.argtypes = [C.c_void_p]
+        _lib.orc_bessel_calls.restype = C.c_long
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _c2(z):
+    z = complex(z)
+    return (C.c_double * 2)(z.real, z.imag)
+
+
+def have_amos():
+    return os.path.exists(AMOS_PATH)
+
+
+def set_bessel_backend(backend):
+    """0 = own restatement, 1 = the reference's AMOS compiled into oracle/_ref."""
+    rc = lib().orc_set_bessel_backend(int(backend), AMOS_PATH.encode())
+    if rc != 0:
+        raise RuntimeError("AMOS backend unavailable (oracle/_ref/libamos_ref.so missing)")
+
+
+def set_threads(n):
+    lib().orc_set_threads(int(n))
+
+
+def set_as_shipped(dense_T, bessel_in_loops):
+    lib().orc_set_as_shipped(int(dense_T), int(bessel_in_loops))
+
+
+def bessel(kind, z, nmax):
+    d = np.zeros(nmax + 1, dtype=np.complex128)
+    dd = np.zeros(nmax + 1, dtype=np.complex128)
+    rc = lib().orc_bessel(int(kind), _c2(z), int(nmax), _p(d), _p(dd))
+    if rc:
+        raise RuntimeError("oracle bessel failed")
+    return d, dd
+
+
+def ynm(the, phi, n, m):
+    out = (C.c_double * 2)()
+    lib().orc_ynm(C.c_double(the), C.c_double(phi), n, m, out)
+    return complex(out[0], out[1])
+
+
+def wigner(kind, js):
+    arr = (C.c_int * len(js))(*[int(j) for j in js])
+    out = C.c_double()
+    lib().orc_wigner(kind, arr, C.byref(out))
+    return out.value
+
+
+def ta(R, k, regular, n, m, l, kk):
+    out = (C.c_double * 2)()
+    rc = lib().orc_ta((C.c_double * 3)(*R), _c2(k), int(regular), n, m, l, kk, out)
+    if rc:
+        raise RuntimeError("oracle ta failed")
+    return complex(out[0], out[1])
+
+
+def coupling(R, k, nMax, regular_flag=True):
+    """Coupling(relR, k, nMax, regular_flag) -> (A, B), n x n with A[p, q] (Coupling.h:29-41)."""
+    n = nMax * (nMax + 2)
+    A = np.zeros((n, n), dtype=np.complex128, order="F")
+    B = np.zeros((n, n), dtype=np.complex128, order="F")
+    rc = lib().orc_coupling((C.c_double * 3)(*R), _c2(k), int(nMax), int(regular_flag), _p(A), _p(B))
+    if rc:
+        raise RuntimeError("oracle coupling failed")
+    return A, B
+
+
+def cg_tables(nMax, nMaxS):
+    n, ns = nMax * (nMax + 2), nMaxS * (nMaxS + 2)
+    T = np.zeros((9, ns * n * n), dtype=np.float64)
+    ptrs = (C.c_void_p * 9)(*[T[i].ctypes.data for i in range(9)])
+    rc = lib().orc_cg_tables(int(nMax), int(nMaxS), ptrs)
+    if rc:
+        raise RuntimeError("oracle cg_tables failed")
+    return T
+
+
+def matvec(S, x):
+    S = np.asfortranarray(S, dtype=np.complex128)
+    x = np.ascontiguousarray(x, dtype=np.complex128)
+    y = np.zeros(S.shape[0], dtype=np.complex128)
+    lib().orc_matvec(_p(S), C.c_long(S.shape[0]), C.c_long(S.shape[1]), _p(x), _p(y))
+    return y
+
+
+SOLVER_DIRECT, SOLVER_ZCOMP, SOLVER_BELOS = 0, 1, 2
+
+
+def solve_dense(S, rhs, solver, tol=1e-6, maxit=240, restart=30, max_restarts=2):
+    S = np.asfortranarray(S, dtype=np.complex128)
+    rhs = np.ascontiguousarray(rhs, dtype=np.complex128)
+    x = np.zeros_like(rhs)
+    it = C.c_int()
+    rr = C.c_double()
+    opts = (C.c_double * 4)(tol, maxit, restart, max_restarts)
+    rc = lib().orc_solve_dense(_p(S), C.c_long(S.shape[0]), _p(rhs), int(solver), opts, _p(x), C.byref(it), C.byref(rr))
+    if rc:
+        raise RuntimeError("Error encountered while solving the linear system")
+    return x, it.value, rr.value
+
+
+MODEL_FIXED, MODEL_GOLD, MODEL_SILICON = 0, 3, 4
+
+
+class Case:
+    """One simulation case: geometry + excitation, as Simulation::scan_wavelengths drives it."""
+
+    def __init__(self):
+        self.h = C.c_void_p(lib().orc_case_create())
+        self.nMax = None
+
+    def __del__(self):
+        try:
+            lib().orc_case_destroy(self.h)
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc:
+            raise RuntimeError(lib().orc_case_error(self.h).decode())
+
+    def add_sphere(self, xyz_m, radius_m, nMax, model, params, nMaxS=None):
+        p = np.asarray(params, dtype=np.float64)
+        self._chk(lib().orc_case_add_sphere(self.h, (C.c_double * 3)(*xyz_m), C.c_double(radius_m), int(nMax),
+                                           int(nMax if nMaxS is None else nMaxS), int(model), _p(p)))
+        self.nMax = nMax
+
+    def set_background(self, eps, mu):
+        lib().orc_case_set_background(self.h, _c2(eps), _c2(mu))
+
+    def set_source(self, wavelength_m, theta, phi, Eth, Eph, SH_cond, nMax=None):
+        self._chk(lib().orc_case_set_source(self.h, C.c_double(wavelength_m), C.c_double(theta), C.c_double(phi),
+                                           _c2(Eth), _c2(Eph), int(SH_cond), int(self.nMax if nMax is None else nMax)))
+
+    def update_wavelength(self, lam_m):
+        self._chk(lib().orc_case_update_wavelength(self.h, C.c_double(lam_m)))
+
+    def info(self):
+        nobj, nMax, nMaxS = C.c_int(), C.c_int(), C.c_int()
+        om = C.c_double()
+        k = (C.c_double * 2)()
+        lib().orc_case_info(self.h, C.byref(nobj), C.byref(nMax), C.byref(nMaxS), C.byref(om), k)
+        return dict(nobj=nobj.value, nMax=nMax.value, nMaxS=nMaxS.value, omega=om.value, waveK=complex(k[0], k[1]))
+
+    def material(self, j):
+        out = np.zeros(6, dtype=np.complex128)
+        lib().orc_case_material(self.h, int(j), _p(out))
+        return dict(eps_r=out[0], eps_r_SH=out[1], ksippp=out[2], ksiparppar=out[3], gamma=out[4], mu_r=out[5])
+
+    def incident(self):
+        n = self.info()["nMax"]
+        n = n * (n + 2)
+        a = np.zeros(n, dtype=np.complex128)
+        b = np.zeros(n, dtype=np.complex128)
+        lib().orc_case_incident(self.h, _p(a), _p(b))
+        return a, b
+
+    def particle_factors(self, j, which):
+        i = self.info()
+        nm = i["nMax"] if which in (0, 4) else i["nMaxS"]
+        out = np.zeros(2 * nm * (nm + 2), dtype=np.complex128)
+        self._chk(lib().orc_case_particle_factors(self.h, int(j), int(which), _p(out)))
+        return out
+
+    def matrix(self, harmonic, i0=0, i1=None):
+        i = self.info()
+        nm = i["nMax"] if harmonic == 1 else i["nMaxS"]
+        n2 = 2 * nm * (nm + 2)
+        if i1 is None:
+            i1 = i["nobj"]
+        S = np.zeros((n2 * (i1 - i0), n2 * i["nobj"]), dtype=np.complex128, order="F")
+        self._chk(lib().orc_case_matrix(self.h, int(harmonic), int(i0), int(i1), _p(S)))
+        return S
+
+    def source(self):
+        i = self.info()
+        Q = np.zeros(2 * i["nMax"] * (i["nMax"] + 2) * i["nobj"], dtype=np.complex128)
+        self._chk(lib().orc_case_source(self.h, _p(Q)))
+        return Q
+
+    def inc_local(self, j):
+        i = self.info()
+        out = np.zeros(2 * i["nMax"] * (i["nMax"] + 2), dtype=np.complex128)
+        self._chk(lib().orc_case_inc_local(self.h, int(j), _p(out)))
+        return out
+
+    def sh_source(self, Xint_conj):
+        i = self.info()
+        x = np.ascontiguousarray(Xint_conj, dtype=np.complex128)
+        n = 2 * i["nMaxS"] * (i["nMaxS"] + 2) * i["nobj"]
+        K = np.zeros(n, dtype=np.complex128)
+        K1 = np.zeros(n, dtype=np.complex128)
+        self._chk(lib().orc_case_sh_source(self.h, _p(x), _p(K), _p(K1)))
+        return K, K1
+
+    def solve(self, solver=SOLVER_DIRECT, tol=1e-6, maxit=240, restart=30, max_restarts=2):
+        opts = (C.c_double * 4)(tol, maxit, restart, max_restarts)
+        self._chk(lib().orc_case_solve(self.h, int(solver), opts))
+
+    def vector(self, which):
+        i = self.info()
+        nm = i["nMax"] if which in (0, 1, 4) else i["nMaxS"]
+        out = np.zeros(2 * nm * (nm + 2) * i["nobj"], dtype=np.complex128)
+        lib().orc_case_get_vector(self.h, int(which), _p(out))
+        return out
+
+    def set_vector(self, which, v):
+        v = np.ascontiguousarray(v, dtype=np.complex128)
+        lib().orc_case_set_vector(self.h, int(which), _p(v), C.c_long(v.size))
+
+    def iters(self):
+        a, b = C.c_int(), C.c_int()
+        ra, rb = C.c_double(), C.c_double()
+        lib().orc_case_iters(self.h, C.byref(a), C.byref(b), C.byref(ra), C.byref(rb))
+        return a.value, b.value, ra.value, rb.value
+
+    def cross_sections(self):
+        out = (C.c_double * 5)()
+        self._chk(lib().orc_case_cross_sections(self.h, out))
+        return dict(ext=out[0], sca=out[1], abs_direct=out[2], sca_SH=out[3], abs_SH=out[4])
