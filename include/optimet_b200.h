@@ -1,0 +1,119 @@
+/* optimet_b200.h -- C ABI of the B200-native multiple-scattering hot path.
+ *
+ * Drop-in boundary for OPTIMET-3D's solver plugin: everything
+ * optimet::solver::AbstractSolver::{update, solve} (srcAna/Solver.h:62-144) and the
+ * Result cross-section reductions (srcAna/Result.cpp:557-794) compute is reachable through
+ * these entry points with plain pointers and sizes.  INTEGRATION.md shows the C++11 adaptor
+ * (`solver::B200Matrix : AbstractSolver`) a maintainer adds to srcAna/Solver.cpp:30-54.
+ *
+ * Conventions
+ *   - complex numbers are interleaved (re, im) doubles == std::complex<double> == Eigen t_complex;
+ *   - all pointers are HOST pointers; every call returns 0 on success, non-zero on error
+ *     (message via ob_last_error), mirroring the reference's std::runtime_error sites;
+ *   - harmonic: 1 = fundamental (FF), 2 = second harmonic (SH);
+ *   - n = nMax (nMax + 2) harmonics per polarisation, particle block = 2n, flat index
+ *     p = l(l+1) - m - 1 (srcAna/CompoundIterator.h:24-31), vector layout per particle
+ *     [TE(n) ; TM(n)], N = 2 n N_obj;
+ *   - one context per process and GPU; with world > 1 the context owns the particle block-rows
+ *     ob_partition() assigns to its rank and Krylov vectors are replicated on every rank.
+ */
+#ifndef OPTIMET_B200_H
+#define OPTIMET_B200_H
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ob_ctx ob_ctx;
+
+/* GMRES flavours.  ZCOMP = the in-tree Gmres_Zcomp (srcAna/PreconditionedMatrix.cpp:892-985:
+ * x0 = 0, modified Gram-Schmidt, |g|/||b|| stopping rule, max_iters per cycle, max_restarts cycles).
+ * BELOS = Belos "GMRES" as driven by srcAna/scalapack/LinearSystemSolver.hpp:94-142 (x0 = b, DGKS,
+ * ||r||/||r0|| rule, restart = "Num Blocks", max_iters = "Maximum Iterations" total). */
+enum { OB_GMRES_ZCOMP = 1, OB_GMRES_BELOS = 2 };
+
+typedef struct ob_gmres_opts {
+  int flavour;      /* OB_GMRES_ZCOMP | OB_GMRES_BELOS */
+  double tol;       /* "Convergence Tolerance" / Gmres_Zcomp tol */
+  int max_iters;    /* ZCOMP: maxit per cycle; BELOS: "Maximum Iterations" */
+  int restart;      /* BELOS: "Num Blocks" (ignored by ZCOMP) */
+  int max_restarts; /* ZCOMP: no_rest; BELOS: "Maximum Restarts" */
+} ob_gmres_opts;
+
+/* ---- context ---- */
+int ob_create(int device, ob_ctx **out);
+void ob_destroy(ob_ctx *ctx);
+const char *ob_last_error(ob_ctx *ctx); /* ctx may be NULL: last error of a failed ob_create */
+int ob_device_info(ob_ctx *ctx, int *sm_count, size_t *free_bytes, size_t *total_bytes);
+
+/* ---- multi-GPU row sharding (replaces the BLACS/MPI layer, srcAna/scalapack, srcAna/mpi) ----
+ * ob_partition: contiguous particle block-rows with the remainder rule of
+ * srcAna/PreconditionedMatrix.cpp:418-424 (pure host arithmetic, no GPU needed). */
+int ob_partition(int nobj, int world, int rank, int *first, int *count);
+int ob_comm_unique_id(char out[128]);                                  /* rank 0, then broadcast by the host */
+int ob_comm_init(ob_ctx *ctx, const char uid[128], int rank, int world); /* NCCL communicator over NVLink */
+
+/* ---- problem definition (what solver->update(run) reads from Geometry / Excitation) ---- */
+/* positions: Cartesian metres (Tools::toCartesian of Scatterer::vR), radius in metres */
+int ob_set_cluster(ob_ctx *ctx, int nobj, const double *xyz_m, const double *radius_m, int nMax, int nMaxS);
+/* omega = c k0; waveK = k0 sqrt(eps_b,r mu_b,r) (Excitation::waveK); eps/mu absolute (ElectroMagnetic::epsilon, mu);
+ * per-particle arrays hold N_obj complex values each; ksippp/ksiparppar/gamma = SH tensor coefficients */
+int ob_set_frequency(ob_ctx *ctx, double omega, const double waveK[2], const double eps_b[2], const double mu_b[2],
+                     const double *eps, const double *mu, const double *eps_SH, const double *mu_SH,
+                     const double *ksippp, const double *ksiparppar, const double *gamma);
+/* plane-wave coefficients at the origin, n complex each (Excitation::dataIncAp / dataIncBp) */
+int ob_set_incident(ob_ctx *ctx, const double *a_origin, const double *b_origin);
+
+/* ---- unit-level surface (parity with the reference's free functions / classes) ---- */
+/* Coupling(relR, k, nMax, regular_flag): A = diagonal, B = offdiagonal, n x n column-major
+ * (srcAna/Coupling.h:29-41; regular_flag has the ctor's meaning: true = particle coupling/Hankel) */
+int ob_vtac(ob_ctx *ctx, const double relR_sph[3], const double k[2], int regular_flag, int nMax, double *A,
+            double *B);
+/* which: 0 T_FF, 1 T_SH, 2 T_SH1_outer, 3 T_SH2_outer, 4 Iaux, 5 IauxSH1, 6 IauxSH2 (srcAna/Scatterer.cpp:39-412);
+ * out: N_obj x 2n complex */
+int ob_particle_factors(ob_ctx *ctx, int which, double *out);
+/* local incident coefficients of every particle, N complex (Excitation::getIncLocal) */
+int ob_inc_local(ob_ctx *ctx, double *out);
+
+/* ---- matrix (preconditioned_scattering_matrix[SH], srcAna/PreconditionedMatrix.cpp:350-400, 555-610) ---- */
+int ob_assemble(ob_ctx *ctx, int harmonic);
+int ob_release_matrix(ob_ctx *ctx, int harmonic);
+int ob_fetch_block(ob_ctx *ctx, int harmonic, int i, int j, double *out); /* 2n x 2n column-major; i must be local */
+int ob_fetch_matrix(ob_ctx *ctx, int harmonic, double *out);              /* local slab, (2n count) x N column-major */
+int ob_matvec(ob_ctx *ctx, int harmonic, const double *x, double *y);     /* y = S x, full length N on every rank */
+
+/* ---- sources (source_vector, source_vectorSH, source_vectorSH_K1ana; PreconditionedMatrix.cpp:1327-1436) ---- */
+int ob_source_ff(ob_ctx *ctx, double *Q);
+int ob_set_cg_tables(ob_ctx *ctx, const double *const tables[9]); /* order of Simulation.cpp:616 */
+int ob_build_cg_tables(ob_ctx *ctx);                              /* device build (symbol::*coeff, Symbol.cpp:1036-1446) */
+int ob_fetch_cg_table(ob_ctx *ctx, int t, double *out);
+int ob_source_sh(ob_ctx *ctx, const double *Xint_conj, double *K, double *K1ana);
+
+/* ---- solve (Solver::solve pieces) ---- */
+/* rhs == NULL: use the resident source of that harmonic (Q or K) */
+int ob_solve(ob_ctx *ctx, int harmonic, const double *rhs, double *x, const ob_gmres_opts *opts, int *iters,
+             double *relres);
+int ob_unprecondition_ff(ob_ctx *ctx, const double *X_sca, double *X_int);                          /* Solver.cpp:57-77 */
+int ob_unprecondition_sh(ob_ctx *ctx, const double *X_sca_SH, const double *K1ana, double *X_int_SH); /* Solver.cpp:95-116 */
+
+/* ---- whole step, device resident: update() + solve() + Result cross sections for the current
+ * frequency (Simulation.cpp:648-667).  Any of the output vector pointers may be NULL.
+ * cs: ext_FF, sca_FF, abs_FF (= ext - sca, Simulation.cpp:659), sca_SH, abs_SH.  stats: iters_FF, iters_SH */
+int ob_run(ob_ctx *ctx, const ob_gmres_opts *opts, int do_sh, double *X_sca, double *X_int, double *X_sca_SH,
+           double *X_int_SH, double cs[5], int stats[2]);
+
+/* ---- reductions (Result::get*CrossSection*, srcAna/Result.cpp:557-794) ---- */
+int ob_cross_sections(ob_ctx *ctx, const double *X_sca, const double *X_int, const double *X_sca_SH,
+                      const double *X_int_SH, int do_sh, double cs[5]);
+
+/* ---- instrumentation ---- */
+/* device-event timings (ms) of the last ob_run: 0 factors+source, 1 assemble FF, 2 solve FF, 3 SH source,
+ * 4 assemble SH, 5 solve SH, 6 cross sections, 7 matvec total (inside solves), 8 matvec count, 9 kernel launches */
+int ob_timings(ob_ctx *ctx, double out[16]);
+int ob_set_option(ob_ctx *ctx, const char *name, double value); /* "matvec_variant", "keep_matrices" */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,1156 @@
+// ob_api.cu -- context, GMRES drivers, row-sharded collectives and the C ABI (include/optimet_b200.h).
+#include "../../include/optimet_b200.h"
+#include "ob_internal.h"
+#include <algorithm>
+#include <cstring>
+#include <dlfcn.h>
+#include <nccl.h>
+
+namespace ob {
+
+typedef std::complex<double> hcd;
+
+// ---------------------------------------------------------------------------------------------
+// NCCL, bound at run time (the torch-bundled libnccl.so.2 when the host process imported torch)
+// ---------------------------------------------------------------------------------------------
+struct NcclApi {
+  void *handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  bool load() {
+    if(handle)
+      return true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for(const char *nm : names) {
+      handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      if(handle)
+        break;
+    }
+    if(!handle)
+      return false;
+#define OB_SYM(field, name) *(void **)(&field) = dlsym(handle, name)
+    OB_SYM(GetUniqueId, "ncclGetUniqueId");
+    OB_SYM(CommInitRank, "ncclCommInitRank");
+    OB_SYM(CommDestroy, "ncclCommDestroy");
+    OB_SYM(AllGather, "ncclAllGather");
+    OB_SYM(Broadcast, "ncclBroadcast");
+    OB_SYM(GroupStart, "ncclGroupStart");
+    OB_SYM(GroupEnd, "ncclGroupEnd");
+    OB_SYM(GetErrorString, "ncclGetErrorString");
+#undef OB_SYM
+    return GetUniqueId && CommInitRank && AllGather && Broadcast && GroupStart && GroupEnd;
+  }
+};
+static NcclApi g_nccl;
+#define OB_NCCL(call)                                                                                                  \
+  do {                                                                                                                 \
+    ncclResult_t r__ = (call);                                                                                         \
+    if(r__ != ncclSuccess)                                                                                             \
+      throw ob::Error(std::string("NCCL error: ") +                                                                    \
+                      (g_nccl.GetErrorString ? g_nccl.GetErrorString(r__) : "unknown"));                               \
+  } while(0)
+
+template <class T> struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  void alloc(size_t count) {
+    if(count <= n && p)
+      return;
+    release();
+    if(count == 0)
+      return;
+    OB_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    n = count;
+  }
+  void release() {
+    if(p)
+      cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  ~DevBuf() { release(); }
+};
+
+static void partition(int nobj, int world, int rank, int &first, int &count) {
+  // remainder rule of srcAna/PreconditionedMatrix.cpp:418-424
+  if(rank < nobj % world) {
+    first = rank * (nobj / world + 1);
+    count = nobj / world + 1;
+  } else {
+    first = rank * (nobj / world) + nobj % world;
+    count = nobj / world;
+  }
+}
+
+struct HarmonicState {
+  int nMax = 0, n = 0;
+  cplx k = mk(0, 0);
+  DevBuf<cplx> S; // local slab, column-major, ld = M_loc
+  bool assembled = false;
+  MatvecPlan plan;
+};
+
+} // namespace ob
+
+using namespace ob;
+
+struct ob_ctx {
+  int device = 0, sm_count = 148;
+  cudaStream_t st = nullptr;
+  int rank = 0, world = 1;
+  ncclComm_t comm = nullptr;
+  std::string err;
+
+  // cluster
+  int nobj = 0, nMax = 0, nMaxS = 0, first = 0, count = 0; // local particle rows [first, first+count)
+  DevBuf<double> xyz, radius;
+  // frequency / materials
+  bool have_freq = false, have_inc = false;
+  double omega = 0;
+  cplx waveK = mk(0, 0), eps_b = mk(0, 0), mu_b = mk(0, 0);
+  DevBuf<cplx> mat[7]; // eps, mu, eps_SH, mu_SH, ksippp, ksiparppar, gamma
+  std::vector<hcd> h_epsr_SH; // eps_SH / eps0 per particle (sigma in Result.cpp:784)
+  DevBuf<cplx> fac[7]; // Mie factors
+  bool fac_valid = false;
+  DevBuf<cplx> ainc;   // [a ; b] 2n
+  VtacTableSet tabs[2];
+  HarmonicState hs[2];
+  // CG tables
+  DevBuf<double> cg[9];
+  int cg_nmax = -1;
+  // resident vectors (full length N, replicated)
+  DevBuf<cplx> Q, Ksrc, K1ana, Xsca, Xint, XscaSH, XintSH, tmpA, tmpB;
+  // GMRES workspace
+  DevBuf<cplx> V, w, h_dev, dot_scratch, ycoef;
+  DevBuf<double> red_d;
+  DevBuf<cplx> red_c;
+  // instrumentation
+  double tim[16] = {0};
+  long launches = 0;
+  int matvec_variant = 0;
+  bool keep_matrices = true;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm0 = nullptr, evm1 = nullptr;
+
+  int N(int h) const { return 2 * hs[h - 1].n * nobj; }
+  int Mloc(int h) const { return 2 * hs[h - 1].n * count; }
+};
+
+namespace ob {
+
+static std::string g_create_error;
+
+static void check_harmonic(int harmonic) {
+  if(harmonic != 1 && harmonic != 2)
+    throw Error("harmonic must be 1 (FF) or 2 (SH)");
+}
+static void need(bool cond, const char *msg) {
+  if(!cond)
+    throw Error(msg);
+}
+
+static VtacTableSet &tables_for(ob_ctx *c, int nMax) {
+  for(int i = 0; i < 2; ++i)
+    if(c->tabs[i].nMax == nMax)
+      return c->tabs[i];
+  for(int i = 0; i < 2; ++i)
+    if(c->tabs[i].nMax < 0) {
+      c->tabs[i].build(nMax);
+      return c->tabs[i];
+    }
+  c->tabs[1].build(nMax);
+  return c->tabs[1];
+}
+
+static void ensure_factors(ob_ctx *c) {
+  if(c->fac_valid)
+    return;
+  need(c->have_freq, "ob_set_frequency has not been called");
+  MieInputs in;
+  in.nobj = c->nobj;
+  in.nMax = c->nMax;
+  in.nMaxS = c->nMaxS;
+  in.omega = c->omega;
+  in.eps_b = c->eps_b;
+  in.mu_b = c->mu_b;
+  in.radius = c->radius.p;
+  in.eps = c->mat[0].p;
+  in.mu = c->mat[1].p;
+  in.eps_SH = c->mat[2].p;
+  in.mu_SH = c->mat[3].p;
+  cplx *out[7];
+  for(int f = 0; f < 7; ++f) {
+    int nm = (f == 0 || f == 4) ? c->nMax : c->nMaxS;
+    c->fac[f].alloc((size_t)c->nobj * 2 * flat_max(nm));
+    out[f] = c->fac[f].p;
+  }
+  launch_mie(in, out, c->st);
+  c->launches += 1;
+  c->fac_valid = true;
+}
+
+// all ranks hold `vec` (full length); each rank produced its own slice [first*blk, (first+count)*blk)
+static void allgather_slices(ob_ctx *c, cplx *vec, int blk) {
+  if(c->world == 1)
+    return;
+  need(c->comm != nullptr, "world > 1 but ob_comm_init has not been called");
+  if(c->nobj % c->world == 0) {
+    size_t cnt = (size_t)c->count * blk * 2; // doubles
+    OB_NCCL(g_nccl.AllGather((const void *)(vec + (size_t)c->first * blk), (void *)vec, cnt, ncclDouble, c->comm,
+                             c->st));
+  } else {
+    OB_NCCL(g_nccl.GroupStart());
+    for(int r = 0; r < c->world; ++r) {
+      int f, n;
+      partition(c->nobj, c->world, r, f, n);
+      cplx *ptr = vec + (size_t)f * blk;
+      OB_NCCL(g_nccl.Broadcast((const void *)ptr, (void *)ptr, (size_t)n * blk * 2, ncclDouble, r, c->comm, c->st));
+    }
+    OB_NCCL(g_nccl.GroupEnd());
+  }
+}
+
+static void assemble(ob_ctx *c, int harmonic) {
+  check_harmonic(harmonic);
+  need(c->nobj > 0, "ob_set_cluster has not been called");
+  ensure_factors(c);
+  HarmonicState &H = c->hs[harmonic - 1];
+  const size_t M = (size_t)c->Mloc(harmonic), N = (size_t)c->N(harmonic);
+  H.S.alloc(M * N);
+  H.k = harmonic == 1 ? c->waveK : cscale(c->waveK, 2.0);
+  VtacTableSet &ts = tables_for(c, H.nMax);
+  launch_assemble(ts, c->xyz.p, c->fac[harmonic == 1 ? 0 : 1].p, H.k, c->nobj, c->first, c->count, H.S.p, M, c->st);
+  c->launches += 1;
+  if(H.plan.M != (int)M || H.plan.N != (int)N || H.plan.variant != c->matvec_variant)
+    matvec_plan(H.plan, (int)M, (int)N, M, c->sm_count, c->matvec_variant);
+  H.assembled = true;
+}
+
+// y (full length, replicated) = S x
+static void matvec(ob_ctx *c, int harmonic, const cplx *x, cplx *y) {
+  HarmonicState &H = c->hs[harmonic - 1];
+  need(H.assembled, "matrix not assembled (call ob_assemble)");
+  cudaEventRecord(c->evm0, c->st);
+  launch_matvec(H.plan, H.S.p, x, y + (size_t)c->first * 2 * H.n, c->st);
+  cudaEventRecord(c->evm1, c->st);
+  c->launches += matvec_launches_per_apply(H.plan);
+  allgather_slices(c, y, 2 * H.n);
+  // timing of the matvec alone (device events); syncing here is harmless: the driver syncs per iteration anyway
+  cudaEventSynchronize(c->evm1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, c->evm0, c->evm1);
+  c->tim[7] += ms;
+  c->tim[8] += 1;
+}
+
+static void ensure_gmres_ws(ob_ctx *c, int N, int basis) {
+  c->V.alloc((size_t)(basis + 1) * N);
+  c->w.alloc(N);
+  c->h_dev.alloc(basis + 4);
+  c->ycoef.alloc(basis + 4);
+  c->dot_scratch.alloc(vec_scratch_elems(N, basis + 2));
+}
+
+static double dev_norm(ob_ctx *c, const cplx *v, int N) {
+  launch_multi_dot(v, 0, 1, v, N, c->h_dev.p, c->dot_scratch.p, c->st);
+  c->launches += 2;
+  cplx r;
+  OB_CUDA(cudaMemcpyAsync(&r, c->h_dev.p, sizeof(cplx), cudaMemcpyDeviceToHost, c->st));
+  OB_CUDA(cudaStreamSynchronize(c->st));
+  return std::sqrt(r.x);
+}
+
+struct GmresOut {
+  int iters = 0;
+  double relres = 0;
+  bool converged = false;
+};
+
+// Gmres_Zcomp (srcAna/PreconditionedMatrix.cpp:892-985) with the dense device operator.
+static GmresOut gmres_zcomp(ob_ctx *c, int harmonic, const cplx *Y, cplx *x, double tol, int maxit, int no_rest) {
+  const int N = c->N(harmonic);
+  ensure_gmres_ws(c, N, maxit);
+  cplx *V = c->V.p, *w = c->w.p;
+  OB_CUDA(cudaMemsetAsync(x, 0, (size_t)N * sizeof(cplx), c->st));
+  const double abs_y = dev_norm(c, Y, N);
+  GmresOut out;
+  double err_n = 1.0;
+  bool x_zero = true;
+  std::vector<hcd> hcol, cs, sn, gi, ym;
+  std::vector<std::vector<hcd>> Rcols;
+  for(int rest = 1; rest <= no_rest; ++rest) {
+    if(err_n <= tol)
+      break;
+    if(x_zero) { // S * 0 = 0: res = Y
+      OB_CUDA(cudaMemcpyAsync(w, Y, (size_t)N * sizeof(cplx), cudaMemcpyDeviceToDevice, c->st));
+    } else {
+      matvec(c, harmonic, x, c->tmpA.p);
+      launch_axpby(mk(1, 0), Y, mk(-1, 0), c->tmpA.p, w, N, c->st);
+      c->launches += 1;
+    }
+    const double beta = dev_norm(c, w, N);
+    launch_scale_to(w, 1.0 / beta, V, N, c->st);
+    c->launches += 1;
+    cs.clear();
+    sn.clear();
+    Rcols.clear();
+    gi.assign(1, hcd(beta, 0));
+    int n = 0;
+    err_n = 1.0;
+    while(n < maxit && err_n > tol) {
+      matvec(c, harmonic, V + (size_t)n * N, w);
+      // modified Gram-Schmidt (:939-943): h_t = v_t^H w ; w -= h_t v_t, sequentially
+      for(int t = 0; t <= n; ++t) {
+        launch_multi_dot(V + (size_t)t * N, 0, 1, w, N, c->h_dev.p + t, c->dot_scratch.p, c->st);
+        launch_multi_axpy(V + (size_t)t * N, 0, 1, c->h_dev.p + t, w, N, c->st);
+        c->launches += 3;
+      }
+      launch_multi_dot(w, 0, 1, w, N, c->h_dev.p + n + 1, c->dot_scratch.p, c->st);
+      c->launches += 2;
+      hcol.assign(n + 2, hcd(0, 0));
+      OB_CUDA(cudaMemcpyAsync(hcol.data(), c->h_dev.p, (size_t)(n + 2) * sizeof(cplx), cudaMemcpyDeviceToHost, c->st));
+      OB_CUDA(cudaStreamSynchronize(c->st));
+      const double hn = std::sqrt(hcol[n + 1].real());
+      hcol[n + 1] = hn;
+      launch_scale_to(w, 1.0 / hn, V + (size_t)(n + 1) * N, N, c->st);
+      c->launches += 1;
+      // Givens exactly as det_approx (:1087-1133): W = [[conj(c), conj(-s)], [s, c]]
+      for(int i = 0; i < n; ++i) {
+        hcd a = hcol[i], b = hcol[i + 1];
+        hcol[i] = std::conj(cs[i]) * a + std::conj(-sn[i]) * b;
+        hcol[i + 1] = sn[i] * a + cs[i] * b;
+      }
+      hcd cc, ss, temp;
+      if(std::abs(hcol[n + 1]) > std::abs(hcol[n])) {
+        temp = hcol[n] / hcol[n + 1];
+        ss = 1.0 / std::sqrt(1.0 + std::pow(std::abs(temp), 2));
+        cc = -temp * ss;
+      } else {
+        temp = hcol[n + 1] / hcol[n];
+        cc = 1.0 / std::sqrt(1.0 + std::pow(std::abs(temp), 2));
+        ss = -temp * cc;
+      }
+      cs.push_back(cc);
+      sn.push_back(ss);
+      {
+        hcd a = hcol[n], b = hcol[n + 1];
+        hcol[n] = std::conj(cc) * a + std::conj(-ss) * b;
+        hcol[n + 1] = ss * a + cc * b;
+      }
+      gi.push_back(hcd(0, 0));
+      {
+        hcd a = gi[n], b = gi[n + 1];
+        gi[n] = std::conj(cc) * a + std::conj(-ss) * b;
+        gi[n + 1] = ss * a + cc * b;
+      }
+      Rcols.push_back(hcol);
+      err_n = std::abs(gi[n + 1]) / abs_y;
+      ++n;
+      ++out.iters;
+    }
+    ym.assign(n, hcd(0, 0));
+    for(int i = n - 1; i >= 0; --i) {
+      hcd s = gi[i];
+      for(int j = i + 1; j < n; ++j)
+        s -= Rcols[j][i] * ym[j];
+      ym[i] = s / Rcols[i][i];
+    }
+    if(n > 0) {
+      OB_CUDA(cudaMemcpyAsync(c->ycoef.p, ym.data(), (size_t)n * sizeof(cplx), cudaMemcpyHostToDevice, c->st));
+      launch_combine(V, N, n, c->ycoef.p, x, N, c->st);
+      c->launches += 1;
+      OB_CUDA(cudaStreamSynchronize(c->st)); // ym is reused
+      x_zero = false;
+    }
+  }
+  out.relres = err_n;
+  out.converged = err_n <= tol;
+  return out;
+}
+
+// Belos "GMRES" restated (see include/optimet_b200.h): x0 = b, DGKS, implicit residual / ||r0||.
+static GmresOut gmres_belos(ob_ctx *c, int harmonic, const cplx *b, cplx *x, double tol, int max_iters, int num_blocks,
+                            int max_restarts) {
+  const int N = c->N(harmonic);
+  ensure_gmres_ws(c, N, num_blocks);
+  cplx *V = c->V.p, *w = c->w.p;
+  OB_CUDA(cudaMemcpyAsync(x, b, (size_t)N * sizeof(cplx), cudaMemcpyDeviceToDevice, c->st));
+  GmresOut out;
+  double r0norm = -1, rel = 1;
+  std::vector<hcd> h, hh, cs, sn, g, ym;
+  std::vector<std::vector<hcd>> Rcols;
+  for(int cycle = 0; cycle <= max_restarts && !out.converged && out.iters < max_iters; ++cycle) {
+    matvec(c, harmonic, x, c->tmpA.p);
+    launch_axpby(mk(1, 0), b, mk(-1, 0), c->tmpA.p, w, N, c->st);
+    c->launches += 1;
+    const double beta = dev_norm(c, w, N);
+    if(r0norm < 0)
+      r0norm = beta;
+    if(r0norm == 0.0 || beta / r0norm <= tol) {
+      out.converged = true;
+      rel = r0norm == 0.0 ? 0.0 : beta / r0norm;
+      break;
+    }
+    launch_scale_to(w, 1.0 / beta, V, N, c->st);
+    c->launches += 1;
+    cs.clear();
+    sn.clear();
+    Rcols.clear();
+    g.assign(1, hcd(beta, 0));
+    int j = 0;
+    while(j < num_blocks && out.iters < max_iters) {
+      matvec(c, harmonic, V + (size_t)j * N, w);
+      // pass 1: classical Gram-Schmidt, all dots at once (+ ||w||^2 as the last "dot")
+      launch_multi_dot(V, N, j + 1, w, N, c->h_dev.p, c->dot_scratch.p, c->st);
+      launch_multi_dot(w, 0, 1, w, N, c->h_dev.p + j + 1, c->dot_scratch.p, c->st);
+      launch_multi_axpy(V, N, j + 1, c->h_dev.p, w, N, c->st);
+      launch_multi_dot(w, 0, 1, w, N, c->h_dev.p + j + 2, c->dot_scratch.p, c->st);
+      c->launches += 7;
+      h.assign(j + 3, hcd(0, 0));
+      OB_CUDA(cudaMemcpyAsync(h.data(), c->h_dev.p, (size_t)(j + 3) * sizeof(cplx), cudaMemcpyDeviceToHost, c->st));
+      OB_CUDA(cudaStreamSynchronize(c->st));
+      const double norm_before = std::sqrt(h[j + 1].real());
+      double norm_after = std::sqrt(h[j + 2].real());
+      h.resize(j + 2);
+      if(norm_after < 0.70710678118654752440 * norm_before) { // DGKS second pass
+        launch_multi_dot(V, N, j + 1, w, N, c->h_dev.p, c->dot_scratch.p, c->st);
+        launch_multi_axpy(V, N, j + 1, c->h_dev.p, w, N, c->st);
+        launch_multi_dot(w, 0, 1, w, N, c->h_dev.p + j + 1, c->dot_scratch.p, c->st);
+        c->launches += 5;
+        hh.assign(j + 2, hcd(0, 0));
+        OB_CUDA(cudaMemcpyAsync(hh.data(), c->h_dev.p, (size_t)(j + 2) * sizeof(cplx), cudaMemcpyDeviceToHost, c->st));
+        OB_CUDA(cudaStreamSynchronize(c->st));
+        for(int t = 0; t <= j; ++t)
+          h[t] += hh[t];
+        norm_after = std::sqrt(hh[j + 1].real());
+      }
+      h[j + 1] = norm_after;
+      launch_scale_to(w, 1.0 / norm_after, V + (size_t)(j + 1) * N, N, c->st);
+      c->launches += 1;
+      for(int i = 0; i < j; ++i) {
+        hcd a = h[i], bb = h[i + 1];
+        h[i] = cs[i] * a + sn[i] * bb;
+        h[i + 1] = -std::conj(sn[i]) * a + cs[i] * bb;
+      }
+      hcd f = h[j], gg = h[j + 1], cc, ss;
+      if(gg == hcd(0, 0)) {
+        cc = 1;
+        ss = 0;
+      } else if(f == hcd(0, 0)) {
+        cc = 0;
+        ss = std::conj(gg) / std::abs(gg);
+      } else {
+        double d = std::sqrt(std::norm(f) + std::norm(gg));
+        cc = std::abs(f) / d;
+        ss = (f / std::abs(f)) * std::conj(gg) / d;
+      }
+      cs.push_back(cc);
+      sn.push_back(ss);
+      h[j] = cc * f + ss * gg;
+      h[j + 1] = 0;
+      g.push_back(hcd(0, 0));
+      hcd ga = g[j];
+      g[j] = cc * ga;
+      g[j + 1] = -std::conj(ss) * ga;
+      Rcols.push_back(h);
+      ++j;
+      ++out.iters;
+      rel = std::abs(g[j]) / r0norm;
+      if(rel <= tol) {
+        out.converged = true;
+        break;
+      }
+    }
+    ym.assign(j, hcd(0, 0));
+    for(int i = j - 1; i >= 0; --i) {
+      hcd s = g[i];
+      for(int k = i + 1; k < j; ++k)
+        s -= Rcols[k][i] * ym[k];
+      ym[i] = s / Rcols[i][i];
+    }
+    if(j > 0) {
+      OB_CUDA(cudaMemcpyAsync(c->ycoef.p, ym.data(), (size_t)j * sizeof(cplx), cudaMemcpyHostToDevice, c->st));
+      launch_combine(V, N, j, c->ycoef.p, x, N, c->st);
+      c->launches += 1;
+      OB_CUDA(cudaStreamSynchronize(c->st));
+    }
+  }
+  out.relres = rel;
+  return out;
+}
+
+static GmresOut solve_dev(ob_ctx *c, int harmonic, const cplx *rhs, cplx *x, const ob_gmres_opts *o) {
+  need(o != nullptr, "ob_gmres_opts is NULL");
+  c->tmpA.alloc(c->N(harmonic));
+  GmresOut r;
+  if(o->flavour == OB_GMRES_ZCOMP)
+    r = gmres_zcomp(c, harmonic, rhs, x, o->tol, o->max_iters, o->max_restarts);
+  else if(o->flavour == OB_GMRES_BELOS) {
+    r = gmres_belos(c, harmonic, rhs, x, o->tol, o->max_iters, o->restart, o->max_restarts);
+    if(!r.converged) // srcAna/MatrixBelosSolver.cpp:60-61
+      throw Error("Error encountered while solving the linear system");
+  } else
+    throw Error("unknown GMRES flavour");
+  return r;
+}
+
+static void source_ff(ob_ctx *c) {
+  need(c->have_inc, "ob_set_incident has not been called");
+  ensure_factors(c);
+  const int N = c->N(1), blk = 2 * c->hs[0].n;
+  c->Q.alloc(N);
+  VtacTableSet &ts = tables_for(c, c->nMax);
+  launch_translate_apply(ts, c->xyz.p, c->waveK, c->first, c->count, c->ainc.p, 0, c->fac[0].p,
+                         c->Q.p + (size_t)c->first * blk, c->st);
+  c->launches += 1;
+  allgather_slices(c, c->Q.p, blk);
+}
+
+static ShInputs sh_inputs(ob_ctx *c) {
+  ShInputs in;
+  in.nobj = c->nobj;
+  in.nMax = c->nMax;
+  in.nMaxS = c->nMaxS;
+  in.omega = c->omega;
+  in.eps_b = c->eps_b;
+  in.mu_b = c->mu_b;
+  in.radius = c->radius.p;
+  in.eps = c->mat[0].p;
+  in.mu = c->mat[1].p;
+  in.eps_SH = c->mat[2].p;
+  in.mu_SH = c->mat[3].p;
+  in.ksippp = c->mat[4].p;
+  in.ksiparppar = c->mat[5].p;
+  in.gamma = c->mat[6].p;
+  for(int t = 0; t < 9; ++t)
+    in.tab[t] = c->cg[t].p;
+  return in;
+}
+
+static void ensure_cg(ob_ctx *c) {
+  if(c->cg_nmax == c->nMax * 1000 + c->nMaxS)
+    return;
+  const size_t sz = (size_t)flat_max(c->nMaxS) * flat_max(c->nMax) * flat_max(c->nMax);
+  double *T[9];
+  for(int t = 0; t < 9; ++t) {
+    c->cg[t].alloc(sz);
+    T[t] = c->cg[t].p;
+  }
+  launch_cg_tables(c->nMax, c->nMaxS, T, c->st);
+  c->launches += 2;
+  c->cg_nmax = c->nMax * 1000 + c->nMaxS;
+}
+
+// K, K1ana from the conjugated FF internal coefficients (device, full length)
+static void source_sh(ob_ctx *c, const cplx *Xint_conj) {
+  ensure_factors(c);
+  ensure_cg(c);
+  const int N = c->N(2), blk = 2 * c->hs[1].n;
+  c->Ksrc.alloc(N);
+  c->K1ana.alloc(N);
+  ShInputs in = sh_inputs(c);
+  launch_sh_source(in, c->first, c->count, Xint_conj, c->fac[2].p, c->fac[3].p, c->fac[6].p, c->Ksrc.p, c->K1ana.p,
+                   c->st);
+  c->launches += 1;
+  allgather_slices(c, c->Ksrc.p, blk);
+  allgather_slices(c, c->K1ana.p, blk);
+}
+
+// Result.cpp:557-794; device vectors; partial sums over local particles, gathered on the host side
+static void cross_sections(ob_ctx *c, const cplx *Xsca, const cplx *Xint, const cplx *XscaSH, const cplx *XintSH,
+                           bool do_sh, double cs[5]) {
+  const int n = c->hs[0].n, blk = 2 * n;
+  std::vector<double> part; // per particle (global index), summed in particle order as the reference does
+  c->red_d.alloc(3 * (size_t)c->nobj + 16);
+  c->red_c.alloc((size_t)c->nobj + 16);
+  VtacTableSet &ts = tables_for(c, c->nMax);
+  // extinction: Q_local = getIncLocal(R_j)  (Result.cpp:564-571)
+  c->tmpB.alloc(std::max(c->N(1), c->N(2)));
+  launch_translate_apply(ts, c->xyz.p, c->waveK, c->first, c->count, c->ainc.p, 0, nullptr,
+                         c->tmpB.p + (size_t)c->first * blk, c->st);
+  launch_sca_sum(ts, c->xyz.p, c->waveK, c->first, c->count, Xsca, c->red_d.p + c->first, c->st);
+  c->launches += 2;
+  std::vector<hcd> qloc((size_t)c->count * blk), xs((size_t)c->count * blk);
+  std::vector<double> sca(c->nobj, 0.0), scaSH(c->nobj, 0.0), ext(c->nobj, 0.0), absSH(c->nobj, 0.0);
+  OB_CUDA(cudaMemcpyAsync(qloc.data(), c->tmpB.p + (size_t)c->first * blk, qloc.size() * sizeof(cplx),
+                          cudaMemcpyDeviceToHost, c->st));
+  OB_CUDA(cudaMemcpyAsync(xs.data(), Xsca + (size_t)c->first * blk, xs.size() * sizeof(cplx), cudaMemcpyDeviceToHost,
+                          c->st));
+  OB_CUDA(cudaMemcpyAsync(sca.data() + c->first, c->red_d.p + c->first, c->count * sizeof(double),
+                          cudaMemcpyDeviceToHost, c->st));
+  if(do_sh) {
+    VtacTableSet &tsS = tables_for(c, c->nMaxS);
+    launch_sca_sum(tsS, c->xyz.p, cscale(c->waveK, 2.0), c->first, c->count, XscaSH, c->red_d.p + c->nobj + c->first,
+                   c->st);
+    ensure_cg(c);
+    ShInputs in = sh_inputs(c);
+    launch_abs_sh(in, c->first, c->count, Xint, XintSH, c->red_c.p + c->first, c->st);
+    c->launches += 2;
+    OB_CUDA(cudaMemcpyAsync(scaSH.data() + c->first, c->red_d.p + c->nobj + c->first, c->count * sizeof(double),
+                            cudaMemcpyDeviceToHost, c->st));
+  }
+  std::vector<hcd> acs(c->nobj, hcd(0, 0));
+  if(do_sh)
+    OB_CUDA(cudaMemcpyAsync(acs.data() + c->first, c->red_c.p + c->first, c->count * sizeof(cplx),
+                            cudaMemcpyDeviceToHost, c->st));
+  OB_CUDA(cudaStreamSynchronize(c->st));
+  for(int jl = 0; jl < c->count; ++jl) {
+    double e = 0;
+    const hcd *q = &qloc[(size_t)jl * blk], *x = &xs[(size_t)jl * blk];
+    for(int p = 0; p < n; ++p)
+      e += std::real(std::conj(q[p]) * x[p] + std::conj(q[p + n]) * x[p + n]);
+    ext[c->first + jl] = e;
+    if(do_sh) {
+      const double mu0 = 4.0 * 3.14159265358979323846 * 1e-7;
+      const double eps0 = 1.0 / (mu0 * 299792458.0 * 299792458.0);
+      hcd eta = std::sqrt(hcd(c->mu_b.x, c->mu_b.y) / hcd(c->eps_b.x, c->eps_b.y));
+      hcd sigma = -hcd(0.0, 1.0) * eps0 * 2.0 * c->omega * (c->h_epsr_SH[c->first + jl] - 1.0); // Result.cpp:784
+      absSH[c->first + jl] = std::real((2.0 * eta) * 0.5 * sigma * acs[c->first + jl]);          // :788
+    }
+  }
+  // the four per-particle partial arrays are summed over ranks on the host by the caller (world > 1:
+  // each rank returns the partial sums of its own particles; bench/host adaptor adds them).
+  double Cext = 0, Csca = 0, CscaSH = 0, CabsSH = 0;
+  for(int j = 0; j < c->nobj; ++j) {
+    Cext += ext[j];
+    Csca += sca[j];
+    CscaSH += scaSH[j];
+    CabsSH = CabsSH + absSH[j];
+  }
+  const double k2 = c->waveK.x * c->waveK.x;
+  const double mu0 = 4.0 * 3.14159265358979323846 * 1e-7;
+  const double eps0 = 1.0 / (mu0 * 299792458.0 * 299792458.0);
+  cs[0] = (-1. / k2) * Cext;
+  cs[1] = (1. / k2) * Csca;
+  cs[2] = cs[0] - cs[1];
+  const double ArbCf = (c->eps_b.x / eps0) * (c->mu_b.x / mu0);
+  cs[3] = do_sh ? (1.0 / (4.0 * ArbCf)) * CscaSH : 0.0;
+  cs[4] = do_sh ? CabsSH : 0.0;
+}
+
+static void upload(ob_ctx *c, DevBuf<cplx> &buf, const double *host, size_t n) {
+  buf.alloc(n);
+  OB_CUDA(cudaMemcpyAsync(buf.p, host, n * sizeof(cplx), cudaMemcpyHostToDevice, c->st));
+}
+static void download(ob_ctx *c, const cplx *dev, double *host, size_t n) {
+  if(!host)
+    return;
+  OB_CUDA(cudaMemcpyAsync(host, dev, n * sizeof(cplx), cudaMemcpyDeviceToHost, c->st));
+  OB_CUDA(cudaStreamSynchronize(c->st));
+}
+
+struct PhaseTimer {
+  ob_ctx *c;
+  int slot;
+  PhaseTimer(ob_ctx *c_, int s) : c(c_), slot(s) { cudaEventRecord(c->ev0, c->st); }
+  void stop() {
+    cudaEventRecord(c->ev1, c->st);
+    cudaEventSynchronize(c->ev1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    c->tim[slot] += ms;
+  }
+};
+
+} // namespace ob
+
+#define OB_BEGIN                                                                                                       \
+  if(!ctx)                                                                                                             \
+    return 1;                                                                                                          \
+  try {                                                                                                                \
+    OB_CUDA(cudaSetDevice(ctx->device));
+#define OB_END                                                                                                         \
+  }                                                                                                                    \
+  catch(std::exception & e) {                                                                                          \
+    ctx->err = e.what();                                                                                               \
+    return 1;                                                                                                          \
+  }                                                                                                                    \
+  return 0;
+
+extern "C" {
+
+int ob_create(int device, ob_ctx **out) {
+  try {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if(e != cudaSuccess || ndev == 0)
+      throw Error("no CUDA device available: the B200 path has no CPU fallback");
+    if(device < 0 || device >= ndev)
+      throw Error("invalid device ordinal");
+    OB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    OB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if(prop.major < 10)
+      throw Error("this library is built for sm_100a (B200) only");
+    ob_ctx *c = new ob_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    OB_CUDA(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    OB_CUDA(cudaEventCreate(&c->ev0));
+    OB_CUDA(cudaEventCreate(&c->ev1));
+    OB_CUDA(cudaEventCreate(&c->evm0));
+    OB_CUDA(cudaEventCreate(&c->evm1));
+    *out = c;
+  } catch(std::exception &e) {
+    g_create_error = e.what();
+    *out = nullptr;
+    return 1;
+  }
+  return 0;
+}
+
+void ob_destroy(ob_ctx *ctx) {
+  if(!ctx)
+    return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->st);
+  if(ctx->comm && g_nccl.CommDestroy)
+    g_nccl.CommDestroy(ctx->comm);
+  for(int i = 0; i < 2; ++i) {
+    ctx->tabs[i].release();
+    matvec_plan_release(ctx->hs[i].plan);
+  }
+  cudaEventDestroy(ctx->ev0);
+  cudaEventDestroy(ctx->ev1);
+  cudaEventDestroy(ctx->evm0);
+  cudaEventDestroy(ctx->evm1);
+  cudaStream_t st = ctx->st;
+  delete ctx;
+  cudaStreamDestroy(st);
+}
+
+const char *ob_last_error(ob_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int ob_device_info(ob_ctx *ctx, int *sm_count, size_t *free_bytes, size_t *total_bytes) {
+  OB_BEGIN
+  *sm_count = ctx->sm_count;
+  OB_CUDA(cudaMemGetInfo(free_bytes, total_bytes));
+  OB_END
+}
+
+int ob_partition(int nobj, int world, int rank, int *first, int *count) {
+  if(nobj < 0 || world < 1 || rank < 0 || rank >= world)
+    return 1;
+  partition(nobj, world, rank, *first, *count);
+  return 0;
+}
+
+int ob_comm_unique_id(char out[128]) {
+  if(!g_nccl.load())
+    return 1;
+  ncclUniqueId id;
+  if(g_nccl.GetUniqueId(&id) != ncclSuccess)
+    return 1;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  memcpy(out, &id, 128);
+  return 0;
+}
+
+int ob_comm_init(ob_ctx *ctx, const char uid[128], int rank, int world) {
+  OB_BEGIN
+  need(world >= 1 && rank >= 0 && rank < world, "bad rank/world");
+  ctx->rank = rank;
+  ctx->world = world;
+  if(world > 1) {
+    need(g_nccl.load(), "libnccl.so.2 not found");
+    ncclUniqueId id;
+    memcpy(&id, uid, 128);
+    OB_NCCL(g_nccl.CommInitRank(&ctx->comm, world, id, rank));
+  }
+  if(ctx->nobj > 0)
+    partition(ctx->nobj, world, rank, ctx->first, ctx->count);
+  OB_END
+}
+
+int ob_set_cluster(ob_ctx *ctx, int nobj, const double *xyz_m, const double *radius_m, int nMax, int nMaxS) {
+  OB_BEGIN
+  need(nobj > 0, "No scatterers defined in input");
+  need(nMax >= 1 && nMax <= OB_MAX_NMAX && nMaxS >= 1 && nMaxS <= OB_MAX_NMAX,
+       "nMax out of range (1..13 supported by the shared-memory VTAC kernel)");
+  // overlap check of Geometry::pushObject (srcAna/Geometry.cpp:39-52), O(N^2) on the host only for small clusters
+  if(nobj <= 4096)
+    for(int i = 0; i < nobj; ++i)
+      for(int j = 0; j < i; ++j) {
+        double dx = xyz_m[3 * i] - xyz_m[3 * j], dy = xyz_m[3 * i + 1] - xyz_m[3 * j + 1],
+               dz = xyz_m[3 * i + 2] - xyz_m[3 * j + 2];
+        if(std::sqrt(dx * dx + dy * dy + dz * dz) <= radius_m[i] + radius_m[j])
+          throw Error("The sphere at index " + std::to_string(i) + " overlaps with the one at index " +
+                      std::to_string(j));
+      }
+  ctx->nobj = nobj;
+  ctx->nMax = nMax;
+  ctx->nMaxS = nMaxS;
+  ctx->hs[0].nMax = nMax;
+  ctx->hs[0].n = flat_max(nMax);
+  ctx->hs[1].nMax = nMaxS;
+  ctx->hs[1].n = flat_max(nMaxS);
+  partition(nobj, ctx->world, ctx->rank, ctx->first, ctx->count);
+  ctx->xyz.alloc(3 * (size_t)nobj);
+  ctx->radius.alloc(nobj);
+  OB_CUDA(cudaMemcpyAsync(ctx->xyz.p, xyz_m, 3 * (size_t)nobj * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
+  OB_CUDA(cudaMemcpyAsync(ctx->radius.p, radius_m, (size_t)nobj * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
+  OB_CUDA(cudaStreamSynchronize(ctx->st));
+  ctx->fac_valid = false;
+  ctx->hs[0].assembled = ctx->hs[1].assembled = false;
+  ctx->have_inc = false;
+  OB_END
+}
+
+int ob_set_frequency(ob_ctx *ctx, double omega, const double waveK[2], const double eps_b[2], const double mu_b[2],
+                     const double *eps, const double *mu, const double *eps_SH, const double *mu_SH,
+                     const double *ksippp, const double *ksiparppar, const double *gamma) {
+  OB_BEGIN
+  need(ctx->nobj > 0, "ob_set_cluster has not been called");
+  ctx->omega = omega;
+  ctx->waveK = mk(waveK[0], waveK[1]);
+  ctx->eps_b = mk(eps_b[0], eps_b[1]);
+  ctx->mu_b = mk(mu_b[0], mu_b[1]);
+  const double *src[7] = {eps, mu, eps_SH, mu_SH, ksippp, ksiparppar, gamma};
+  for(int i = 0; i < 7; ++i) {
+    need(src[i] != nullptr, "ob_set_frequency: NULL material array");
+    upload(ctx, ctx->mat[i], src[i], ctx->nobj);
+  }
+  const double mu0 = 4.0 * 3.14159265358979323846 * 1e-7;
+  const double eps0 = 1.0 / (mu0 * 299792458.0 * 299792458.0);
+  ctx->h_epsr_SH.resize(ctx->nobj);
+  for(int j = 0; j < ctx->nobj; ++j)
+    ctx->h_epsr_SH[j] = hcd(eps_SH[2 * j], eps_SH[2 * j + 1]) / eps0;
+  OB_CUDA(cudaStreamSynchronize(ctx->st));
+  ctx->have_freq = true;
+  ctx->fac_valid = false;
+  ctx->hs[0].assembled = ctx->hs[1].assembled = false;
+  OB_END
+}
+
+int ob_set_incident(ob_ctx *ctx, const double *a_origin, const double *b_origin) {
+  OB_BEGIN
+  need(ctx->nobj > 0, "ob_set_cluster has not been called");
+  const int n = ctx->hs[0].n;
+  ctx->ainc.alloc(2 * n);
+  OB_CUDA(cudaMemcpyAsync(ctx->ainc.p, a_origin, n * sizeof(cplx), cudaMemcpyHostToDevice, ctx->st));
+  OB_CUDA(cudaMemcpyAsync(ctx->ainc.p + n, b_origin, n * sizeof(cplx), cudaMemcpyHostToDevice, ctx->st));
+  OB_CUDA(cudaStreamSynchronize(ctx->st));
+  ctx->have_inc = true;
+  OB_END
+}
+
+int ob_vtac(ob_ctx *ctx, const double relR_sph[3], const double k[2], int regular_flag, int nMax, double *A,
+            double *B) {
+  OB_BEGIN
+  need(nMax >= 1 && nMax <= OB_MAX_NMAX, "nMax out of range");
+  VtacTableSet &ts = tables_for(ctx, nMax);
+  const size_t n = flat_max(nMax);
+  DevBuf<cplx> dA, dB;
+  dA.alloc(n * n);
+  dB.alloc(n * n);
+  // Coupling.cpp:86: the ctor flag is inverted when handed to the TA coefficients
+  launch_vtac_single(ts, relR_sph[0], relR_sph[1], relR_sph[2], mk(k[0], k[1]), regular_flag ? 0 : 1, dA.p, dB.p,
+                     ctx->st);
+  ctx->launches += 1;
+  download(ctx, dA.p, A, n * n);
+  download(ctx, dB.p, B, n * n);
+  OB_END
+}
+
+int ob_particle_factors(ob_ctx *ctx, int which, double *out) {
+  OB_BEGIN
+  need(which >= 0 && which < 7, "which must be 0..6");
+  ensure_factors(ctx);
+  download(ctx, ctx->fac[which].p, out, ctx->fac[which].n);
+  OB_END
+}
+
+int ob_inc_local(ob_ctx *ctx, double *out) {
+  OB_BEGIN
+  need(ctx->have_inc && ctx->have_freq, "incident field / frequency not set");
+  const int N = ctx->N(1), blk = 2 * ctx->hs[0].n;
+  ctx->tmpB.alloc(std::max(ctx->N(1), ctx->N(2)));
+  VtacTableSet &ts = tables_for(ctx, ctx->nMax);
+  launch_translate_apply(ts, ctx->xyz.p, ctx->waveK, ctx->first, ctx->count, ctx->ainc.p, 0, nullptr,
+                         ctx->tmpB.p + (size_t)ctx->first * blk, ctx->st);
+  ctx->launches += 1;
+  allgather_slices(ctx, ctx->tmpB.p, blk);
+  download(ctx, ctx->tmpB.p, out, N);
+  OB_END
+}
+
+int ob_assemble(ob_ctx *ctx, int harmonic) {
+  OB_BEGIN
+  assemble(ctx, harmonic);
+  OB_CUDA(cudaStreamSynchronize(ctx->st));
+  OB_END
+}
+
+int ob_release_matrix(ob_ctx *ctx, int harmonic) {
+  OB_BEGIN
+  check_harmonic(harmonic);
+  ctx->hs[harmonic - 1].S.release();
+  ctx->hs[harmonic - 1].assembled = false;
+  OB_END
+}
+
+int ob_fetch_block(ob_ctx *ctx, int harmonic, int i, int j, double *out) {
+  OB_BEGIN
+  check_harmonic(harmonic);
+  HarmonicState &H = ctx->hs[harmonic - 1];
+  need(H.assembled, "matrix not assembled");
+  need(i >= ctx->first && i < ctx->first + ctx->count && j >= 0 && j < ctx->nobj, "block is not local to this rank");
+  const size_t b = 2 * H.n, ld = (size_t)ctx->Mloc(harmonic);
+  const cplx *src = H.S.p + (size_t)j * b * ld + (size_t)(i - ctx->first) * b;
+  OB_CUDA(cudaMemcpy2DAsync(out, b * sizeof(cplx), src, ld * sizeof(cplx), b * sizeof(cplx), b, cudaMemcpyDeviceToHost,
+                            ctx->st));
+  OB_CUDA(cudaStreamSynchronize(ctx->st));
+  OB_END
+}
+
+int ob_fetch_matrix(ob_ctx *ctx, int harmonic, double *out) {
+  OB_BEGIN
+  check_harmonic(harmonic);
+  HarmonicState &H = ctx->hs[harmonic - 1];
+  need(H.assembled, "matrix not assembled");
+  download(ctx, H.S.p, out, (size_t)ctx->Mloc(harmonic) * ctx->N(harmonic));
+  OB_END
+}
+
+int ob_matvec(ob_ctx *ctx, int harmonic, const double *x, double *y) {
+  OB_BEGIN
+  check_harmonic(harmonic);
+  const int N = ctx->N(harmonic);
+  upload(ctx, ctx->tmpA, x, N);
+  ctx->tmpB.alloc(std::max(ctx->N(1), ctx->N(2)));
+  matvec(ctx, harmonic, ctx->tmpA.p, ctx->tmpB.p);
+  download(ctx, ctx->tmpB.p, y, N);
+  OB_END
+}
+
+int ob_source_ff(ob_ctx *ctx, double *Q) {
+  OB_BEGIN
+  source_ff(ctx);
+  download(ctx, ctx->Q.p, Q, ctx->N(1));
+  OB_END
+}
+
+int ob_set_cg_tables(ob_ctx *ctx, const double *const tables[9]) {
+  OB_BEGIN
+  need(ctx->nobj > 0, "ob_set_cluster has not been called");
+  const size_t sz = (size_t)flat_max(ctx->nMaxS) * flat_max(ctx->nMax) * flat_max(ctx->nMax);
+  for(int t = 0; t < 9; ++t) {
+    ctx->cg[t].alloc(sz);
+    OB_CUDA(cudaMemcpyAsync(ctx->cg[t].p, tables[t], sz * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
+  }
+  OB_CUDA(cudaStreamSynchronize(ctx->st));
+  ctx->cg_nmax = ctx->nMax * 1000 + ctx->nMaxS;
+  OB_END
+}
+
+int ob_build_cg_tables(ob_ctx *ctx) {
+  OB_BEGIN
+  need(ctx->nobj > 0, "ob_set_cluster has not been called");
+  ctx->cg_nmax = -1;
+  ensure_cg(ctx);
+  OB_END
+}
+
+int ob_fetch_cg_table(ob_ctx *ctx, int t, double *out) {
+  OB_BEGIN
+  need(t >= 0 && t < 9 && ctx->cg_nmax >= 0, "tables not built");
+  OB_CUDA(cudaMemcpyAsync(out, ctx->cg[t].p, ctx->cg[t].n * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+  OB_CUDA(cudaStreamSynchronize(ctx->st));
+  OB_END
+}
+
+int ob_source_sh(ob_ctx *ctx, const double *Xint_conj, double *K, double *K1ana) {
+  OB_BEGIN
+  upload(ctx, ctx->tmpA, Xint_conj, ctx->N(1));
+  source_sh(ctx, ctx->tmpA.p);
+  download(ctx, ctx->Ksrc.p, K, ctx->N(2));
+  download(ctx, ctx->K1ana.p, K1ana, ctx->N(2));
+  OB_END
+}
+
+int ob_solve(ob_ctx *ctx, int harmonic, const double *rhs, double *x, const ob_gmres_opts *opts, int *iters,
+             double *relres) {
+  OB_BEGIN
+  check_harmonic(harmonic);
+  const int N = ctx->N(harmonic);
+  DevBuf<cplx> &X = harmonic == 1 ? ctx->Xsca : ctx->XscaSH;
+  X.alloc(N);
+  const cplx *b;
+  if(rhs) {
+    upload(ctx, ctx->tmpB, rhs, N);
+    b = ctx->tmpB.p;
+  } else {
+    DevBuf<cplx> &R = harmonic == 1 ? ctx->Q : ctx->Ksrc;
+    need(R.p != nullptr, "no resident source vector for this harmonic");
+    b = R.p;
+  }
+  GmresOut r = solve_dev(ctx, harmonic, b, X.p, opts);
+  if(iters)
+    *iters = r.iters;
+  if(relres)
+    *relres = r.relres;
+  download(ctx, X.p, x, N);
+  OB_END
+}
+
+int ob_unprecondition_ff(ob_ctx *ctx, const double *X_sca, double *X_int) {
+  OB_BEGIN
+  ensure_factors(ctx);
+  const int N = ctx->N(1);
+  upload(ctx, ctx->tmpA, X_sca, N);
+  ctx->Xint.alloc(N);
+  launch_hadamard(ctx->tmpA.p, ctx->fac[4].p, nullptr, ctx->Xint.p, N, 0, ctx->st);
+  ctx->launches += 1;
+  download(ctx, ctx->Xint.p, X_int, N);
+  OB_END
+}
+
+int ob_unprecondition_sh(ob_ctx *ctx, const double *X_sca_SH, const double *K1ana, double *X_int_SH) {
+  OB_BEGIN
+  ensure_factors(ctx);
+  const int N = ctx->N(2);
+  upload(ctx, ctx->tmpA, X_sca_SH, N);
+  upload(ctx, ctx->tmpB, K1ana, N);
+  ctx->XintSH.alloc(N);
+  launch_hadamard(ctx->tmpA.p, ctx->fac[5].p, ctx->tmpB.p, ctx->XintSH.p, N, 0, ctx->st);
+  ctx->launches += 1;
+  download(ctx, ctx->XintSH.p, X_int_SH, N);
+  OB_END
+}
+
+int ob_cross_sections(ob_ctx *ctx, const double *X_sca, const double *X_int, const double *X_sca_SH,
+                      const double *X_int_SH, int do_sh, double cs[5]) {
+  OB_BEGIN
+  need(ctx->have_inc && ctx->have_freq, "incident field / frequency not set");
+  ensure_factors(ctx);
+  upload(ctx, ctx->Xsca, X_sca, ctx->N(1));
+  if(do_sh) {
+    upload(ctx, ctx->Xint, X_int, ctx->N(1));
+    upload(ctx, ctx->XscaSH, X_sca_SH, ctx->N(2));
+    upload(ctx, ctx->XintSH, X_int_SH, ctx->N(2));
+  }
+  cross_sections(ctx, ctx->Xsca.p, ctx->Xint.p, ctx->XscaSH.p, ctx->XintSH.p, do_sh != 0, cs);
+  OB_END
+}
+
+int ob_run(ob_ctx *ctx, const ob_gmres_opts *opts, int do_sh, double *X_sca, double *X_int, double *X_sca_SH,
+           double *X_int_SH, double cs[5], int stats[2]) {
+  OB_BEGIN
+  need(ctx->have_inc && ctx->have_freq, "incident field / frequency not set");
+  for(int i = 0; i < 16; ++i)
+    ctx->tim[i] = 0;
+  ctx->launches = 0;
+  const int N1 = ctx->N(1), N2 = ctx->N(2);
+  int it_ff = 0, it_sh = 0;
+  // ---- update(): Q, S (PreconditionedMatrixSolver.h:82-100) ----
+  {
+    PhaseTimer t(ctx, 0);
+    ctx->fac_valid = false;
+    ensure_factors(ctx);
+    source_ff(ctx);
+    t.stop();
+  }
+  {
+    PhaseTimer t(ctx, 1);
+    assemble(ctx, 1);
+    t.stop();
+  }
+  // ---- solve(): FF ----
+  {
+    ctx->Xsca.alloc(N1);
+    ctx->Xint.alloc(N1);
+    double t0 = ctx->tim[7];
+    PhaseTimer t(ctx, 2);
+    GmresOut r = solve_dev(ctx, 1, ctx->Q.p, ctx->Xsca.p, opts);
+    it_ff = r.iters;
+    launch_hadamard(ctx->Xsca.p, ctx->fac[4].p, nullptr, ctx->Xint.p, N1, 0, ctx->st); // Solver.cpp:57-77
+    ctx->launches += 1;
+    t.stop();
+    (void)t0;
+  }
+  if(do_sh) {
+    if(!ctx->keep_matrices) {
+      ctx->hs[0].S.release();
+      ctx->hs[0].assembled = false;
+    }
+    {
+      PhaseTimer t(ctx, 3);
+      ctx->tmpA.alloc(std::max(N1, N2));
+      // X_int_conj (PreconditionedMatrixSolver.h:66-67): a .* b conjugated
+      launch_hadamard(ctx->Xsca.p, ctx->fac[4].p, nullptr, ctx->tmpA.p, N1, 1, ctx->st);
+      ctx->launches += 1;
+      ctx->tmpB.alloc(std::max(N1, N2));
+      OB_CUDA(cudaMemcpyAsync(ctx->tmpB.p, ctx->tmpA.p, (size_t)N1 * sizeof(cplx), cudaMemcpyDeviceToDevice, ctx->st));
+      source_sh(ctx, ctx->tmpB.p);
+      t.stop();
+    }
+    {
+      PhaseTimer t(ctx, 4);
+      assemble(ctx, 2);
+      t.stop();
+    }
+    {
+      ctx->XscaSH.alloc(N2);
+      ctx->XintSH.alloc(N2);
+      PhaseTimer t(ctx, 5);
+      GmresOut r = solve_dev(ctx, 2, ctx->Ksrc.p, ctx->XscaSH.p, opts);
+      it_sh = r.iters;
+      launch_hadamard(ctx->XscaSH.p, ctx->fac[5].p, ctx->K1ana.p, ctx->XintSH.p, N2, 0, ctx->st); // Solver.cpp:95-116
+      ctx->launches += 1;
+      t.stop();
+    }
+  }
+  {
+    PhaseTimer t(ctx, 6);
+    cross_sections(ctx, ctx->Xsca.p, ctx->Xint.p, ctx->XscaSH.p, ctx->XintSH.p, do_sh != 0, cs);
+    t.stop();
+  }
+  download(ctx, ctx->Xsca.p, X_sca, N1);
+  download(ctx, ctx->Xint.p, X_int, N1);
+  if(do_sh) {
+    download(ctx, ctx->XscaSH.p, X_sca_SH, N2);
+    download(ctx, ctx->XintSH.p, X_int_SH, N2);
+  }
+  if(stats) {
+    stats[0] = it_ff;
+    stats[1] = it_sh;
+  }
+  ctx->tim[9] = (double)ctx->launches;
+  OB_END
+}
+
+int ob_timings(ob_ctx *ctx, double out[16]) {
+  if(!ctx)
+    return 1;
+  for(int i = 0; i < 16; ++i)
+    out[i] = ctx->tim[i];
+  out[9] = (double)ctx->launches;
+  return 0;
+}
+
+int ob_set_option(ob_ctx *ctx, const char *name, double value) {
+  OB_BEGIN
+  std::string n(name ? name : "");
+  if(n == "matvec_variant") {
+    ctx->matvec_variant = (int)value;
+    for(int h = 0; h < 2; ++h)
+      if(ctx->hs[h].assembled)
+        matvec_plan(ctx->hs[h].plan, ctx->hs[h].plan.M, ctx->hs[h].plan.N, ctx->hs[h].plan.ld, ctx->sm_count,
+                    ctx->matvec_variant);
+  } else if(n == "keep_matrices")
+    ctx->keep_matrices = value != 0;
+  else if(n == "reset_timings") {
+    for(int i = 0; i < 16; ++i)
+      ctx->tim[i] = 0;
+    ctx->launches = 0;
+  } else
+    throw Error("unknown option " + n);
+  OB_END
+}
+
+} // extern "C"

@@ -1,0 +1,89 @@
+// ob_internal.h -- internal declarations shared by the .cu translation units (not part of the C ABI).
+#pragma once
+#include "ob_common.cuh"
+#include <cmath>
+#include <complex>
+#include <string>
+#include <vector>
+
+#define OB_VTAC_THREADS 512
+#define OB_MAX_NMAX 13           // shared-memory limit of the VTAC level buffers (2 x T(nMax) x 16 B <= 227 KB)
+#define OB_MAX_FLAT (13 * 15)    // nMax (nMax + 2) at OB_MAX_NMAX
+
+#include "ob_vtac.cuh"
+
+namespace ob {
+
+// index-only VTAC tables for one nMax, resident on one device
+struct VtacTableSet {
+  int nMax = -1;
+  size_t smem = 0;
+  VtacTables tb;
+  std::vector<void *> allocs;
+  void build(int NM);
+  void release();
+};
+
+// ---- ob_vtac.cu ----
+void launch_assemble(VtacTableSet const &ts, const double *xyz, const cplx *Tdiag, cplx k, int nobj, int row0,
+                     int nrows, cplx *S, size_t ld, cudaStream_t st);
+void launch_vtac_single(VtacTableSet const &ts, double r, double the, double phi, cplx k, int regular, cplx *A, cplx *B,
+                        cudaStream_t st);
+void launch_translate_apply(VtacTableSet const &ts, const double *xyz, cplx k, int j0, int count, const cplx *x,
+                            int x_stride, const cplx *scale, cplx *out, cudaStream_t st);
+void launch_sca_sum(VtacTableSet const &ts, const double *xyz, cplx k, int j0, int count, const cplx *x, double *out,
+                    cudaStream_t st);
+
+// ---- ob_mie.cu ----
+struct MieInputs {
+  int nobj, nMax, nMaxS;
+  double omega;
+  cplx eps_b, mu_b;
+  const double *radius;                       // device, nobj
+  const cplx *eps, *mu, *eps_SH, *mu_SH;      // device, nobj each (absolute values)
+};
+// out[which]: 0 T_FF, 1 T_SH, 2 TSH1_outer, 3 TSH2_outer, 4 Iaux, 5 IauxSH1, 6 IauxSH2; each nobj x 2n
+void launch_mie(MieInputs const &in, cplx *const out[7], cudaStream_t st);
+
+// ---- ob_sh.cu ----
+struct ShInputs {
+  int nobj, nMax, nMaxS;
+  double omega;
+  cplx eps_b, mu_b;
+  const double *radius;
+  const cplx *eps, *mu, *eps_SH, *mu_SH, *ksippp, *ksiparppar, *gamma;
+  const double *tab[9]; // C_10m1, C_11m1, C_00m1, C_01m1, W_m1m1, W_11, W_00, W_10, W_01
+};
+void launch_cg_tables(int nMax, int nMaxS, double *const T[9], cudaStream_t st);
+void launch_sh_source(ShInputs const &in, int j0, int count, const cplx *Xint_conj, const cplx *TSH1o,
+                      const cplx *TSH2o, const cplx *IauxSH2, cplx *K, cplx *K1ana, cudaStream_t st);
+void launch_abs_sh(ShInputs const &in, int j0, int count, const cplx *Xint, const cplx *Xint_SH, cplx *out,
+                   cudaStream_t st);
+
+// ---- ob_matvec.cu ----
+struct MatvecPlan {
+  int M = 0, N = 0;       // local rows, columns
+  size_t ld = 0;
+  int tiles = 0, chunks = 0, cols_per_chunk = 0, grid = 0;
+  cplx *partial = nullptr; // [chunks][M] when chunks > 1
+  int variant = 0;
+};
+void matvec_plan(MatvecPlan &p, int M, int N, size_t ld, int sm_count, int variant);
+void matvec_plan_release(MatvecPlan &p);
+void launch_matvec(MatvecPlan const &p, const cplx *S, const cplx *x, cplx *y, cudaStream_t st);
+size_t matvec_launches_per_apply(MatvecPlan const &p);
+
+// ---- ob_vec.cu (Krylov vector kernels) ----
+// h[t] = v_t^H w for t < j (V is ldv-strided), deterministic two-stage reduction
+void launch_multi_dot(const cplx *V, size_t ldv, int j, const cplx *w, int N, cplx *h_dev, cplx *scratch,
+                      cudaStream_t st);
+// w -= sum_t h[t] v_t
+void launch_multi_axpy(const cplx *V, size_t ldv, int j, const cplx *h_dev, cplx *w, int N, cudaStream_t st);
+void launch_norm2(const cplx *w, int N, double *out_dev, double *scratch, cudaStream_t st);
+void launch_scale_to(const cplx *w, double inv, cplx *v, int N, cudaStream_t st); // v = w * inv
+void launch_axpby(cplx a, const cplx *x, cplx b, const cplx *y, cplx *z, int N, cudaStream_t st); // z = a x + b y
+void launch_combine(const cplx *V, size_t ldv, int j, const cplx *coef_dev, cplx *x, int N, cudaStream_t st); // x += V c
+void launch_hadamard(const cplx *a, const cplx *b, const cplx *c, cplx *out, int N, int conj_out, cudaStream_t st);
+size_t vec_scratch_elems(int N, int jmax);
+
+} // namespace ob
