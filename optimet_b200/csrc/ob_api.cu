@@ -861,7 +861,8 @@ int ob_particle_factors(ob_ctx *ctx, int which, double *out) {
   OB_BEGIN
   need(which >= 0 && which < 7, "which must be 0..6");
   ensure_factors(ctx);
-  download(ctx, ctx->fac[which].p, out, ctx->fac[which].n);
+  const int nm = (which == 0 || which == 4) ? ctx->nMax : ctx->nMaxS;
+  download(ctx, ctx->fac[which].p, out, (size_t)ctx->nobj * 2 * flat_max(nm));
   OB_END
 }
 
@@ -959,7 +960,8 @@ int ob_build_cg_tables(ob_ctx *ctx) {
 int ob_fetch_cg_table(ob_ctx *ctx, int t, double *out) {
   OB_BEGIN
   need(t >= 0 && t < 9 && ctx->cg_nmax >= 0, "tables not built");
-  OB_CUDA(cudaMemcpyAsync(out, ctx->cg[t].p, ctx->cg[t].n * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+  const size_t sz = (size_t)flat_max(ctx->nMaxS) * flat_max(ctx->nMax) * flat_max(ctx->nMax);
+  OB_CUDA(cudaMemcpyAsync(out, ctx->cg[t].p, sz * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
   OB_CUDA(cudaStreamSynchronize(ctx->st));
   OB_END
 }
@@ -1084,9 +1086,7 @@ int ob_run(ob_ctx *ctx, const ob_gmres_opts *opts, int do_sh, double *X_sca, dou
       // X_int_conj (PreconditionedMatrixSolver.h:66-67): a .* b conjugated
       launch_hadamard(ctx->Xsca.p, ctx->fac[4].p, nullptr, ctx->tmpA.p, N1, 1, ctx->st);
       ctx->launches += 1;
-      ctx->tmpB.alloc(std::max(N1, N2));
-      OB_CUDA(cudaMemcpyAsync(ctx->tmpB.p, ctx->tmpA.p, (size_t)N1 * sizeof(cplx), cudaMemcpyDeviceToDevice, ctx->st));
-      source_sh(ctx, ctx->tmpB.p);
+      source_sh(ctx, ctx->tmpA.p);
       t.stop();
     }
     {

@@ -91,7 +91,8 @@ void VtacTableSet::build(int NM) {
   tb.off = (const int *)up(off.data(), off.size() * 4);
   tb.rowc = (const double *)up(rowc.data(), rowc.size() * 8);
   tb.colc = (const double *)up(colc.data(), colc.size() * 8);
-  smem = vtac_smem_bytes(NM);
+  // k_translate_apply reuses the buffers for its [groups][2][rows] reduction (<= THREADS * 2 complex)
+  smem = std::max(vtac_smem_bytes(NM), (size_t)OB_VTAC_THREADS * 2 * sizeof(cplx));
 }
 void VtacTableSet::release() {
   for(void *p : allocs)

@@ -138,9 +138,20 @@ def test_full_step_cross_sections(prepared):
     res = ctx.run(opts, do_sh=True)
     orc.solve(O.SOLVER_DIRECT)
     cs = orc.cross_sections()
-    for h, which in ((1, 0), (1, 1), (2, 2), (2, 3)):
-        name = ["X_sca", "X_int", "X_sca_SH", "X_int_SH"][which]
-        assert U.relerr(res[name], orc.vector(which)) < 1e-9, name
+    # scattered coefficients: 2-norm parity (never component-wise)
+    assert U.relerr(res["X_sca"], orc.vector(0)) < 1e-9
+    assert U.relerr(res["X_sca_SH"], orc.vector(2)) < 1e-9
+    # internal coefficients are X_sca scaled by factors spanning ~16 decades (|Iaux_n| ~ (kr)^-n): their plain
+    # 2-norm is dominated by components no double-precision solve of S determines (numpy.linalg.solve and the
+    # oracle's LU already differ by ~6e-5 there), so they are checked (i) as the exact elementwise map of the
+    # device's own X_sca (Solver.cpp:57-77, :95-116) and (ii) through everything that consumes them (K, X_sca_SH,
+    # sigma_abs^SH below).
+    n1, n2 = ctx.n(1), ctx.n(2)
+    Iaux = np.concatenate([orc.particle_factors(j, 4) for j in range(ctx.nobj)])
+    assert U.relerr(res["X_int"], Iaux * res["X_sca"]) < 1e-12
+    Iaux1 = np.concatenate([orc.particle_factors(j, 5) for j in range(ctx.nobj)])
+    _, K1o = orc.sh_source(np.conj(res["X_int"]))
+    assert U.relerr(res["X_int_SH"], Iaux1 * res["X_sca_SH"] - K1o) < 1e-9
     assert abs(res["ext"] / cs["ext"] - 1) < 1e-9
     assert abs(res["sca"] / cs["sca"] - 1) < 1e-9
     assert abs(res["abs"] - (cs["ext"] - cs["sca"])) < 1e-9 * abs(cs["ext"])
