@@ -111,6 +111,8 @@ int ob_cross_sections(ob_ctx *ctx, const double *X_sca, const double *X_int, con
 /* device-event timings (ms) of the last ob_run: 0 factors+source, 1 assemble FF, 2 solve FF, 3 SH source,
  * 4 assemble SH, 5 solve SH, 6 cross sections, 7 matvec total (inside solves), 8 matvec count, 9 kernel launches */
 int ob_timings(ob_ctx *ctx, double out[16]);
+/* CUDA-event stopwatch on the library's stream: op 0 = start, op 1 = stop (+ synchronise) -> elapsed ms */
+int ob_timer(ob_ctx *ctx, int op, double *ms);
 int ob_set_option(ob_ctx *ctx, const char *name, double value); /* "matvec_variant", "keep_matrices" */
 
 #ifdef __cplusplus

@@ -25,7 +25,7 @@ SYMBOLS = [
     "ob_comm_init", "ob_set_cluster", "ob_set_frequency", "ob_set_incident", "ob_vtac", "ob_particle_factors",
     "ob_inc_local", "ob_assemble", "ob_release_matrix", "ob_fetch_block", "ob_fetch_matrix", "ob_matvec",
     "ob_source_ff", "ob_set_cg_tables", "ob_build_cg_tables", "ob_fetch_cg_table", "ob_source_sh", "ob_solve",
-    "ob_unprecondition_ff", "ob_unprecondition_sh", "ob_run", "ob_cross_sections", "ob_timings", "ob_set_option",
+    "ob_unprecondition_ff", "ob_unprecondition_sh", "ob_run", "ob_cross_sections", "ob_timings", "ob_timer", "ob_set_option",
 ]
 
 _lib = None

@@ -135,7 +135,7 @@ struct ob_ctx {
   long launches = 0;
   int matvec_variant = 0;
   bool keep_matrices = true;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm0 = nullptr, evm1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm0 = nullptr, evm1 = nullptr, evt0 = nullptr, evt1 = nullptr;
 
   int N(int h) const { return 2 * hs[h - 1].n * nobj; }
   int Mloc(int h) const { return 2 * hs[h - 1].n * count; }
@@ -235,9 +235,7 @@ static void assemble(ob_ctx *c, int harmonic) {
 static void matvec(ob_ctx *c, int harmonic, const cplx *x, cplx *y) {
   HarmonicState &H = c->hs[harmonic - 1];
   need(H.assembled, "matrix not assembled (call ob_assemble)");
-  cudaEventRecord(c->evm0, c->st);
-  launch_matvec(H.plan, H.S.p, x, y + (size_t)c->first * 2 * H.n, c->st);
-  cudaEventRecord(c->evm1, c->st);
+  launch_matvec(H.plan, H.S.p, x, y + (size_t)c->first * 2 * H.n, c->st, c->evm0, c->evm1);
   c->launches += matvec_launches_per_apply(H.plan);
   allgather_slices(c, y, 2 * H.n);
   // timing of the matvec alone (device events); syncing here is harmless: the driver syncs per iteration anyway
@@ -695,6 +693,8 @@ int ob_create(int device, ob_ctx **out) {
     OB_CUDA(cudaEventCreate(&c->ev1));
     OB_CUDA(cudaEventCreate(&c->evm0));
     OB_CUDA(cudaEventCreate(&c->evm1));
+    OB_CUDA(cudaEventCreate(&c->evt0));
+    OB_CUDA(cudaEventCreate(&c->evt1));
     *out = c;
   } catch(std::exception &e) {
     g_create_error = e.what();
@@ -719,6 +719,8 @@ void ob_destroy(ob_ctx *ctx) {
   cudaEventDestroy(ctx->ev1);
   cudaEventDestroy(ctx->evm0);
   cudaEventDestroy(ctx->evm1);
+  cudaEventDestroy(ctx->evt0);
+  cudaEventDestroy(ctx->evt1);
   cudaStream_t st = ctx->st;
   delete ctx;
   cudaStreamDestroy(st);
@@ -1131,6 +1133,21 @@ int ob_timings(ob_ctx *ctx, double out[16]) {
     out[i] = ctx->tim[i];
   out[9] = (double)ctx->launches;
   return 0;
+}
+
+int ob_timer(ob_ctx *ctx, int op, double *ms) {
+  OB_BEGIN
+  if(op == 0)
+    OB_CUDA(cudaEventRecord(ctx->evt0, ctx->st));
+  else {
+    OB_CUDA(cudaEventRecord(ctx->evt1, ctx->st));
+    OB_CUDA(cudaEventSynchronize(ctx->evt1));
+    float f = 0;
+    OB_CUDA(cudaEventElapsedTime(&f, ctx->evt0, ctx->evt1));
+    if(ms)
+      *ms = f;
+  }
+  OB_END
 }
 
 int ob_set_option(ob_ctx *ctx, const char *name, double value) {

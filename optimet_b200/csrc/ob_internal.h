@@ -70,7 +70,8 @@ struct MatvecPlan {
 };
 void matvec_plan(MatvecPlan &p, int M, int N, size_t ld, int sm_count, int variant);
 void matvec_plan_release(MatvecPlan &p);
-void launch_matvec(MatvecPlan const &p, const cplx *S, const cplx *x, cplx *y, cudaStream_t st);
+void launch_matvec(MatvecPlan const &p, const cplx *S, const cplx *x, cplx *y, cudaStream_t st,
+                   cudaEvent_t e0 = nullptr, cudaEvent_t e1 = nullptr);
 size_t matvec_launches_per_apply(MatvecPlan const &p);
 
 // ---- ob_vec.cu (Krylov vector kernels) ----

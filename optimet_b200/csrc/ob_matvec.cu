@@ -253,9 +253,12 @@ void matvec_plan_release(MatvecPlan &p) {
 }
 size_t matvec_launches_per_apply(MatvecPlan const &p) { return p.chunks > 1 ? 2 : 1; }
 
-void launch_matvec(MatvecPlan const &p, const cplx *S, const cplx *x, cplx *y, cudaStream_t st) {
+void launch_matvec(MatvecPlan const &p, const cplx *S, const cplx *x, cplx *y, cudaStream_t st, cudaEvent_t e0,
+                   cudaEvent_t e1) {
   if(p.M == 0)
     return;
+  if(e0)
+    cudaEventRecord(e0, st);
   cplx *out = p.chunks > 1 ? p.partial : y;
   switch(p.variant) {
   case 0: launch_variant<1, 16, 6>(p, S, x, out, st); break;
@@ -265,6 +268,8 @@ void launch_matvec(MatvecPlan const &p, const cplx *S, const cplx *x, cplx *y, c
   case 4: launch_variant<1, 32, 3>(p, S, x, out, st); break;
   default: launch_variant<1, 16, 4>(p, S, x, out, st); break;
   }
+  if(e1)
+    cudaEventRecord(e1, st); // brackets the streaming kernel alone (the roofline denominator)
   if(p.chunks > 1) {
     k_matvec_reduce<<<(p.M + 255) / 256, 256, 0, st>>>(p.partial, p.M, p.chunks, y);
     OB_CUDA(cudaGetLastError());
