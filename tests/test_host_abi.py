@@ -1,0 +1,167 @@
+"""CPU tests of the boundary: the C-ABI library loads and exports every symbol include/optimet_b200.h declares
+(no compute calls without a GPU), fails loudly without a device, and the C++11 host layer (XML reader, material
+models, plane-wave coefficients) reproduces the reference's host-side preparation as restated by the oracle."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from optimet_b200 import capi, host as H, xmlgen
+from oracle import oracle as O
+from tests import util as U
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXAMPLES = "/root/reference/examples"  # only present in the build container; tests needing it skip elsewhere
+have_examples = os.path.isdir(EXAMPLES)
+
+
+def _have_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_header_symbols_are_exported():
+    hdr = open(os.path.join(ROOT, "include", "optimet_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(ob_[a-z_0-9]+)\s*\(", hdr)))
+    assert len(declared) >= 30
+    lib = capi.load()
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert not missing, missing
+    assert sorted(capi.SYMBOLS) == declared  # the ctypes view lists exactly the header's entry points
+    hl = H.load()
+    assert not [s for s in H.HOST_SYMBOLS if not hasattr(hl, s)]
+
+
+def test_library_is_sm100a_only():
+    import subprocess
+    out = subprocess.run(["cuobjdump", "--list-elf", capi.lib_path()], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    archs = set(re.findall(r"sm_\d+a?", out.stdout))
+    assert archs == {"sm_100a"}, archs
+
+
+@pytest.mark.skipif(_have_gpu(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        capi.Context(0)
+    case = H.Case(xml=xmlgen.cluster_xml([[0, 0, 0], [0, 0, 200.0]], 50.0, 3, 1240.0))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        H.Solver(case)
+
+
+@pytest.mark.parametrize("nobj,world", [(1000, 8), (200, 8), (343, 4), (11, 2), (3, 8), (7, 7), (5, 1)])
+def test_partition_rule(nobj, world):
+    # contiguous block-rows with the remainder rule of PreconditionedMatrix.cpp:418-424
+    nxt = 0
+    for r in range(world):
+        f, n = capi.Library.partition(nobj, world, r)
+        assert f == nxt and n in (nobj // world, nobj // world + 1)
+        assert (n == nobj // world + 1) == (r < nobj % world)
+        nxt = f + n
+    assert nxt == nobj
+    with pytest.raises(ValueError):
+        capi.Library.partition(10, 2, 2)
+
+
+def test_gmres_opts_layout():
+    # struct ob_gmres_opts { int; double; int; int; int } : the ctypes mirror must match the C layout
+    assert C.sizeof(capi.GmresOpts) == 32
+    assert capi.GmresOpts.tol.offset == 8 and capi.GmresOpts.max_iters.offset == 16
+
+
+# ---------------------------------------------------------------------------------------------------
+# host layer vs the oracle's restatement of Reader / ElectroMagnetic / Excitation::populate
+# ---------------------------------------------------------------------------------------------------
+def _compare_case_with_oracle(case, spec_materials, lam_m, theta, phi, Eth, Eph):
+    a = case.arrays()
+    i = case.info()
+    orc = O.Case()
+    for j in range(i["nobj"]):
+        model, params = spec_materials[j] if isinstance(spec_materials, list) else spec_materials
+        orc.add_sphere(list(a["xyz"][j]), float(a["radius"][j]), i["nMax"], model, params)
+    orc.set_source(lam_m, theta, phi, Eth, Eph, True)
+    oi = orc.info()
+    assert abs(a["omega"] / oi["omega"] - 1) < 1e-15
+    assert abs(a["waveK"] / oi["waveK"] - 1) < 1e-15
+    ao, bo = orc.incident()
+    assert U.relerr(a["a"], ao) < 1e-14 and U.relerr(a["b"], bo) < 1e-14
+    for j in range(i["nobj"]):
+        m = orc.material(j)
+        assert abs(a["eps"][j] / (m["eps_r"] * U.EPS0) - 1) < 1e-14
+        assert abs(a["eps_SH"][j] / (m["eps_r_SH"] * U.EPS0) - 1) < 1e-14
+        assert abs(a["mu"][j] / (m["mu_r"] * U.MU0) - 1) < 1e-14
+        for key in ("ksippp", "ksiparppar", "gamma"):
+            assert abs(a[key][j] - m[key]) <= 1e-14 * abs(m[key])
+    return orc
+
+
+@pytest.mark.skipif(not have_examples, reason="reference examples not present")
+def test_reads_two_particles_si_as_shipped():
+    case = H.Case(path=os.path.join(EXAMPLES, "TwoParticlesSi.xml"))
+    i = case.info()
+    assert (i["nobj"], i["nMax"], i["nMaxS"], i["SH_cond"], i["ACA_cond"], i["outputType"]) == (2, 6, 6, True, True, 11)
+    lams = case.scan_wavelengths_list()  # Reader.cpp:886-891, Simulation.cpp:634-644
+    assert len(lams) == 46 and abs(lams[0] - 1000e-9) < 1e-20 and abs(lams[-1] - 1450e-9) < 1e-20
+    o = case.gmres_defaults()  # serial solver constants, PreconditionedMatrixSolver.h:50-52
+    assert (o.flavour, o.tol, o.max_iters, o.max_restarts) == (capi.OB_GMRES_ZCOMP, 1e-6, 240, 2)
+    _compare_case_with_oracle(case, U.SI, i["wavelength"], np.deg2rad(45.0), np.deg2rad(90.0), 1.0, 0.0)
+    # spectral sweep: the Si table is re-interpolated at each wavelength (ElectroMagnetic.cpp:145-241)
+    case.set_wavelength(1105e-9)
+    _compare_case_with_oracle(case, U.SI, 1105e-9, np.deg2rad(45.0), np.deg2rad(90.0), 1.0, 0.0)
+
+
+@pytest.mark.skipif(not have_examples, reason="reference examples not present")
+def test_reads_three_particles_au_as_shipped():
+    case = H.Case(path=os.path.join(EXAMPLES, "ThreeParticlesAu.xml"))
+    i = case.info()
+    assert (i["nobj"], i["nMax"], i["SH_cond"]) == (3, 3, True)
+    a = case.arrays()
+    assert np.allclose(a["radius"], [50e-9, 100e-9, 150e-9], rtol=1e-15)
+    assert len(case.scan_wavelengths_list()) == 2
+    _compare_case_with_oracle(case, U.AU, i["wavelength"], np.deg2rad(45.0), np.deg2rad(90.0), 1.0, 0.0)
+
+
+@pytest.mark.skipif(not have_examples, reason="reference examples not present")
+def test_reads_eleven_particles_belos_list():
+    case = H.Case(path=os.path.join(EXAMPLES, "ElevenParticlesSi.xml"))
+    i = case.info()
+    assert (i["nobj"], i["nMax"], i["outputType"]) == (11, 12, 0)
+    o = case.gmres_defaults()  # examples/ElevenParticlesSi.xml:4-12
+    assert (o.flavour, o.tol, o.max_iters, o.restart, o.max_restarts) == (capi.OB_GMRES_BELOS, 1e-5, 50, 30, 20)
+
+
+@pytest.mark.skipif(not have_examples, reason="reference examples not present")
+def test_cube_lattice_enumeration_quirk():
+    # Reader.cpp:150-181: x fastest; object k <- site k+1, last object at the origin
+    case = H.Case(path=os.path.join(EXAMPLES, "ManyParticles.xml"))
+    assert case.info()["nobj"] == 343
+    xyz = case.arrays()["xyz"] * 1e9
+    sites = xmlgen.cube_sites(7, None, 190.0)
+    assert np.allclose(xyz[:342], sites[1:], atol=1e-9)
+    assert np.allclose(xyz[342], 0.0, atol=1e-12)
+
+
+def test_generated_xml_roundtrip_all_material_models():
+    mats = [("silicon",), ("gold", 1.0, -1.0, 1.0), ("fixed", 9.0 + 0.4j, 7.0 + 0.9j, 1e-19, 2e-19, 0.5e-19)]
+    xml = xmlgen.cluster_xml([[0, 0, 0], [260, 40, -90], [-30, 310, 120]], [60, 80, 70], 4, 700.0, material=mats,
+                             theta_deg=30, phi_deg=20, Eth=0.6, Eph=0.8j)
+    case = H.Case(xml=xml)
+    spec = [U.SI, U.AU, U.fixed(9.0 + 0.4j, 7.0 + 0.9j)]
+    _compare_case_with_oracle(case, spec, 700e-9, np.deg2rad(30.0), np.deg2rad(20.0), 0.6, 0.8j)
+
+
+def test_bad_inputs_raise_like_the_reference():
+    with pytest.raises(RuntimeError):  # Reader.cpp:966-970
+        H.Case(path="/nonexistent/input.xml")
+    with pytest.raises(RuntimeError):  # no <geometry>: Reader.cpp:59
+        H.Case(xml='<simulation><harmonics nmax="3"/></simulation>')
+    xml = xmlgen.cluster_xml([[0, 0, 0], [0, 0, 90.0]], 50.0, 3, 800.0)  # overlapping spheres: Geometry.cpp:41-49
+    with pytest.raises(RuntimeError, match="overlap"):
+        H.Case(xml=xml)
