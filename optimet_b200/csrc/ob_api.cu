@@ -19,6 +19,7 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
@@ -39,12 +40,13 @@ struct NcclApi {
     OB_SYM(CommInitRank, "ncclCommInitRank");
     OB_SYM(CommDestroy, "ncclCommDestroy");
     OB_SYM(AllGather, "ncclAllGather");
+    OB_SYM(AllReduce, "ncclAllReduce");
     OB_SYM(Broadcast, "ncclBroadcast");
     OB_SYM(GroupStart, "ncclGroupStart");
     OB_SYM(GroupEnd, "ncclGroupEnd");
     OB_SYM(GetErrorString, "ncclGetErrorString");
 #undef OB_SYM
-    return GetUniqueId && CommInitRank && AllGather && Broadcast && GroupStart && GroupEnd;
+    return GetUniqueId && CommInitRank && AllGather && AllReduce && Broadcast && GroupStart && GroupEnd;
   }
 };
 static NcclApi g_nccl;
@@ -91,9 +93,14 @@ static void partition(int nobj, int world, int rank, int &first, int &count) {
 struct HarmonicState {
   int nMax = 0, n = 0;
   cplx k = mk(0, 0);
-  DevBuf<cplx> S; // local slab, column-major, ld = M_loc
+  DevBuf<cplx> S; // dense form: local slab, column-major, ld = M_loc
   bool assembled = false;
   MatvecPlan plan;
+  // pair form (ob_pairs.cu): unscaled A^T, B^T of the local pairs i < j
+  int mode = 0; // operator form this harmonic was assembled in (0 dense, 1 pairs)
+  DevBuf<cplx> AB;
+  PairPlan pplan;
+  int pplan_world = -1, pplan_rank = -1;
 };
 
 } // namespace ob
@@ -134,6 +141,7 @@ struct ob_ctx {
   double tim[16] = {0};
   long launches = 0;
   int matvec_variant = 0;
+  int operator_mode = 1; // 0 = dense slab (reference layout), 1 = compact pair form (default)
   bool keep_matrices = true;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm0 = nullptr, evm1 = nullptr, evt0 = nullptr, evt1 = nullptr;
 
@@ -221,9 +229,25 @@ static void assemble(ob_ctx *c, int harmonic) {
   ensure_factors(c);
   HarmonicState &H = c->hs[harmonic - 1];
   const size_t M = (size_t)c->Mloc(harmonic), N = (size_t)c->N(harmonic);
-  H.S.alloc(M * N);
   H.k = harmonic == 1 ? c->waveK : cscale(c->waveK, 2.0);
   VtacTableSet &ts = tables_for(c, H.nMax);
+  if(c->operator_mode == 1) {
+    if(H.pplan.nobj != c->nobj || H.pplan.n != H.n || H.pplan_world != c->world || H.pplan_rank != c->rank) {
+      pair_plan_build(H.pplan, c->nobj, H.n, c->world, c->rank, c->sm_count);
+      H.pplan_world = c->world;
+      H.pplan_rank = c->rank;
+    }
+    H.S.release();
+    H.AB.alloc(std::max<size_t>(1, pair_storage_elems(H.pplan)));
+    launch_assemble_pairs(ts, c->xyz.p, H.k, H.pplan.pair_ij, H.pplan.npairs, H.AB.p, c->st);
+    c->launches += 1;
+    H.mode = 1;
+    H.assembled = true;
+    return;
+  }
+  H.AB.release();
+  H.mode = 0;
+  H.S.alloc(M * N);
   launch_assemble(ts, c->xyz.p, c->fac[harmonic == 1 ? 0 : 1].p, H.k, c->nobj, c->first, c->count, H.S.p, M, c->st);
   c->launches += 1;
   if(H.plan.M != (int)M || H.plan.N != (int)N || H.plan.variant != c->matvec_variant)
@@ -235,9 +259,27 @@ static void assemble(ob_ctx *c, int harmonic) {
 static void matvec(ob_ctx *c, int harmonic, const cplx *x, cplx *y) {
   HarmonicState &H = c->hs[harmonic - 1];
   need(H.assembled, "matrix not assembled (call ob_assemble)");
-  launch_matvec(H.plan, H.S.p, x, y + (size_t)c->first * 2 * H.n, c->st, c->evm0, c->evm1);
-  c->launches += matvec_launches_per_apply(H.plan);
-  allgather_slices(c, y, 2 * H.n);
+  if(H.mode == 1) {
+    const cplx *T = c->fac[harmonic == 1 ? 0 : 1].p;
+    const size_t N = (size_t)c->N(harmonic);
+    if(c->world == 1) {
+      launch_matvec_pairs(H.pplan, H.AB.p, x, T, y, 1, c->st, c->evm0, c->evm1);
+      c->launches += 3;
+    } else {
+      need(c->comm != nullptr, "world > 1 but ob_comm_init has not been called");
+      launch_matvec_pairs(H.pplan, H.AB.p, x, T, H.pplan.acc, 0, c->st, c->evm0, c->evm1);
+      OB_NCCL(g_nccl.AllReduce((const void *)H.pplan.acc, (void *)H.pplan.acc, 2 * N, ncclDouble, ncclSum, c->comm,
+                               c->st));
+      launch_pairs_finalize(x, T, H.pplan.acc, N, y, c->st);
+      c->launches += 4;
+    }
+    c->tim[10] = 16.0 * (double)pair_storage_elems(H.pplan) + 32.0 * (double)N;
+  } else {
+    launch_matvec(H.plan, H.S.p, x, y + (size_t)c->first * 2 * H.n, c->st, c->evm0, c->evm1);
+    c->launches += matvec_launches_per_apply(H.plan);
+    allgather_slices(c, y, 2 * H.n);
+    c->tim[10] = 16.0 * (double)c->Mloc(harmonic) * (double)c->N(harmonic) + 32.0 * (double)c->N(harmonic);
+  }
   // timing of the matvec alone (device events); syncing here is harmless: the driver syncs per iteration anyway
   cudaEventSynchronize(c->evm1);
   float ms = 0;
@@ -714,6 +756,7 @@ void ob_destroy(ob_ctx *ctx) {
   for(int i = 0; i < 2; ++i) {
     ctx->tabs[i].release();
     matvec_plan_release(ctx->hs[i].plan);
+    pair_plan_release(ctx->hs[i].pplan);
   }
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
@@ -893,6 +936,7 @@ int ob_release_matrix(ob_ctx *ctx, int harmonic) {
   OB_BEGIN
   check_harmonic(harmonic);
   ctx->hs[harmonic - 1].S.release();
+  ctx->hs[harmonic - 1].AB.release();
   ctx->hs[harmonic - 1].assembled = false;
   OB_END
 }
@@ -902,6 +946,15 @@ int ob_fetch_block(ob_ctx *ctx, int harmonic, int i, int j, double *out) {
   check_harmonic(harmonic);
   HarmonicState &H = ctx->hs[harmonic - 1];
   need(H.assembled, "matrix not assembled");
+  if(H.mode == 1) {
+    need(i >= 0 && i < ctx->nobj && j >= 0 && j < ctx->nobj, "block index out of range");
+    const size_t b2 = (size_t)4 * H.n * H.n;
+    ctx->tmpA.alloc(std::max(b2, (size_t)ctx->N(harmonic)));
+    launch_pairs_expand_block(H.pplan, H.AB.p, i, j, ctx->fac[harmonic == 1 ? 0 : 1].p, ctx->tmpA.p, ctx->st);
+    ctx->launches += 1;
+    download(ctx, ctx->tmpA.p, out, b2);
+    return 0;
+  }
   need(i >= ctx->first && i < ctx->first + ctx->count && j >= 0 && j < ctx->nobj, "block is not local to this rank");
   const size_t b = 2 * H.n, ld = (size_t)ctx->Mloc(harmonic);
   const cplx *src = H.S.p + (size_t)j * b * ld + (size_t)(i - ctx->first) * b;
@@ -916,6 +969,23 @@ int ob_fetch_matrix(ob_ctx *ctx, int harmonic, double *out) {
   check_harmonic(harmonic);
   HarmonicState &H = ctx->hs[harmonic - 1];
   need(H.assembled, "matrix not assembled");
+  if(H.mode == 1) { // rebuild the dense reference layout block by block (tests; single rank only)
+    need(ctx->world == 1, "ob_fetch_matrix in pair form needs world == 1");
+    const size_t b = 2 * (size_t)H.n, ld = (size_t)ctx->N(harmonic);
+    DevBuf<cplx> blk;
+    blk.alloc(b * b);
+    std::vector<hcd> hb(b * b);
+    hcd *o = (hcd *)out;
+    for(int i = 0; i < ctx->nobj; ++i)
+      for(int j = 0; j < ctx->nobj; ++j) {
+        launch_pairs_expand_block(H.pplan, H.AB.p, i, j, ctx->fac[harmonic == 1 ? 0 : 1].p, blk.p, ctx->st);
+        OB_CUDA(cudaMemcpyAsync(hb.data(), blk.p, b * b * sizeof(cplx), cudaMemcpyDeviceToHost, ctx->st));
+        OB_CUDA(cudaStreamSynchronize(ctx->st));
+        for(size_t cc = 0; cc < b; ++cc)
+          memcpy(o + ((size_t)j * b + cc) * ld + (size_t)i * b, hb.data() + cc * b, b * sizeof(hcd));
+      }
+    return 0;
+  }
   download(ctx, H.S.p, out, (size_t)ctx->Mloc(harmonic) * ctx->N(harmonic));
   OB_END
 }
@@ -1080,6 +1150,7 @@ int ob_run(ob_ctx *ctx, const ob_gmres_opts *opts, int do_sh, double *X_sca, dou
   if(do_sh) {
     if(!ctx->keep_matrices) {
       ctx->hs[0].S.release();
+      ctx->hs[0].AB.release();
       ctx->hs[0].assembled = false;
     }
     {
@@ -1161,6 +1232,11 @@ int ob_set_option(ob_ctx *ctx, const char *name, double value) {
                     ctx->matvec_variant);
   } else if(n == "keep_matrices")
     ctx->keep_matrices = value != 0;
+  else if(n == "operator") { // 0 = dense slab, 1 = compact pair form
+    need(value == 0 || value == 1, "operator must be 0 (dense) or 1 (pairs)");
+    ctx->operator_mode = (int)value;
+    ctx->hs[0].assembled = ctx->hs[1].assembled = false;
+  }
   else if(n == "reset_timings") {
     for(int i = 0; i < 16; ++i)
       ctx->tim[i] = 0;

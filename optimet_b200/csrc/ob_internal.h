@@ -74,6 +74,31 @@ void launch_matvec(MatvecPlan const &p, const cplx *S, const cplx *x, cplx *y, c
                    cudaEvent_t e0 = nullptr, cudaEvent_t e1 = nullptr);
 size_t matvec_launches_per_apply(MatvecPlan const &p);
 
+// ---- ob_pairs.cu (compact pair operator: unscaled A^T, B^T of the pairs i < j) ----
+struct PairPlan {
+  int nobj = 0, n = 0, grid = 0, nseg = 0;
+  long p0 = 0, p1 = 0, npairs = 0; // global pair range [p0, p1) owned by this rank
+  int KB = 0, NS = 0, G = 0;
+  size_t smem = 0;
+  int2 *pair_ij = nullptr;
+  int4 *segs = nullptr;
+  int *cta_seg = nullptr, *row_seg = nullptr;
+  int2 *col_range = nullptr;
+  long *col_first = nullptr;
+  cplx *rowpart = nullptr, *colpart = nullptr, *XP = nullptr, *XS = nullptr, *acc = nullptr;
+};
+void pair_plan_build(PairPlan &p, int nobj, int n, int world, int rank, int sm_count);
+void pair_plan_release(PairPlan &p);
+size_t pair_storage_elems(PairPlan const &p);
+void launch_matvec_pairs(PairPlan const &p, const cplx *AB, const cplx *x, const cplx *Tdiag, cplx *acc_or_y,
+                         int finalize, cudaStream_t st, cudaEvent_t e0 = nullptr, cudaEvent_t e1 = nullptr);
+void launch_pairs_finalize(const cplx *x, const cplx *Tdiag, const cplx *acc, size_t N, cplx *y, cudaStream_t st);
+void launch_pairs_expand_block(PairPlan const &p, const cplx *AB, int i, int j, const cplx *Tdiag, cplx *out,
+                               cudaStream_t st);
+// ob_vtac.cu: assembly of the pair storage (one CTA per local pair)
+void launch_assemble_pairs(VtacTableSet const &ts, const double *xyz, cplx k, const int2 *pair_ij, long npairs,
+                           cplx *AB, cudaStream_t st);
+
 // ---- ob_vec.cu (Krylov vector kernels) ----
 // h[t] = v_t^H w for t < j (V is ldv-strided), deterministic two-stage reduction
 void launch_multi_dot(const cplx *V, size_t ldv, int j, const cplx *w, int N, cplx *h_dev, cplx *scratch,

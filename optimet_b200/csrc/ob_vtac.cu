@@ -167,6 +167,34 @@ k_assemble(VtacTables tb, const double *__restrict__ xyz, const cplx *__restrict
 }
 
 // ---------------------------------------------------------------------------------------------
+// K1 (pair form): one CTA per local pair (i < j); stores the unscaled A^T, B^T (n x n each, rows = harmonics of
+// particle i fastest) -- see ob_pairs.cu.  Same vtac_block, half the CTAs and a quarter of the bytes of k_assemble.
+// ---------------------------------------------------------------------------------------------
+struct EmitPair {
+  cplx *A, *B;
+  int n;
+  __device__ __forceinline__ void item(int p, int r, cplx a, cplx b) {
+    __stcs(A + (size_t)p * n + r, a);
+    __stcs(B + (size_t)p * n + r, b);
+  }
+};
+__global__ void __launch_bounds__(OB_VTAC_THREADS)
+k_assemble_pairs(VtacTables tb, const double *__restrict__ xyz, cplx k, const int2 *__restrict__ pair_ij,
+                 cplx *__restrict__ AB) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int2 ij = pair_ij[blockIdx.x];
+  const int i = ij.x, j = ij.y;
+  const int n = flat_max(tb.NM);
+  double r, the, phi;
+  to_spherical(xyz[3 * i] - xyz[3 * j], xyz[3 * i + 1] - xyz[3 * j + 1], xyz[3 * i + 2] - xyz[3 * j + 2], r, the, phi);
+  EmitPair em;
+  em.A = AB + (size_t)blockIdx.x * 2 * n * n;
+  em.B = em.A + (size_t)n * n;
+  em.n = n;
+  vtac_block(tb, smem_raw, r, the, phi, k, false, em);
+}
+
+// ---------------------------------------------------------------------------------------------
 // single displacement -> A, B (n x n, column-major, A[p + q n] = Coupling.diagonal(p, q))
 // ---------------------------------------------------------------------------------------------
 struct EmitAB {
@@ -317,6 +345,14 @@ void launch_assemble(VtacTableSet const &ts, const double *xyz, const cplx *Tdia
   set_smem((const void *)k_assemble, ts.smem);
   dim3 grid(nobj, nrows);
   k_assemble<<<grid, OB_VTAC_THREADS, ts.smem, st>>>(ts.tb, xyz, Tdiag, k, row0, S, ld);
+  OB_CUDA(cudaGetLastError());
+}
+void launch_assemble_pairs(VtacTableSet const &ts, const double *xyz, cplx k, const int2 *pair_ij, long npairs,
+                           cplx *AB, cudaStream_t st) {
+  if(npairs <= 0)
+    return;
+  set_smem((const void *)k_assemble_pairs, ts.smem);
+  k_assemble_pairs<<<(unsigned)npairs, OB_VTAC_THREADS, ts.smem, st>>>(ts.tb, xyz, k, pair_ij, AB);
   OB_CUDA(cudaGetLastError());
 }
 void launch_vtac_single(VtacTableSet const &ts, double r, double the, double phi, cplx k, int regular, cplx *A, cplx *B,

@@ -46,12 +46,20 @@ SPECS = {
 }
 
 
-@pytest.fixture(params=sorted(SPECS))
+# operator forms: "dense" = the reference's column-major slab streamed by k_matvec; "pairs" = the compact
+# A^T/B^T-of-i<j form streamed by k_matvec_pairs (csrc/ob_pairs.cu, the default).  Both must meet the same bar.
+MODES = {"dense": 0, "pairs": 1}
+
+
+@pytest.fixture(params=[(s, m) for s in sorted(SPECS) for m in sorted(MODES)], ids=lambda p: "%s-%s" % p)
 def prepared(request, gpu_ctx):
-    spec = SPECS[request.param]()
+    name, mode = request.param
+    spec = SPECS[name]()
     orc = U.oracle_case(spec)
+    gpu_ctx.set_option("operator", MODES[mode])
     U.configure_ctx(gpu_ctx, spec, orc)
-    return spec, orc, gpu_ctx
+    yield spec, orc, gpu_ctx
+    gpu_ctx.set_option("operator", 1)
 
 
 def test_particle_factors(prepared):
@@ -161,3 +169,27 @@ def test_full_step_cross_sections(prepared):
     cs2 = ctx.cross_sections(res["X_sca"], res["X_int"], res["X_sca_SH"], res["X_int_SH"])
     for k in ("ext", "sca", "sca_SH", "abs_SH"):
         assert abs(cs2[k] / res[k] - 1) < 1e-12
+
+
+@pytest.mark.parametrize("nobj,nMax", [(40, 3), (12, 6), (3, 13), (2, 1), (1, 4), (23, 8)])
+@pytest.mark.parametrize("harmonic", [1, 2])
+def test_pair_operator_matvec_many_blocks(gpu_ctx, nobj, nMax, harmonic):
+    """Pair form on clusters large enough that the pair list spans many CTAs, row segments and partial rows
+    (780 pairs at 40 particles), on the widest block (nMax 13, one column group) and on the degenerate
+    1-/2-particle cases; checked against the oracle's dense product."""
+    spec = U.random_cluster(nobj, nMax, seed=nobj + nMax)
+    orc = U.oracle_case(spec)
+    gpu_ctx.set_option("operator", 1)
+    U.configure_ctx(gpu_ctx, spec, orc)
+    gpu_ctx.assemble(harmonic)
+    So = orc.matrix(harmonic)
+    rng = np.random.RandomState(nobj)
+    for _ in range(2):
+        x = rng.standard_normal(So.shape[1]) + 1j * rng.standard_normal(So.shape[1])
+        assert U.relerr(gpu_ctx.matvec(harmonic, x), O.matvec(So, x)) < 1e-12
+    # the dense form gives the same product
+    gpu_ctx.set_option("operator", 0)
+    gpu_ctx.assemble(harmonic)
+    yd = gpu_ctx.matvec(harmonic, x)
+    gpu_ctx.set_option("operator", 1)
+    assert U.relerr(yd, O.matvec(So, x)) < 1e-12
