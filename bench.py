@@ -174,7 +174,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c4")
     ap.add_argument("--matvec-variant", type=int, default=None)
+    ap.add_argument("--operator", default="pairs", choices=["pairs", "dense"],
+                    help="pairs: compact A^T/B^T-of-i<j form (default); dense: the reference's full slab")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="library tuning option name=value (ob_set_option)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -227,6 +230,10 @@ def main():
         solver.comm_init(uid[0], rank, world)
     if args.matvec_variant is not None:
         solver.set_option("matvec_variant", args.matvec_variant)
+    solver.set_option("operator", 1 if args.operator == "pairs" else 0)
+    for opt in args.opt:
+        k, v = opt.split("=")
+        solver.set_option(k, float(v))
     lib = capi.load()
     ctx = C.c_void_p(H.load().obh_solver_ctx(solver.s))
     opts = case.gmres_defaults()
@@ -267,7 +274,7 @@ def main():
         cs, st = run_resident()
         tm = solver.ctx_timings()
         for k, v in tm.items():
-            acc[k] = acc.get(k, 0.0) + v
+            acc[k] = v if k == "operator_bytes" else acc.get(k, 0.0) + v
     lib.ob_timer(ctx, 1, C.byref(ms))
     barrier()
     wall = time.perf_counter() - t0
@@ -301,7 +308,9 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peaks()
         m_loc = n2 * count
-        mv_bytes = 16.0 * m_loc * N + 32.0 * N  # 16 N^2 + 32 N per apply (local slab)
+        # dense 16 M_loc N + 32 N per apply; pair form 32 n^2 per local pair + 32 N
+        # (= 4 N^2 (1 - 1/N_obj) + 32 N on one GPU), reported by the library for the form actually streamed
+        mv_bytes = acc["operator_bytes"]
         achieved = mv_bytes / (float(mv_t.item()) * 1e-3) / 1e9
         os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
         try:
@@ -317,14 +326,17 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "c128 (complex FP64)", "data": "synthetic",
             "config": {"workload": wl["name"], "N": N, "rows_per_gpu": m_loc, "gmres": "belos tol=1e-5 restart=30",
                        "iters_ff": st[0], "iters_sh": st[1], "l2": "inputs larger than L2",
-                       "phases_ms_per_step": {k: acc[k] / args.steps for k in acc if k not in ("matvec_count", "launches")},
+                       "operator": args.operator,
+                       "phases_ms_per_step": {k: acc[k] / args.steps for k in acc
+                                              if k not in ("matvec_count", "launches", "operator_bytes")},
                        "matvecs_per_step": acc["matvec_count"] / args.steps,
                        "cross_sections": dict(zip(["ext", "sca", "abs", "sca_SH", "abs_SH"], [float(x) for x in cs_t.tolist()])),
                        "wall_s_resident_arm": wall},
             "clocks": clocks,
             "e2e": {"value": e2e_per_step / 1e3, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(acc["launches"]),
-            "roofline": {"bound": "hbm", "kernel": "k_matvec (TMA-streamed complex-FP64 block matvec)",
+            "roofline": {"bound": "hbm", "kernel": ("k_matvec_pairs (TMA-streamed complex-FP64 pair-form block matvec)" if args.operator == "pairs"
+                                    else "k_matvec (TMA-streamed complex-FP64 dense block matvec)"),
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "traffic": None,
                          "algorithmic_bytes_per_launch": mv_bytes, "avg_launch_ms": float(mv_t.item())},

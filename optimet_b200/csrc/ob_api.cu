@@ -1232,7 +1232,15 @@ int ob_set_option(ob_ctx *ctx, const char *name, double value) {
                     ctx->matvec_variant);
   } else if(n == "keep_matrices")
     ctx->keep_matrices = value != 0;
-  else if(n == "operator") { // 0 = dense slab, 1 = compact pair form
+  else if(n == "pairs_kb" || n == "pairs_groups") { // tuning: columns per pipeline stage / column groups (0 = auto)
+    static int kb = 0, gr = 0;
+    (n == "pairs_kb" ? kb : gr) = (int)value;
+    pair_plan_tuning(kb, gr);
+    for(int h = 0; h < 2; ++h) {
+      ctx->hs[h].pplan_world = -1; // force a rebuild of the plan at the next assembly
+      ctx->hs[h].assembled = false;
+    }
+  } else if(n == "operator") { // 0 = dense slab, 1 = compact pair form
     need(value == 0 || value == 1, "operator must be 0 (dense) or 1 (pairs)");
     ctx->operator_mode = (int)value;
     ctx->hs[0].assembled = ctx->hs[1].assembled = false;

@@ -89,6 +89,7 @@ struct PairPlan {
 };
 void pair_plan_build(PairPlan &p, int nobj, int n, int world, int rank, int sm_count);
 void pair_plan_release(PairPlan &p);
+void pair_plan_tuning(int kb, int groups);
 size_t pair_storage_elems(PairPlan const &p);
 void launch_matvec_pairs(PairPlan const &p, const cplx *AB, const cplx *x, const cplx *Tdiag, cplx *acc_or_y,
                          int finalize, cudaStream_t st, cudaEvent_t e0 = nullptr, cudaEvent_t e1 = nullptr);

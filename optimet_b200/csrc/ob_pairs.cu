@@ -340,6 +340,12 @@ void pair_plan_release(PairPlan &p) {
   p = PairPlan();
 }
 
+static int g_pairs_kb = 0, g_pairs_groups = 0; // tuning overrides (ob_set_option "pairs_kb" / "pairs_groups"); 0 = auto
+void pair_plan_tuning(int kb, int groups) {
+  g_pairs_kb = kb;
+  g_pairs_groups = groups;
+}
+
 void pair_plan_build(PairPlan &p, int nobj, int n, int world, int rank, int sm_count) {
   pair_plan_release(p);
   p.nobj = nobj;
@@ -351,9 +357,13 @@ void pair_plan_build(PairPlan &p, int nobj, int n, int world, int rank, int sm_c
   p.npairs = Ploc;
   // pipeline geometry: KB columns per stage, as many stages as fit next to the reduction scratch
   p.KB = n >= 160 ? 4 : 8;
+  if(g_pairs_kb > 0)
+    p.KB = g_pairs_kb;
   if(p.KB > n)
     p.KB = n;
   p.G = std::max(1, std::min(OB_PAIR_CONSUMERS / n, p.KB));
+  if(g_pairs_groups > 0)
+    p.G = std::max(1, std::min(g_pairs_groups, p.G));
   const size_t stage = ((size_t)2 * p.KB * n + 4 * p.KB) * sizeof(cplx);
   const size_t scratch = (size_t)2 * p.G * 2 * n * sizeof(cplx);
   const size_t budget = 220 * 1024;
