@@ -6,7 +6,7 @@
 #include <string>
 #include <vector>
 
-#define OB_VTAC_THREADS 512
+#define OB_VTAC_THREADS 384
 #define OB_MAX_NMAX 13           // shared-memory limit of the VTAC level buffers (2 x T(nMax) x 16 B <= 227 KB)
 #define OB_MAX_FLAT (13 * 15)    // nMax (nMax + 2) at OB_MAX_NMAX
 

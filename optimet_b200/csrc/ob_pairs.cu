@@ -356,14 +356,20 @@ void pair_plan_build(PairPlan &p, int nobj, int n, int world, int rank, int sm_c
   const long Ploc = p.p1 - p.p0;
   p.npairs = Ploc;
   // pipeline geometry: KB columns per stage, as many stages as fit next to the reduction scratch
-  p.KB = n >= 160 ? 4 : 8;
-  if(g_pairs_kb > 0)
-    p.KB = g_pairs_kb;
-  if(p.KB > n)
-    p.KB = n;
-  p.G = std::max(1, std::min(OB_PAIR_CONSUMERS / n, p.KB));
+  // column groups G: as many (row, group) lanes as the consumer threads allow; KB = 4 columns per thread and stage
+  // (measured on C4, n = 80: KB 4/8/12/16 -> 4.58/6.14/6.70/6.85 TB/s: short stages are pipeline-sync bound),
+  // shrunk until at least 4 stages fit in shared memory
+  p.G = std::max(1, std::min(OB_PAIR_CONSUMERS / n, 8));
   if(g_pairs_groups > 0)
     p.G = std::max(1, std::min(g_pairs_groups, p.G));
+  p.KB = 4 * p.G;
+  if(g_pairs_kb > 0)
+    p.KB = g_pairs_kb;
+  p.KB = std::min(p.KB, n);
+  p.G = std::min(p.G, p.KB);
+  while(p.KB > p.G && 4 * ((size_t)2 * p.KB * n + 4 * p.KB) * sizeof(cplx) + (size_t)2 * p.G * 2 * n * sizeof(cplx) >
+                          (size_t)215 * 1024)
+    p.KB -= p.G;
   const size_t stage = ((size_t)2 * p.KB * n + 4 * p.KB) * sizeof(cplx);
   const size_t scratch = (size_t)2 * p.G * 2 * n * sizeof(cplx);
   const size_t budget = 220 * 1024;

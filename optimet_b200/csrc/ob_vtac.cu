@@ -45,10 +45,17 @@ void VtacTableSet::build(int NM) {
       am_nm[n * (NM + 1) + m] = h_a_minus(n - 1, m);
     }
   }
-  std::vector<unsigned char> lamOf((L + 1) * (L + 1));
-  for(int l = 0; l <= L; ++l)
-    for(int k = -l; k <= l; ++k)
-      lamOf[l * (l + 1) + k] = (unsigned char)l;
+  // Legendre recurrence coefficients (ob_special.cuh: legendre_norm_m), tabulated
+  std::vector<double> legA((L + 1) * (L + 2) / 2 + 1, 0.0), legB(legA), legD(L + 2, 0.0), legF(L + 2, 0.0);
+  for(int m = 0; m <= L; ++m) {
+    legD[m] = std::sqrt((double)(2 * m + 3));
+    if(m >= 1)
+      legF[m] = -std::sqrt((double)(2 * m + 1) / (double)(2 * m));
+    for(int l = m + 2; l <= L; ++l) {
+      legA[l * (l + 1) / 2 + m] = std::sqrt((double)(4 * l * l - 1) / (double)(l * l - m * m));
+      legB[l * (l + 1) / 2 + m] = std::sqrt((double)((l - 1) * (l - 1) - m * m) / (double)(4 * (l - 1) * (l - 1) - 1));
+    }
+  }
   std::vector<int> off(NM + 2, 0);
   for(int m = 0; m <= NM; ++m)
     off[m + 1] = off[m] + (L - m + 1) * (L - m + 1);
@@ -87,7 +94,10 @@ void VtacTableSet::build(int NM) {
   tb.inv_ap_nm = (const double *)up(inv_ap.data(), inv_ap.size() * 8);
   tb.am_nm = (const double *)up(am_nm.data(), am_nm.size() * 8);
   tb.inv_bp_n = (const double *)up(inv_bp.data(), inv_bp.size() * 8);
-  tb.lamOf = (const unsigned char *)up(lamOf.data(), lamOf.size());
+  tb.legA = (const double *)up(legA.data(), legA.size() * 8);
+  tb.legB = (const double *)up(legB.data(), legB.size() * 8);
+  tb.legD = (const double *)up(legD.data(), legD.size() * 8);
+  tb.legF = (const double *)up(legF.data(), legF.size() * 8);
   tb.off = (const int *)up(off.data(), off.size() * 4);
   tb.rowc = (const double *)up(rowc.data(), rowc.size() * 8);
   tb.colc = (const double *)up(colc.data(), colc.size() * 8);
@@ -136,7 +146,7 @@ struct EmitStore {
   }
 };
 
-__global__ void __launch_bounds__(OB_VTAC_THREADS)
+__global__ void __launch_bounds__(OB_VTAC_THREADS, 2)
 k_assemble(VtacTables tb, const double *__restrict__ xyz, const cplx *__restrict__ Tdiag, cplx k, int row0,
            cplx *__restrict__ S, size_t ld) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -178,7 +188,7 @@ struct EmitPair {
     __stcs(B + (size_t)p * n + r, b);
   }
 };
-__global__ void __launch_bounds__(OB_VTAC_THREADS)
+__global__ void __launch_bounds__(OB_VTAC_THREADS, 2)
 k_assemble_pairs(VtacTables tb, const double *__restrict__ xyz, cplx k, const int2 *__restrict__ pair_ij,
                  cplx *__restrict__ AB) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -336,6 +346,8 @@ k_sca_sum(VtacTables tb, const double *__restrict__ xyz, cplx k, int j0, const c
 // ---------------------------------------------------------------------------------------------
 static void set_smem(const void *fn, size_t bytes) {
   OB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  // several CTAs per SM overlap one block's serial seed phase with another's level march
+  OB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 }
 
 void launch_assemble(VtacTableSet const &ts, const double *xyz, const cplx *Tdiag, cplx k, int nobj, int row0,

@@ -26,10 +26,11 @@ struct VtacTables {
   const double *ap, *am, *bp, *bm;     // a+,a-,b+,b- (TranslationAdditionCoefficients.cpp:35-61), [(L+2)^2] at l(l+1)+k
   const double *inv_ap_nm, *am_nm;     // 1/a+(n-1,m), a-(n-1,m) at n*(NM+1)+m
   const double *inv_bp_n;              // 1/b+(n-1,n-1) at n
-  const unsigned char *lamOf;          // l of triangular index idx = l(l+1)+k, idx < (L+1)^2
   const int *off;                      // chain offsets, [NM+2]
   const double *rowc;                  // per row r=(l,k): fA, fB, t1, t2, u0, u1, u2, pad   (Coupling.cpp:33-37, 43-48)
   const double *colc;                  // per column p=(n,mu): gn, s1, s2, pad
+  const double *legA, *legB;           // Legendre recurrence coefficients at l(l+1)/2+m
+  const double *legD, *legF;           // sqrt(2m+3) and -sqrt((2m+1)/(2m)) at m
 };
 
 __host__ __device__ inline int vtac_buffer_entries(int NM) {
@@ -45,6 +46,7 @@ __host__ __device__ inline size_t vtac_smem_bytes(int NM) {
   b += (size_t)(L + 1) * sizeof(cplx);                          // radial z_l
   b += (size_t)(4 * NM + 1) * sizeof(cplx);                     // phase table
   b += (size_t)((L + 1) * (L + 2) / 2) * sizeof(double);        // Legendre
+  b += (size_t)(NM + 2 + 2) * sizeof(int);                      // chain offsets
   return b;
 }
 
@@ -53,6 +55,7 @@ struct VtacSmem {
   cplx *zl;
   cplx *ph;
   double *nlm;
+  int *offs;
   __device__ VtacSmem(unsigned char *base, int NM) {
     int T = vtac_buffer_entries(NM), L = 2 * NM;
     buf[0] = (cplx *)base;
@@ -60,20 +63,9 @@ struct VtacSmem {
     zl = buf[1] + T;
     ph = zl + (L + 1);
     nlm = (double *)(ph + (4 * NM + 1));
+    offs = (int *)(nlm + (L + 1) * (L + 2) / 2);
   }
 };
-
-// phase-free coefficient R(n, mu, lam, kap) of the current level (buffer G), incl. the mu<0 symmetry
-__device__ __forceinline__ cplx vtac_beta(const cplx *G, const int *off, int n, int mu, int lam, int kap) {
-  int ak = kap < 0 ? -kap : kap;
-  int am = mu < 0 ? -mu : mu;
-  if(lam < 0 || ak > lam || am > n)
-    return mk(0, 0);
-  if(mu >= 0)
-    return G[off[mu] + lam * (lam + 1) + kap];
-  cplx v = G[off[am] + lam * (lam + 1) - kap];
-  return ((mu + kap) & 1) ? cneg(v) : v;
-}
 
 // Runs the whole VTAC computation for displacement (r, theta, phi) and wavenumber k on one CTA and
 // calls emit(p, r, A, B) for every column p = flat(n, mu) and row r = flat(l, k):
@@ -89,7 +81,7 @@ __device__ void vtac_block(VtacTables const &tb, unsigned char *smem_raw, double
   VtacSmem sm(smem_raw, NM);
   const int nrows = flat_max(NM);
 
-  // ---- seeds: radial sequence (one thread), Legendre (one thread per order m), phases ----
+  // ---- seeds: radial sequence (one thread), Legendre (one thread per order m), phases, chain offsets ----
   if(tid == 0) {
     cplx z = cscale(k, r);
     if(regular)
@@ -98,22 +90,22 @@ __device__ void vtac_block(VtacTables const &tb, unsigned char *smem_raw, double
       sph_hankel1(z, L, sm.zl);
   }
   if(tid >= 32 && tid < 32 + L + 1) {
-    int m = tid - 32;
+    // sqrt(4 pi) N_l^m(cos theta), l = m..L, at nlm[l(l+1)/2 + m]; the square-root coefficients come from host tables
+    // (same IEEE operations as computing them here, without the FP64 sqrt/div latency chain)
+    const int m = tid - 32;
     double x = cos(the), s = sin(the);
     if(s < 0)
       s = -s;
-    // out[l] for l=m..L lives at nlm[l(l+1)/2 + m]: strided writes through a small adaptor
     double pmm = 1.0; // sqrt(4 pi) folded in: sqrt(4pi) * sqrt(1/(4pi))
     for(int i = 1; i <= m; ++i)
-      pmm *= -sqrt((double)(2 * i + 1) / (double)(2 * i)) * s;
+      pmm *= __ldg(tb.legF + i) * s;
     sm.nlm[m * (m + 1) / 2 + m] = pmm;
     if(L > m) {
-      double pmmp1 = x * sqrt((double)(2 * m + 3)) * pmm;
+      double pmmp1 = x * __ldg(tb.legD + m) * pmm;
       sm.nlm[(m + 1) * (m + 2) / 2 + m] = pmmp1;
       for(int l = m + 2; l <= L; ++l) {
-        double a = sqrt((double)(4 * l * l - 1) / (double)(l * l - m * m));
-        double b = sqrt((double)((l - 1) * (l - 1) - m * m) / (double)(4 * (l - 1) * (l - 1) - 1));
-        double pll = a * (x * pmmp1 - b * pmm);
+        const double a = __ldg(tb.legA + l * (l + 1) / 2 + m), b = __ldg(tb.legB + l * (l + 1) / 2 + m);
+        const double pll = a * (x * pmmp1 - b * pmm);
         pmm = pmmp1;
         pmmp1 = pll;
         sm.nlm[l * (l + 1) / 2 + m] = pll;
@@ -126,12 +118,14 @@ __device__ void vtac_block(VtacTables const &tb, unsigned char *smem_raw, double
     sincos((double)d * phi, &s, &c);
     sm.ph[tid - 96] = mk(c, s);
   }
+  if(tid >= 192 && tid < 192 + NM + 2)
+    sm.offs[tid - 192] = tb.off[tid - 192];
   __syncthreads();
   {
     cplx *G = sm.buf[0];
     const int sz = (L + 1) * (L + 1);
     for(int idx = tid; idx < sz; idx += nthr) {
-      int lam = tb.lamOf[idx];
+      const int lam = (int)__fsqrt_rn((float)idx); // idx in [lam^2, (lam+1)^2)
       int kap = idx - lam * (lam + 1);
       int ak = kap < 0 ? -kap : kap;
       int sg = kap >= 0 ? lam : lam + kap;
@@ -149,60 +143,69 @@ __device__ void vtac_block(VtacTables const &tb, unsigned char *smem_raw, double
   const int row = tid % gs;
   const int grp = tid / gs;
   const bool row_active = row < nrows && grp < ngroups;
-  int rl = 0, rk = 0;
-  double fA = 0, fB = 0, t1 = 0, t2 = 0, u0 = 0, u1 = 0, u2 = 0;
+  int rl = 1, rk = 0;
+  double rA0 = 0, rA1 = 0, rA2 = 0, rB0 = 0, rB1 = 0, rB2 = 0;
   if(row_active) {
     unflatten(row, rl, rk);
     const double *rc = tb.rowc + 8 * row;
-    fA = rc[0];
-    fB = rc[1];
-    t1 = rc[2];
-    t2 = rc[3];
-    u0 = rc[4];
-    u1 = rc[5];
-    u2 = rc[6];
+    const double fA = rc[0], fB = rc[1];
+    rA0 = fA * (double)(2 * rk); // with beta(n,mu,l,k) (times mu)
+    rA1 = fA * rc[2];            // with beta(n,mu+1,l,k+1)
+    rA2 = fA * rc[3];            // with beta(n,mu-1,l,k-1)
+    rB0 = fB * 2.0 * rc[4];      // with beta(n,mu,l-1,k) (times mu)
+    rB1 = fB * rc[5];            // with beta(n,mu+1,l-1,k+1)
+    rB2 = fB * rc[6];            // with beta(n,mu-1,l-1,k-1)
   }
+  // index bases of this row inside one chain: lam = l and lam = l-1; the mirrored (-kappa) ones serve mu' < 0
+  const int b0 = rl * (rl + 1) + rk, b1 = rl * (rl - 1) + rk;
+  const int b0n = b0 - 2 * rk, b1n = b1 - 2 * rk;
+  // validity of kappa' = k + d at lam = l (always for d = 0) and lam = l - 1; an invalid entry always meets an
+  // exactly-zero coefficient (the square roots in Coupling.cpp:33-37, 43-48 vanish there), it only must not be read
+  const bool vP0 = rk < rl, vM0 = rk > -rl, vZ1 = (rk < rl) && (rk > -rl), vP1 = rk <= rl - 2, vM1 = rk >= 2 - rl;
 
   auto compute_level = [&](int n) {
     const int Ln = L - n;
     const int sz = (Ln + 1) * (Ln + 1);
     const int items = (n + 1) * sz;
+    const float inv_sz = 1.0f / (float)sz;
     cplx *dstb = sm.buf[n & 1];
     const cplx *src = sm.buf[(n - 1) & 1];
+    const double inv_bp = __ldg(tb.inv_bp_n + n);
     for(int it = tid; it < items; it += nthr) {
-      int m = it / sz;
-      int idx = it - m * sz;
-      int lam = tb.lamOf[idx];
-      int kap = idx - lam * (lam + 1);
+      const int m = __float2int_rz(((float)it + 0.5f) * inv_sz);
+      const int idx = it - m * sz;
+      const int lam = (int)__fsqrt_rn((float)idx);
+      const int kap = idx - lam * (lam + 1);
       cplx v = mk(0, 0);
-      int up = (lam + 1) * (lam + 2) + kap, dn = (lam - 1) * lam + kap;
+      const int up = idx + 2 * lam + 2, dn = idx - 2 * lam; // (lam+1, kap) and (lam-1, kap)
       if(m == n) { // sectorial step (TranslationAdditionCoefficients.cpp:113-117)
-        const cplx *s = src + tb.off[n - 1];
-        int k1 = kap - 1;
+        const cplx *s = src + sm.offs[n - 1];
+        const int k1 = kap - 1;
         if(lam >= 1 && (k1 < 0 ? -k1 : k1) <= lam - 1)
           v = cscale(s[dn - 1], __ldg(tb.bp + dn - 1));
-        cplx w = s[up - 1];
-        double c = __ldg(tb.bm + up - 1);
+        const cplx w = s[up - 1];
+        const double c = __ldg(tb.bm + up - 1);
         v.x = fma(w.x, c, v.x);
         v.y = fma(w.y, c, v.y);
-        v = cscale(v, __ldg(tb.inv_bp_n + n));
+        v = cscale(v, inv_bp);
       } else { // general step (:119-124)
-        const cplx *s = src + tb.off[m];
+        const int om = sm.offs[m];
+        const cplx *s = src + om;
         if((kap < 0 ? -kap : kap) <= lam - 1)
           v = cscale(s[dn], __ldg(tb.ap + dn));
-        cplx w = s[up];
-        double c = __ldg(tb.am + up);
+        const cplx w = s[up];
+        const double c = __ldg(tb.am + up);
         v.x = fma(w.x, c, v.x);
         v.y = fma(w.y, c, v.y);
         if(n - 2 >= m) {
-          cplx o = dstb[tb.off[m] + idx];
-          double a = __ldg(tb.am_nm + n * (NM + 1) + m);
+          const cplx o = dstb[om + idx];
+          const double a = __ldg(tb.am_nm + n * (NM + 1) + m);
           v.x = fma(-o.x, a, v.x);
           v.y = fma(-o.y, a, v.y);
         }
         v = cscale(v, __ldg(tb.inv_ap_nm + n * (NM + 1) + m));
       }
-      dstb[tb.off[m] + idx] = v;
+      dstb[sm.offs[m] + idx] = v;
     }
   };
 
@@ -210,31 +213,52 @@ __device__ void vtac_block(VtacTables const &tb, unsigned char *smem_raw, double
     if(!row_active)
       return;
     const cplx *G = sm.buf[n & 1];
-    const int l = rl, kk = rk;
+    const int pbase = n * (n + 1) - 1; // flat(n, mu) = pbase - mu
     for(int mu = n - grp; mu >= -n; mu -= ngroups) {
-      const int p = flat_index(n, mu);
+      const int p = pbase - mu;
       const double *cc = tb.colc + 4 * p;
       const double gn = __ldg(cc), s1 = __ldg(cc + 1), s2 = __ldg(cc + 2);
-      // A (Coupling.cpp:30-38)
-      cplx b0 = vtac_beta(G, tb.off, n, mu, l, kk);
-      cplx bpv = vtac_beta(G, tb.off, n, mu + 1, l, kk + 1);
-      cplx bmv = vtac_beta(G, tb.off, n, mu - 1, l, kk - 1);
-      double c0 = (double)(2 * kk * mu), c1 = s1 * t1, c2 = s2 * t2;
-      cplx a;
-      a.x = c0 * b0.x + c1 * bpv.x + c2 * bmv.x;
-      a.y = c0 * b0.y + c1 * bpv.y + c2 * bmv.y;
-      a = cscale(a, fA * gn);
-      // B (Coupling.cpp:40-51): factor -i/2 sqrt(...)
-      cplx g0 = vtac_beta(G, tb.off, n, mu, l - 1, kk);
-      cplx gp = vtac_beta(G, tb.off, n, mu + 1, l - 1, kk + 1);
-      cplx gm = vtac_beta(G, tb.off, n, mu - 1, l - 1, kk - 1);
-      double d0 = (double)(2 * mu) * u0, d1 = s1 * u1, d2 = s2 * u2;
-      cplx b;
-      b.x = d0 * g0.x + d1 * gp.x - d2 * gm.x;
-      b.y = d0 * g0.y + d1 * gp.y - d2 * gm.y;
-      double fb = fB * gn;
-      b = mk(b.y * fb, -b.x * fb); // times -i
-      cplx phs = sm.ph[mu - kk + 2 * NM];
+      // entries with mu' < 0 come from the mirrored entry of chain |mu'| with sign (-1)^(mu'+kappa'); the parity of
+      // mu' + kappa' = 2 mu' + k - mu is the same for mu' = mu-1, mu, mu+1
+      const double flip = ((rk - mu) & 1) ? -1.0 : 1.0;
+      cplx z0 = mk(0, 0), zp = z0, zm = z0, y0 = z0, yp = z0, ym = z0;
+      double k0 = gn * (double)mu, k1 = gn * s1, k2 = gn * s2;
+      { // mu' = mu
+        const int am = mu < 0 ? -mu : mu, o = sm.offs[am];
+        z0 = G[o + (mu >= 0 ? b0 : b0n)];
+        if(vZ1)
+          y0 = G[o + (mu >= 0 ? b1 : b1n)];
+        if(mu < 0)
+          k0 *= flip;
+      }
+      if(mu < n) { // mu' = mu + 1, kappa' = k + 1
+        const int mp = mu + 1, am = mp < 0 ? -mp : mp, o = sm.offs[am];
+        if(vP0)
+          zp = G[o + (mp >= 0 ? b0 + 1 : b0n - 1)];
+        if(vP1)
+          yp = G[o + (mp >= 0 ? b1 + 1 : b1n - 1)];
+        if(mp < 0)
+          k1 *= flip;
+      }
+      if(mu > -n) { // mu' = mu - 1, kappa' = k - 1
+        const int mp = mu - 1, am = mp < 0 ? -mp : mp, o = sm.offs[am];
+        if(vM0)
+          zm = G[o + (mp >= 0 ? b0 - 1 : b0n + 1)];
+        if(vM1)
+          ym = G[o + (mp >= 0 ? b1 - 1 : b1n + 1)];
+        if(mp < 0)
+          k2 *= flip;
+      }
+      // A (Coupling.cpp:30-38) and B (Coupling.cpp:40-51; factor -i/2 sqrt(...))
+      const double ca0 = rA0 * k0, ca1 = rA1 * k1, ca2 = rA2 * k2;
+      const double cb0 = rB0 * k0, cb1 = rB1 * k1, cb2 = -(rB2 * k2);
+      cplx a, b;
+      a.x = ca0 * z0.x + ca1 * zp.x + ca2 * zm.x;
+      a.y = ca0 * z0.y + ca1 * zp.y + ca2 * zm.y;
+      b.x = cb0 * y0.x + cb1 * yp.x + cb2 * ym.x;
+      b.y = cb0 * y0.y + cb1 * yp.y + cb2 * ym.y;
+      b = mk(b.y, -b.x); // times -i
+      const cplx phs = sm.ph[mu - rk + 2 * NM];
       emit.item(p, row, cmul(a, phs), cmul(b, phs));
     }
   };
