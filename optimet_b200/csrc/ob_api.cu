@@ -134,7 +134,9 @@ struct ob_ctx {
   // resident vectors (full length N, replicated)
   DevBuf<cplx> Q, Ksrc, K1ana, Xsca, Xint, XscaSH, XintSH, tmpA, tmpB;
   // GMRES workspace
-  DevBuf<cplx> V, w, h_dev, dot_scratch, ycoef;
+  DevBuf<cplx> V, w, h_dev, dot_scratch, ycoef, arn_partial;
+  DevBuf<unsigned> arn_sync;
+  bool fused_arnoldi = true;
   DevBuf<double> red_d;
   DevBuf<cplx> red_c;
   // instrumentation
@@ -256,18 +258,18 @@ static void assemble(ob_ctx *c, int harmonic) {
 }
 
 // y (full length, replicated) = S x
-static void matvec(ob_ctx *c, int harmonic, const cplx *x, cplx *y) {
+static void matvec(ob_ctx *c, int harmonic, const cplx *x, cplx *y, bool x_staged = false) {
   HarmonicState &H = c->hs[harmonic - 1];
   need(H.assembled, "matrix not assembled (call ob_assemble)");
   if(H.mode == 1) {
     const cplx *T = c->fac[harmonic == 1 ? 0 : 1].p;
     const size_t N = (size_t)c->N(harmonic);
     if(c->world == 1) {
-      launch_matvec_pairs(H.pplan, H.AB.p, x, T, y, 1, c->st, c->evm0, c->evm1);
-      c->launches += 3;
+      launch_matvec_pairs(H.pplan, H.AB.p, x, T, y, 1, c->st, c->evm0, c->evm1, x_staged);
+      c->launches += x_staged ? 2 : 3;
     } else {
       need(c->comm != nullptr, "world > 1 but ob_comm_init has not been called");
-      launch_matvec_pairs(H.pplan, H.AB.p, x, T, H.pplan.acc, 0, c->st, c->evm0, c->evm1);
+      launch_matvec_pairs(H.pplan, H.AB.p, x, T, H.pplan.acc, 0, c->st, c->evm0, c->evm1, x_staged);
       OB_NCCL(g_nccl.AllReduce((const void *)H.pplan.acc, (void *)H.pplan.acc, 2 * N, ncclDouble, ncclSum, c->comm,
                                c->st));
       launch_pairs_finalize(x, T, H.pplan.acc, N, y, c->st);
@@ -294,6 +296,24 @@ static void ensure_gmres_ws(ob_ctx *c, int N, int basis) {
   c->h_dev.alloc(basis + 4);
   c->ycoef.alloc(basis + 4);
   c->dot_scratch.alloc(vec_scratch_elems(N, basis + 2));
+  c->arn_partial.alloc(arnoldi_scratch_elems(N, basis + 2, c->sm_count));
+  if(!c->arn_sync.p) {
+    c->arn_sync.alloc(4);
+    OB_CUDA(cudaMemsetAsync(c->arn_sync.p, 0, 4 * sizeof(unsigned), c->st));
+  }
+}
+
+// one fused Arnoldi step on w against V[0..j]; returns through h_dev (see launch_arnoldi_step)
+static bool use_fused(ob_ctx *c, int N, int basis) {
+  return c->fused_arnoldi && basis + 1 <= 256 && arnoldi_fused_supported(N, c->sm_count);
+}
+static void fused_step(ob_ctx *c, int harmonic, int j, int mode) {
+  const int N = c->N(harmonic);
+  HarmonicState &H = c->hs[harmonic - 1];
+  cplx *XP = H.mode == 1 ? H.pplan.XP : nullptr, *XS = H.mode == 1 ? H.pplan.XS : nullptr;
+  launch_arnoldi_step(c->V.p, N, j, c->w.p, N, mode, c->h_dev.p, c->arn_partial.p, c->arn_sync.p,
+                      c->V.p + (size_t)(j + 1) * N, XP, XS, H.n, c->sm_count, c->st);
+  c->launches += 1;
 }
 
 static double dev_norm(ob_ctx *c, const cplx *v, int N) {
@@ -315,6 +335,7 @@ struct GmresOut {
 static GmresOut gmres_zcomp(ob_ctx *c, int harmonic, const cplx *Y, cplx *x, double tol, int maxit, int no_rest) {
   const int N = c->N(harmonic);
   ensure_gmres_ws(c, N, maxit);
+  const bool fused = use_fused(c, N, maxit);
   cplx *V = c->V.p, *w = c->w.p;
   OB_CUDA(cudaMemsetAsync(x, 0, (size_t)N * sizeof(cplx), c->st));
   const double abs_y = dev_norm(c, Y, N);
@@ -342,23 +363,31 @@ static GmresOut gmres_zcomp(ob_ctx *c, int harmonic, const cplx *Y, cplx *x, dou
     gi.assign(1, hcd(beta, 0));
     int n = 0;
     err_n = 1.0;
+    bool staged = false; // v_n already staged for the pair operator by the previous fused step
     while(n < maxit && err_n > tol) {
-      matvec(c, harmonic, V + (size_t)n * N, w);
-      // modified Gram-Schmidt (:939-943): h_t = v_t^H w ; w -= h_t v_t, sequentially
-      for(int t = 0; t <= n; ++t) {
-        launch_multi_dot(V + (size_t)t * N, 0, 1, w, N, c->h_dev.p + t, c->dot_scratch.p, c->st);
-        launch_multi_axpy(V + (size_t)t * N, 0, 1, c->h_dev.p + t, w, N, c->st);
-        c->launches += 3;
+      matvec(c, harmonic, V + (size_t)n * N, w, staged);
+      // modified Gram-Schmidt (:939-943): h_t = v_t^H w ; w -= h_t v_t, sequentially; then v_{n+1} = w / ||w||
+      if(fused) {
+        fused_step(c, harmonic, n, 1);
+        staged = c->hs[harmonic - 1].mode == 1;
+      } else {
+        for(int t = 0; t <= n; ++t) {
+          launch_multi_dot(V + (size_t)t * N, 0, 1, w, N, c->h_dev.p + t, c->dot_scratch.p, c->st);
+          launch_multi_axpy(V + (size_t)t * N, 0, 1, c->h_dev.p + t, w, N, c->st);
+          c->launches += 3;
+        }
+        launch_multi_dot(w, 0, 1, w, N, c->h_dev.p + n + 1, c->dot_scratch.p, c->st);
+        c->launches += 2;
       }
-      launch_multi_dot(w, 0, 1, w, N, c->h_dev.p + n + 1, c->dot_scratch.p, c->st);
-      c->launches += 2;
       hcol.assign(n + 2, hcd(0, 0));
       OB_CUDA(cudaMemcpyAsync(hcol.data(), c->h_dev.p, (size_t)(n + 2) * sizeof(cplx), cudaMemcpyDeviceToHost, c->st));
       OB_CUDA(cudaStreamSynchronize(c->st));
       const double hn = std::sqrt(hcol[n + 1].real());
       hcol[n + 1] = hn;
-      launch_scale_to(w, 1.0 / hn, V + (size_t)(n + 1) * N, N, c->st);
-      c->launches += 1;
+      if(!fused) {
+        launch_scale_to(w, 1.0 / hn, V + (size_t)(n + 1) * N, N, c->st);
+        c->launches += 1;
+      }
       // Givens exactly as det_approx (:1087-1133): W = [[conj(c), conj(-s)], [s, c]]
       for(int i = 0; i < n; ++i) {
         hcd a = hcol[i], b = hcol[i + 1];
@@ -418,6 +447,7 @@ static GmresOut gmres_belos(ob_ctx *c, int harmonic, const cplx *b, cplx *x, dou
                             int max_restarts) {
   const int N = c->N(harmonic);
   ensure_gmres_ws(c, N, num_blocks);
+  const bool fused = use_fused(c, N, num_blocks);
   cplx *V = c->V.p, *w = c->w.p;
   OB_CUDA(cudaMemcpyAsync(x, b, (size_t)N * sizeof(cplx), cudaMemcpyDeviceToDevice, c->st));
   GmresOut out;
@@ -443,35 +473,48 @@ static GmresOut gmres_belos(ob_ctx *c, int harmonic, const cplx *b, cplx *x, dou
     Rcols.clear();
     g.assign(1, hcd(beta, 0));
     int j = 0;
+    bool staged = false; // v_j already staged for the pair operator by the previous fused step
     while(j < num_blocks && out.iters < max_iters) {
-      matvec(c, harmonic, V + (size_t)j * N, w);
-      // pass 1: classical Gram-Schmidt, all dots at once (+ ||w||^2 as the last "dot")
-      launch_multi_dot(V, N, j + 1, w, N, c->h_dev.p, c->dot_scratch.p, c->st);
-      launch_multi_dot(w, 0, 1, w, N, c->h_dev.p + j + 1, c->dot_scratch.p, c->st);
-      launch_multi_axpy(V, N, j + 1, c->h_dev.p, w, N, c->st);
-      launch_multi_dot(w, 0, 1, w, N, c->h_dev.p + j + 2, c->dot_scratch.p, c->st);
-      c->launches += 7;
-      h.assign(j + 3, hcd(0, 0));
-      OB_CUDA(cudaMemcpyAsync(h.data(), c->h_dev.p, (size_t)(j + 3) * sizeof(cplx), cudaMemcpyDeviceToHost, c->st));
-      OB_CUDA(cudaStreamSynchronize(c->st));
-      const double norm_before = std::sqrt(h[j + 1].real());
-      double norm_after = std::sqrt(h[j + 2].real());
-      h.resize(j + 2);
-      if(norm_after < 0.70710678118654752440 * norm_before) { // DGKS second pass
-        launch_multi_dot(V, N, j + 1, w, N, c->h_dev.p, c->dot_scratch.p, c->st);
-        launch_multi_axpy(V, N, j + 1, c->h_dev.p, w, N, c->st);
-        launch_multi_dot(w, 0, 1, w, N, c->h_dev.p + j + 1, c->dot_scratch.p, c->st);
-        c->launches += 5;
-        hh.assign(j + 2, hcd(0, 0));
-        OB_CUDA(cudaMemcpyAsync(hh.data(), c->h_dev.p, (size_t)(j + 2) * sizeof(cplx), cudaMemcpyDeviceToHost, c->st));
+      matvec(c, harmonic, V + (size_t)j * N, w, staged);
+      double norm_after;
+      if(fused) {
+        // classical Gram-Schmidt + DGKS second pass (decided on the device) + normalisation: one launch
+        fused_step(c, harmonic, j, 0);
+        staged = c->hs[harmonic - 1].mode == 1;
+        h.assign(j + 3, hcd(0, 0));
+        OB_CUDA(cudaMemcpyAsync(h.data(), c->h_dev.p, (size_t)(j + 3) * sizeof(cplx), cudaMemcpyDeviceToHost, c->st));
         OB_CUDA(cudaStreamSynchronize(c->st));
-        for(int t = 0; t <= j; ++t)
-          h[t] += hh[t];
-        norm_after = std::sqrt(hh[j + 1].real());
+        norm_after = std::sqrt(h[j + 2].real());
+        h.resize(j + 2);
+      } else {
+        // pass 1: classical Gram-Schmidt, all dots at once (+ ||w||^2 as the last "dot")
+        launch_multi_dot(V, N, j + 1, w, N, c->h_dev.p, c->dot_scratch.p, c->st);
+        launch_multi_dot(w, 0, 1, w, N, c->h_dev.p + j + 1, c->dot_scratch.p, c->st);
+        launch_multi_axpy(V, N, j + 1, c->h_dev.p, w, N, c->st);
+        launch_multi_dot(w, 0, 1, w, N, c->h_dev.p + j + 2, c->dot_scratch.p, c->st);
+        c->launches += 7;
+        h.assign(j + 3, hcd(0, 0));
+        OB_CUDA(cudaMemcpyAsync(h.data(), c->h_dev.p, (size_t)(j + 3) * sizeof(cplx), cudaMemcpyDeviceToHost, c->st));
+        OB_CUDA(cudaStreamSynchronize(c->st));
+        const double norm_before = std::sqrt(h[j + 1].real());
+        norm_after = std::sqrt(h[j + 2].real());
+        h.resize(j + 2);
+        if(norm_after < 0.70710678118654752440 * norm_before) { // DGKS second pass
+          launch_multi_dot(V, N, j + 1, w, N, c->h_dev.p, c->dot_scratch.p, c->st);
+          launch_multi_axpy(V, N, j + 1, c->h_dev.p, w, N, c->st);
+          launch_multi_dot(w, 0, 1, w, N, c->h_dev.p + j + 1, c->dot_scratch.p, c->st);
+          c->launches += 5;
+          hh.assign(j + 2, hcd(0, 0));
+          OB_CUDA(cudaMemcpyAsync(hh.data(), c->h_dev.p, (size_t)(j + 2) * sizeof(cplx), cudaMemcpyDeviceToHost, c->st));
+          OB_CUDA(cudaStreamSynchronize(c->st));
+          for(int t = 0; t <= j; ++t)
+            h[t] += hh[t];
+          norm_after = std::sqrt(hh[j + 1].real());
+        }
+        launch_scale_to(w, 1.0 / norm_after, V + (size_t)(j + 1) * N, N, c->st);
+        c->launches += 1;
       }
       h[j + 1] = norm_after;
-      launch_scale_to(w, 1.0 / norm_after, V + (size_t)(j + 1) * N, N, c->st);
-      c->launches += 1;
       for(int i = 0; i < j; ++i) {
         hcd a = h[i], bb = h[i + 1];
         h[i] = cs[i] * a + sn[i] * bb;
@@ -1232,6 +1275,8 @@ int ob_set_option(ob_ctx *ctx, const char *name, double value) {
                     ctx->matvec_variant);
   } else if(n == "keep_matrices")
     ctx->keep_matrices = value != 0;
+  else if(n == "fused_arnoldi")
+    ctx->fused_arnoldi = value != 0;
   else if(n == "pairs_kb" || n == "pairs_groups") { // tuning: columns per pipeline stage / column groups (0 = auto)
     static int kb = 0, gr = 0;
     (n == "pairs_kb" ? kb : gr) = (int)value;

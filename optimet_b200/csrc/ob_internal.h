@@ -92,7 +92,8 @@ void pair_plan_release(PairPlan &p);
 void pair_plan_tuning(int kb, int groups);
 size_t pair_storage_elems(PairPlan const &p);
 void launch_matvec_pairs(PairPlan const &p, const cplx *AB, const cplx *x, const cplx *Tdiag, cplx *acc_or_y,
-                         int finalize, cudaStream_t st, cudaEvent_t e0 = nullptr, cudaEvent_t e1 = nullptr);
+                         int finalize, cudaStream_t st, cudaEvent_t e0 = nullptr, cudaEvent_t e1 = nullptr,
+                         bool x_staged = false);
 void launch_pairs_finalize(const cplx *x, const cplx *Tdiag, const cplx *acc, size_t N, cplx *y, cudaStream_t st);
 void launch_pairs_expand_block(PairPlan const &p, const cplx *AB, int i, int j, const cplx *Tdiag, cplx *out,
                                cudaStream_t st);
@@ -112,5 +113,11 @@ void launch_axpby(cplx a, const cplx *x, cplx b, const cplx *y, cplx *z, int N, 
 void launch_combine(const cplx *V, size_t ldv, int j, const cplx *coef_dev, cplx *x, int N, cudaStream_t st); // x += V c
 void launch_hadamard(const cplx *a, const cplx *b, const cplx *c, cplx *out, int N, int conj_out, cudaStream_t st);
 size_t vec_scratch_elems(int N, int jmax);
+// fused Arnoldi step (one cooperative launch): mode 0 = classical GS + DGKS, 1 = modified GS; h_out[0..j] = h,
+// h_out[j+1] = ||w||^2 before, h_out[j+2] = ||w||^2 after; vnext = w / ||w||; optional XP/XS staging (ob_pairs.cu)
+bool arnoldi_fused_supported(int N, int sm_count);
+size_t arnoldi_scratch_elems(int N, int jmax, int sm_count);
+void launch_arnoldi_step(const cplx *V, size_t ldv, int j, cplx *w, int N, int mode, cplx *h_out, cplx *partial,
+                         unsigned *sync, cplx *vnext, cplx *XP, cplx *XS, int n_harm, int sm_count, cudaStream_t st);
 
 } // namespace ob

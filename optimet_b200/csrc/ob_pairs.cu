@@ -457,9 +457,9 @@ size_t pair_storage_elems(PairPlan const &p) { return (size_t)p.npairs * 2 * p.n
 
 // streams the local pairs once; afterwards `acc_or_y` holds either y (finalize) or this rank's partial sums
 void launch_matvec_pairs(PairPlan const &p, const cplx *AB, const cplx *x, const cplx *Tdiag, cplx *acc_or_y,
-                         int finalize, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1) {
+                         int finalize, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, bool x_staged) {
   const int n = p.n;
-  {
+  if(!x_staged) { // XP / XS already written by the fused Arnoldi step that produced x (ob_vec.cu)
     const size_t tot = (size_t)p.nobj * n;
     k_pairs_prepare_x<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(x, p.nobj, n, p.XP, p.XS);
     OB_CUDA(cudaGetLastError());

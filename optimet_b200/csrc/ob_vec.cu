@@ -158,4 +158,315 @@ void launch_hadamard(const cplx *a, const cplx *b, const cplx *c, cplx *out, int
   OB_CUDA(cudaGetLastError());
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Fused Arnoldi step: ONE cooperative launch per GMRES iteration (orthogonalisation of w against v_0..v_j,
+// norm, normalisation into v_{j+1}) instead of 4 + 3 (j + 1) small launches.  The grid is at most one CTA per SM
+// (co-resident by cudaLaunchCooperativeKernel), each thread keeps its <= AR_EPT elements of w in registers, and
+// the grid meets at a self-resetting counter/generation barrier.  All sums have a fixed order (per-thread,
+// warp tree, warps in order, blocks by a warp tree over b): bit-reproducible and identical on every rank.
+//   mode 0: classical Gram-Schmidt with the DGKS second pass decided on the device (Belos "DGKS", restated);
+//   mode 1: modified Gram-Schmidt, one vector at a time (Gmres_Zcomp, srcAna/PreconditionedMatrix.cpp:939-947).
+// h_out: [0..j] = h_t, [j+1] = ||w||^2 before (mode 0), [j+2] = ||w||^2 after orthogonalisation.
+// ---------------------------------------------------------------------------------------------
+#define AR_THREADS 256
+#define AR_EPT 8
+
+struct ArnoldiArgs {
+  const cplx *V;
+  size_t ldv;
+  int j, N, mode, n_harm;
+  cplx *w, *vnext, *h_out, *partial; // partial: [2][(j + 3) * B], row j+2 = norm partials
+  cplx *XP, *XS;                     // optional: pair-operator staging of v_{j+1} (ob_pairs.cu), or null
+  unsigned *sync;                    // [0] arrival counter, [1] generation
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned *sync, unsigned nblocks) {
+  __syncthreads();
+  if(threadIdx.x == 0) {
+    volatile unsigned *gen_p = sync + 1;
+    const unsigned gen = *gen_p;
+    __threadfence();
+    if(atomicAdd(sync, 1u) == nblocks - 1) {
+      sync[0] = 0;
+      __threadfence();
+      atomicAdd(sync + 1, 1u);
+    } else {
+      while(*gen_p == gen) {
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// block-wide sum of NV complex values per thread; result valid in thread 0.. (returned to every thread of warp 0)
+template <int NV> __device__ __forceinline__ void block_sum(cplx (&v)[NV], double *sh /* [8][2 NV] */) {
+#pragma unroll
+  for(int q = 0; q < NV; ++q)
+    for(int o = 16; o > 0; o >>= 1) {
+      v[q].x += __shfl_down_sync(0xffffffffu, v[q].x, o);
+      v[q].y += __shfl_down_sync(0xffffffffu, v[q].y, o);
+    }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads(); // sh reuse
+  if(lane == 0)
+#pragma unroll
+    for(int q = 0; q < NV; ++q) {
+      sh[(warp * NV + q) * 2] = v[q].x;
+      sh[(warp * NV + q) * 2 + 1] = v[q].y;
+    }
+  __syncthreads();
+  if(threadIdx.x < NV) {
+    double r = 0, im = 0;
+    for(int wv = 0; wv < AR_THREADS / 32; ++wv) {
+      r += sh[(wv * NV + threadIdx.x) * 2];
+      im += sh[(wv * NV + threadIdx.x) * 2 + 1];
+    }
+    v[0] = mk(r, im); // thread q holds the total of value q
+  }
+}
+
+// sum over blocks of partial[b], b < B, by warp 0 with a fixed tree; result broadcast through sh_out
+__device__ __forceinline__ cplx sum_over_blocks(const cplx *partial, int B) {
+  // executed by one full warp
+  const int lane = threadIdx.x & 31;
+  double r = 0, im = 0;
+  for(int b = lane; b < B; b += 32) {
+    const cplx p = __ldcg(partial + b);
+    r += p.x;
+    im += p.y;
+  }
+  for(int o = 16; o > 0; o >>= 1) {
+    r += __shfl_down_sync(0xffffffffu, r, o);
+    im += __shfl_down_sync(0xffffffffu, im, o);
+  }
+  r = __shfl_sync(0xffffffffu, r, 0);
+  im = __shfl_sync(0xffffffffu, im, 0);
+  return mk(r, im);
+}
+
+__global__ void __launch_bounds__(AR_THREADS, 1) k_arnoldi_step(ArnoldiArgs a) {
+  __shared__ double sh[8 * 2 * 4];
+  __shared__ cplx hs[260]; // h_t of the current pass (j + 1 <= 256) + scalars
+  __shared__ double s_scal[4];
+  const int B = gridDim.x, b = blockIdx.x, tid = threadIdx.x;
+  const int N = a.N, j = a.j;
+  const int chunk = (N + B - 1) / B;
+  const int i0 = b * chunk, i1 = min(N, i0 + chunk);
+  cplx wv[AR_EPT];
+  int idx[AR_EPT];
+#pragma unroll
+  for(int k = 0; k < AR_EPT; ++k) {
+    idx[k] = i0 + tid + k * AR_THREADS;
+    wv[k] = idx[k] < i1 ? a.w[idx[k]] : mk(0, 0);
+  }
+  cplx *part0 = a.partial, *part1 = a.partial + (size_t)(j + 3) * B;
+  double nb = 0, na = 0;
+
+  auto local_norm2 = [&]() {
+    cplx acc[1] = {mk(0, 0)};
+#pragma unroll
+    for(int k = 0; k < AR_EPT; ++k)
+      if(idx[k] < i1)
+        acc[0].x = fma(wv[k].x, wv[k].x, fma(wv[k].y, wv[k].y, acc[0].x));
+    block_sum<1>(acc, sh);
+    return acc[0];
+  };
+
+  if(a.mode == 0) {
+    // ===== classical Gram-Schmidt (+ DGKS) =====
+    for(int pass = 0; pass < 2; ++pass) {
+      const int T = pass == 0 ? j + 2 : j + 1; // pass 0 also takes ||w||^2 as the "dot" with itself
+      cplx *part = pass == 0 ? part0 : part1;
+      for(int t0 = 0; t0 < T; t0 += 4) {
+        cplx acc[4] = {mk(0, 0), mk(0, 0), mk(0, 0), mk(0, 0)};
+#pragma unroll
+        for(int q = 0; q < 4; ++q) {
+          const int t = t0 + q;
+          if(t < T) {
+#pragma unroll
+            for(int k = 0; k < AR_EPT; ++k)
+              if(idx[k] < i1) {
+                const cplx v = t <= j ? a.V[(size_t)t * a.ldv + idx[k]] : wv[k];
+                acc[q].x = fma(v.x, wv[k].x, acc[q].x);
+                acc[q].x = fma(v.y, wv[k].y, acc[q].x);
+                acc[q].y = fma(v.x, wv[k].y, acc[q].y);
+                acc[q].y = fma(-v.y, wv[k].x, acc[q].y);
+              }
+          }
+        }
+        block_sum<4>(acc, sh);
+        if(tid < 4 && t0 + tid < T)
+          part[(size_t)(t0 + tid) * B + b] = acc[0];
+      }
+      grid_barrier(a.sync, B);
+      // block b sums the partials of t = b, b + B, ... (warp 0), publishes h_t
+      if(tid < 32)
+        for(int t = b; t < T; t += B) {
+          const cplx s = sum_over_blocks(part + (size_t)t * B, B);
+          if(tid == 0)
+            part[(size_t)t * B] = s; // in place: slot 0 of row t now holds the total
+        }
+      grid_barrier(a.sync, B);
+      for(int t = tid; t < T; t += AR_THREADS)
+        hs[t] = __ldcg(part + (size_t)t * B);
+      __syncthreads();
+      if(pass == 0)
+        nb = hs[j + 1].x;
+      // w -= sum_t h_t v_t  (t ascending, as k_multi_axpy)
+#pragma unroll
+      for(int k = 0; k < AR_EPT; ++k)
+        if(idx[k] < i1) {
+          cplx acc = wv[k];
+          for(int t = 0; t <= j; ++t) {
+            const cplx c = hs[t], v = a.V[(size_t)t * a.ldv + idx[k]];
+            acc.x = fma(-c.x, v.x, acc.x);
+            acc.x = fma(c.y, v.y, acc.x);
+            acc.y = fma(-c.x, v.y, acc.y);
+            acc.y = fma(-c.y, v.x, acc.y);
+          }
+          wv[k] = acc;
+        }
+      // ||w||^2 after the pass
+      {
+        const cplx ln = local_norm2();
+        cplx *pn = part + (size_t)(j + 2) * B; // own row: row j+1 (||w||^2 before) may still be read by slower blocks
+        __syncthreads();
+        if(tid == 0)
+          pn[b] = ln;
+        grid_barrier(a.sync, B);
+        if(tid < 32) {
+          const cplx s = sum_over_blocks(pn, B);
+          if(tid == 0)
+            s_scal[0] = s.x;
+        }
+        __syncthreads();
+        na = s_scal[0];
+      }
+      if(b == 0) { // publish / accumulate h
+        for(int t = tid; t <= j; t += AR_THREADS)
+          a.h_out[t] = pass == 0 ? hs[t] : cadd(a.h_out[t], hs[t]);
+        if(tid == 0) {
+          if(pass == 0)
+            a.h_out[j + 1] = mk(nb, 0);
+          a.h_out[j + 2] = mk(na, 0);
+        }
+      }
+      // DGKS: a second pass when the norm dropped by more than 1/sqrt(2)  (uniform over the grid)
+      if(pass == 0 && !(sqrt(na) < 0.70710678118654752440 * sqrt(nb)))
+        break;
+      // pass 1 works in part1 (nothing of part0 is overwritten) and block 0 accumulates h_out with the same threads
+    }
+  } else {
+    // ===== modified Gram-Schmidt =====
+    for(int t = 0; t <= j; ++t) {
+      cplx *part = (t & 1) ? part1 : part0;
+      cplx acc[1] = {mk(0, 0)};
+#pragma unroll
+      for(int k = 0; k < AR_EPT; ++k)
+        if(idx[k] < i1) {
+          const cplx v = a.V[(size_t)t * a.ldv + idx[k]];
+          acc[0].x = fma(v.x, wv[k].x, acc[0].x);
+          acc[0].x = fma(v.y, wv[k].y, acc[0].x);
+          acc[0].y = fma(v.x, wv[k].y, acc[0].y);
+          acc[0].y = fma(-v.y, wv[k].x, acc[0].y);
+        }
+      block_sum<1>(acc, sh);
+      if(tid == 0)
+        part[b] = acc[0];
+      grid_barrier(a.sync, B);
+      if(tid < 32) {
+        const cplx s = sum_over_blocks(part, B);
+        if(tid == 0) {
+          hs[0] = s;
+          if(b == 0)
+            a.h_out[t] = s;
+        }
+      }
+      __syncthreads();
+      const cplx c = hs[0];
+#pragma unroll
+      for(int k = 0; k < AR_EPT; ++k)
+        if(idx[k] < i1) {
+          const cplx v = a.V[(size_t)t * a.ldv + idx[k]];
+          wv[k].x = fma(-c.x, v.x, wv[k].x);
+          wv[k].x = fma(c.y, v.y, wv[k].x);
+          wv[k].y = fma(-c.x, v.y, wv[k].y);
+          wv[k].y = fma(-c.y, v.x, wv[k].y);
+        }
+      __syncthreads(); // hs[0] reuse
+    }
+    {
+      const cplx ln = local_norm2();
+      cplx *pn = (((j + 1) & 1) ? part1 : part0) + (size_t)(j + 2) * B;
+      __syncthreads();
+      if(tid == 0)
+        pn[b] = ln;
+      grid_barrier(a.sync, B);
+      if(tid < 32) {
+        const cplx s = sum_over_blocks(pn, B);
+        if(tid == 0)
+          s_scal[0] = s.x;
+      }
+      __syncthreads();
+      na = s_scal[0];
+      if(b == 0 && tid == 0) {
+        a.h_out[j + 1] = mk(na, 0);
+        a.h_out[j + 2] = mk(na, 0);
+      }
+    }
+  }
+  // ---- w (orthogonalised) back to memory, v_{j+1} = w / ||w|| (+ pair-operator staging of v_{j+1}) ----
+  const double inv = 1.0 / sqrt(na);
+#pragma unroll
+  for(int k = 0; k < AR_EPT; ++k)
+    if(idx[k] < i1) {
+      a.w[idx[k]] = wv[k];
+      const cplx v = cscale(wv[k], inv);
+      a.vnext[idx[k]] = v;
+      if(a.XP) {
+        const int n = a.n_harm, p = idx[k] / (2 * n), e = idx[k] - p * 2 * n, half = e / n, c = e - half * n;
+        int l = (int)sqrt((double)c + 1.0);
+        while(l * l > c + 1)
+          --l;
+        while((l + 1) * (l + 1) <= c + 1)
+          ++l;
+        const double sg = (l & 1) ? -1.0 : 1.0;
+        const size_t o = ((size_t)p * n + c) * 2 + half;
+        a.XP[o] = v;
+        a.XS[o] = mk(sg * v.x, sg * v.y);
+      }
+    }
+}
+
+bool arnoldi_fused_supported(int N, int sm_count) {
+  const int B = std::max(1, std::min(sm_count, (N + AR_THREADS - 1) / AR_THREADS));
+  return (N + B - 1) / B <= AR_THREADS * AR_EPT;
+}
+size_t arnoldi_scratch_elems(int N, int jmax, int sm_count) { return (size_t)2 * (jmax + 3) * sm_count + 16; }
+
+void launch_arnoldi_step(const cplx *V, size_t ldv, int j, cplx *w, int N, int mode, cplx *h_out, cplx *partial,
+                         unsigned *sync, cplx *vnext, cplx *XP, cplx *XS, int n_harm, int sm_count, cudaStream_t st) {
+  if(j + 1 > 256)
+    throw Error("fused Arnoldi step: Krylov basis larger than 256");
+  ArnoldiArgs a;
+  a.V = V;
+  a.ldv = ldv;
+  a.j = j;
+  a.N = N;
+  a.mode = mode;
+  a.n_harm = n_harm;
+  a.w = w;
+  a.vnext = vnext;
+  a.h_out = h_out;
+  a.partial = partial;
+  a.XP = XP;
+  a.XS = XS;
+  a.sync = sync;
+  const int B = std::max(1, std::min(sm_count, (N + AR_THREADS - 1) / AR_THREADS));
+  void *args[] = {&a};
+  OB_CUDA(cudaLaunchCooperativeKernel((const void *)k_arnoldi_step, dim3(B), dim3(AR_THREADS), args, 0, st));
+}
+
 } // namespace ob

@@ -193,3 +193,28 @@ def test_pair_operator_matvec_many_blocks(gpu_ctx, nobj, nMax, harmonic):
     yd = gpu_ctx.matvec(harmonic, x)
     gpu_ctx.set_option("operator", 1)
     assert U.relerr(yd, O.matvec(So, x)) < 1e-12
+
+
+@pytest.mark.parametrize("flavour", ["zcomp", "belos"])
+def test_fused_arnoldi_step_matches_unfused(gpu_ctx, flavour):
+    """The single-launch cooperative Arnoldi step (csrc/ob_vec.cu: k_arnoldi_step) against the multi-launch path:
+    same iteration count, same iterate up to summation-order rounding; both against the oracle's flavour."""
+    spec = U.random_cluster(9, 5, seed=21)
+    orc = U.oracle_case(spec)
+    U.configure_ctx(gpu_ctx, spec, orc)
+    gpu_ctx.assemble(1)
+    So, Q = orc.matrix(1), orc.source()
+    if flavour == "zcomp":
+        opts = ob.GmresOpts(ob.OB_GMRES_ZCOMP, 1e-10, 200, 0, 2)
+        xo, ito, _ = O.solve_dense(So, Q, O.SOLVER_ZCOMP, tol=1e-10, maxit=200, max_restarts=2)
+    else:
+        opts = ob.GmresOpts(ob.OB_GMRES_BELOS, 1e-10, 300, 12, 30)  # short cycles: exercises restarts
+        xo, ito, _ = O.solve_dense(So, Q, O.SOLVER_BELOS, tol=1e-10, maxit=300, restart=12, max_restarts=30)
+    res = {}
+    for fused in (1, 0):
+        gpu_ctx.set_option("fused_arnoldi", fused)
+        res[fused] = gpu_ctx.solve(1, Q, opts)
+    gpu_ctx.set_option("fused_arnoldi", 1)
+    assert abs(res[1][1] - res[0][1]) <= 1 and abs(res[1][1] - ito) <= 1
+    assert U.relerr(res[1][0], res[0][0]) < 1e-9
+    assert U.relerr(res[1][0], xo) < 1e-8
