@@ -2187,11 +2187,30 @@ int orc_case_cross_sections(void *h, double out[5]) {
 }
 // generic dense helpers for tests / baselines
 int orc_matvec(const double *S, long rows, long cols, const double *x, double *y) {
-  CMat M(rows, cols);
-  memcpy(M.a.data(), S, (size_t)rows * cols * sizeof(cd));
-  std::vector<cd> xv((cd *)x, (cd *)x + cols);
-  std::vector<cd> yv = matvec_dense(M, xv);
-  memcpy(y, yv.data(), yv.size() * sizeof(cd));
+  // y = S x on the caller's column-major buffer (no copy), threads over row chunks, explicit real arithmetic
+  // (std::complex operator* goes through __muldc3 without -fcx-limited-range): the CPU baseline of bench.py
+  const cd *M = (const cd *)S;
+  const cd *xv = (const cd *)x;
+  cd *yv = (cd *)y;
+  int nt = std::max(1, g_threads);
+  size_t chunk = ((size_t)rows + nt - 1) / nt;
+  parallel_for(nt, [&](int t) {
+    size_t r0 = t * chunk, r1 = std::min((size_t)rows, r0 + chunk);
+    if(r0 >= r1)
+      return;
+    std::vector<double> re(r1 - r0, 0.0), im(r1 - r0, 0.0);
+    for(long j = 0; j < cols; ++j) {
+      const double xr = xv[j].real(), xi = xv[j].imag();
+      const double *col = (const double *)(M + (size_t)j * rows + r0);
+      for(size_t i = 0; i < r1 - r0; ++i) {
+        const double ar = col[2 * i], ai = col[2 * i + 1];
+        re[i] += ar * xr - ai * xi;
+        im[i] += ar * xi + ai * xr;
+      }
+    }
+    for(size_t i = 0; i < r1 - r0; ++i)
+      yv[r0 + i] = cd(re[i], im[i]);
+  });
   return 0;
 }
 int orc_solve_dense(const double *S, long n, const double *rhs, int solver, const double *opts, double *x, int *iters,
