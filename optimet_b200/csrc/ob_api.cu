@@ -146,6 +146,10 @@ struct ob_ctx {
   int operator_mode = 1; // 0 = dense slab (reference layout), 1 = compact pair form (default)
   bool keep_matrices = true;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm0 = nullptr, evm1 = nullptr, evt0 = nullptr, evt1 = nullptr;
+  // matvec timing without a host sync per apply: a pool of event pairs, read back lazily (flush_matvec_timing)
+  std::vector<cudaEvent_t> mv_ev;
+  int mv_ev_used = 0;
+  hcd *h_pinned = nullptr; // pinned staging for the per-iteration Hessenberg column read-back
 
   int N(int h) const { return 2 * hs[h - 1].n * nobj; }
   int Mloc(int h) const { return 2 * hs[h - 1].n * count; }
@@ -257,19 +261,34 @@ static void assemble(ob_ctx *c, int harmonic) {
   H.assembled = true;
 }
 
+static void flush_matvec_timing(ob_ctx *c) {
+  for(int i = 0; i < c->mv_ev_used; i += 2) {
+    cudaEventSynchronize(c->mv_ev[i + 1]);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->mv_ev[i], c->mv_ev[i + 1]);
+    c->tim[7] += ms;
+    c->tim[8] += 1;
+  }
+  c->mv_ev_used = 0;
+}
+
 // y (full length, replicated) = S x
 static void matvec(ob_ctx *c, int harmonic, const cplx *x, cplx *y, bool x_staged = false) {
   HarmonicState &H = c->hs[harmonic - 1];
   need(H.assembled, "matrix not assembled (call ob_assemble)");
+  if(c->mv_ev_used + 2 > (int)c->mv_ev.size())
+    flush_matvec_timing(c);
+  cudaEvent_t evm0 = c->mv_ev[c->mv_ev_used], evm1 = c->mv_ev[c->mv_ev_used + 1];
+  c->mv_ev_used += 2;
   if(H.mode == 1) {
     const cplx *T = c->fac[harmonic == 1 ? 0 : 1].p;
     const size_t N = (size_t)c->N(harmonic);
     if(c->world == 1) {
-      launch_matvec_pairs(H.pplan, H.AB.p, x, T, y, 1, c->st, c->evm0, c->evm1, x_staged);
+      launch_matvec_pairs(H.pplan, H.AB.p, x, T, y, 1, c->st, evm0, evm1, x_staged);
       c->launches += x_staged ? 2 : 3;
     } else {
       need(c->comm != nullptr, "world > 1 but ob_comm_init has not been called");
-      launch_matvec_pairs(H.pplan, H.AB.p, x, T, H.pplan.acc, 0, c->st, c->evm0, c->evm1, x_staged);
+      launch_matvec_pairs(H.pplan, H.AB.p, x, T, H.pplan.acc, 0, c->st, evm0, evm1, x_staged);
       OB_NCCL(g_nccl.AllReduce((const void *)H.pplan.acc, (void *)H.pplan.acc, 2 * N, ncclDouble, ncclSum, c->comm,
                                c->st));
       launch_pairs_finalize(x, T, H.pplan.acc, N, y, c->st);
@@ -277,17 +296,11 @@ static void matvec(ob_ctx *c, int harmonic, const cplx *x, cplx *y, bool x_stage
     }
     c->tim[10] = 16.0 * (double)pair_storage_elems(H.pplan) + 32.0 * (double)N;
   } else {
-    launch_matvec(H.plan, H.S.p, x, y + (size_t)c->first * 2 * H.n, c->st, c->evm0, c->evm1);
+    launch_matvec(H.plan, H.S.p, x, y + (size_t)c->first * 2 * H.n, c->st, evm0, evm1);
     c->launches += matvec_launches_per_apply(H.plan);
     allgather_slices(c, y, 2 * H.n);
     c->tim[10] = 16.0 * (double)c->Mloc(harmonic) * (double)c->N(harmonic) + 32.0 * (double)c->N(harmonic);
   }
-  // timing of the matvec alone (device events); syncing here is harmless: the driver syncs per iteration anyway
-  cudaEventSynchronize(c->evm1);
-  float ms = 0;
-  cudaEventElapsedTime(&ms, c->evm0, c->evm1);
-  c->tim[7] += ms;
-  c->tim[8] += 1;
 }
 
 static void ensure_gmres_ws(ob_ctx *c, int N, int basis) {
@@ -379,9 +392,9 @@ static GmresOut gmres_zcomp(ob_ctx *c, int harmonic, const cplx *Y, cplx *x, dou
         launch_multi_dot(w, 0, 1, w, N, c->h_dev.p + n + 1, c->dot_scratch.p, c->st);
         c->launches += 2;
       }
-      hcol.assign(n + 2, hcd(0, 0));
-      OB_CUDA(cudaMemcpyAsync(hcol.data(), c->h_dev.p, (size_t)(n + 2) * sizeof(cplx), cudaMemcpyDeviceToHost, c->st));
+      OB_CUDA(cudaMemcpyAsync(c->h_pinned, c->h_dev.p, (size_t)(n + 2) * sizeof(cplx), cudaMemcpyDeviceToHost, c->st));
       OB_CUDA(cudaStreamSynchronize(c->st));
+      hcol.assign(c->h_pinned, c->h_pinned + n + 2);
       const double hn = std::sqrt(hcol[n + 1].real());
       hcol[n + 1] = hn;
       if(!fused) {
@@ -481,9 +494,9 @@ static GmresOut gmres_belos(ob_ctx *c, int harmonic, const cplx *b, cplx *x, dou
         // classical Gram-Schmidt + DGKS second pass (decided on the device) + normalisation: one launch
         fused_step(c, harmonic, j, 0);
         staged = c->hs[harmonic - 1].mode == 1;
-        h.assign(j + 3, hcd(0, 0));
-        OB_CUDA(cudaMemcpyAsync(h.data(), c->h_dev.p, (size_t)(j + 3) * sizeof(cplx), cudaMemcpyDeviceToHost, c->st));
+        OB_CUDA(cudaMemcpyAsync(c->h_pinned, c->h_dev.p, (size_t)(j + 3) * sizeof(cplx), cudaMemcpyDeviceToHost, c->st));
         OB_CUDA(cudaStreamSynchronize(c->st));
+        h.assign(c->h_pinned, c->h_pinned + j + 3);
         norm_after = std::sqrt(h[j + 2].real());
         h.resize(j + 2);
       } else {
@@ -571,6 +584,10 @@ static GmresOut solve_dev(ob_ctx *c, int harmonic, const cplx *rhs, cplx *x, con
   need(o != nullptr, "ob_gmres_opts is NULL");
   c->tmpA.alloc(c->N(harmonic));
   GmresOut r;
+  struct Flush { // matvec timings are read back when the solve ends (also on the error path)
+    ob_ctx *c;
+    ~Flush() { flush_matvec_timing(c); }
+  } flush_guard{c};
   if(o->flavour == OB_GMRES_ZCOMP)
     r = gmres_zcomp(c, harmonic, rhs, x, o->tol, o->max_iters, o->max_restarts);
   else if(o->flavour == OB_GMRES_BELOS) {
@@ -780,6 +797,10 @@ int ob_create(int device, ob_ctx **out) {
     OB_CUDA(cudaEventCreate(&c->evm1));
     OB_CUDA(cudaEventCreate(&c->evt0));
     OB_CUDA(cudaEventCreate(&c->evt1));
+    c->mv_ev.resize(128);
+    for(auto &e : c->mv_ev)
+      OB_CUDA(cudaEventCreate(&e));
+    OB_CUDA(cudaMallocHost(&c->h_pinned, 512 * sizeof(hcd)));
     *out = c;
   } catch(std::exception &e) {
     g_create_error = e.what();
@@ -807,6 +828,10 @@ void ob_destroy(ob_ctx *ctx) {
   cudaEventDestroy(ctx->evm1);
   cudaEventDestroy(ctx->evt0);
   cudaEventDestroy(ctx->evt1);
+  for(auto &e : ctx->mv_ev)
+    cudaEventDestroy(e);
+  if(ctx->h_pinned)
+    cudaFreeHost(ctx->h_pinned);
   cudaStream_t st = ctx->st;
   delete ctx;
   cudaStreamDestroy(st);
@@ -1041,6 +1066,7 @@ int ob_matvec(ob_ctx *ctx, int harmonic, const double *x, double *y) {
   ctx->tmpB.alloc(std::max(ctx->N(1), ctx->N(2)));
   matvec(ctx, harmonic, ctx->tmpA.p, ctx->tmpB.p);
   download(ctx, ctx->tmpB.p, y, N);
+  flush_matvec_timing(ctx);
   OB_END
 }
 

@@ -247,7 +247,7 @@ __device__ __forceinline__ cplx sum_over_blocks(const cplx *partial, int B) {
 }
 
 __global__ void __launch_bounds__(AR_THREADS, 1) k_arnoldi_step(ArnoldiArgs a) {
-  __shared__ double sh[8 * 2 * 4];
+  __shared__ double sh[8 * 2 * 8];
   __shared__ cplx hs[260]; // h_t of the current pass (j + 1 <= 256) + scalars
   __shared__ double s_scal[4];
   const int B = gridDim.x, b = blockIdx.x, tid = threadIdx.x;
@@ -279,52 +279,62 @@ __global__ void __launch_bounds__(AR_THREADS, 1) k_arnoldi_step(ArnoldiArgs a) {
     for(int pass = 0; pass < 2; ++pass) {
       const int T = pass == 0 ? j + 2 : j + 1; // pass 0 also takes ||w||^2 as the "dot" with itself
       cplx *part = pass == 0 ? part0 : part1;
-      for(int t0 = 0; t0 < T; t0 += 4) {
-        cplx acc[4] = {mk(0, 0), mk(0, 0), mk(0, 0), mk(0, 0)};
+      for(int t0 = 0; t0 < T; t0 += 8) {
+        cplx acc[8];
 #pragma unroll
-        for(int q = 0; q < 4; ++q) {
-          const int t = t0 + q;
-          if(t < T) {
+        for(int q = 0; q < 8; ++q)
+          acc[q] = mk(0, 0);
 #pragma unroll
-            for(int k = 0; k < AR_EPT; ++k)
-              if(idx[k] < i1) {
-                const cplx v = t <= j ? a.V[(size_t)t * a.ldv + idx[k]] : wv[k];
-                acc[q].x = fma(v.x, wv[k].x, acc[q].x);
-                acc[q].x = fma(v.y, wv[k].y, acc[q].x);
-                acc[q].y = fma(v.x, wv[k].y, acc[q].y);
-                acc[q].y = fma(-v.y, wv[k].x, acc[q].y);
-              }
+        for(int k = 0; k < AR_EPT; ++k)
+          if(idx[k] < i1) {
+            cplx v[8]; // eight independent loads in flight per element
+#pragma unroll
+            for(int q = 0; q < 8; ++q) {
+              const int t = t0 + q;
+              v[q] = t <= j ? a.V[(size_t)t * a.ldv + idx[k]] : (t < T ? wv[k] : mk(0, 0));
+            }
+#pragma unroll
+            for(int q = 0; q < 8; ++q) {
+              acc[q].x = fma(v[q].x, wv[k].x, acc[q].x);
+              acc[q].x = fma(v[q].y, wv[k].y, acc[q].x);
+              acc[q].y = fma(v[q].x, wv[k].y, acc[q].y);
+              acc[q].y = fma(-v[q].y, wv[k].x, acc[q].y);
+            }
           }
-        }
-        block_sum<4>(acc, sh);
-        if(tid < 4 && t0 + tid < T)
+        block_sum<8>(acc, sh);
+        if(tid < 8 && t0 + tid < T)
           part[(size_t)(t0 + tid) * B + b] = acc[0];
       }
       grid_barrier(a.sync, B);
-      // block b sums the partials of t = b, b + B, ... (warp 0), publishes h_t
-      if(tid < 32)
-        for(int t = b; t < T; t += B) {
-          const cplx s = sum_over_blocks(part + (size_t)t * B, B);
-          if(tid == 0)
-            part[(size_t)t * B] = s; // in place: slot 0 of row t now holds the total
-        }
-      grid_barrier(a.sync, B);
-      for(int t = tid; t < T; t += AR_THREADS)
-        hs[t] = __ldcg(part + (size_t)t * B);
+      // every block sums all T rows itself (warp w takes rows w, w + 8, ...; fixed tree over b): T * B partials
+      // from L2 per block instead of a second grid-wide barrier
+      for(int t = tid >> 5; t < T; t += AR_THREADS / 32) {
+        const cplx s = sum_over_blocks(part + (size_t)t * B, B);
+        if((tid & 31) == 0)
+          hs[t] = s;
+      }
       __syncthreads();
       if(pass == 0)
         nb = hs[j + 1].x;
-      // w -= sum_t h_t v_t  (t ascending, as k_multi_axpy)
+      // w -= sum_t h_t v_t  (t ascending, as k_multi_axpy); loads issued eight at a time
 #pragma unroll
       for(int k = 0; k < AR_EPT; ++k)
         if(idx[k] < i1) {
           cplx acc = wv[k];
-          for(int t = 0; t <= j; ++t) {
-            const cplx c = hs[t], v = a.V[(size_t)t * a.ldv + idx[k]];
-            acc.x = fma(-c.x, v.x, acc.x);
-            acc.x = fma(c.y, v.y, acc.x);
-            acc.y = fma(-c.x, v.y, acc.y);
-            acc.y = fma(-c.y, v.x, acc.y);
+          for(int t0 = 0; t0 <= j; t0 += 8) {
+            cplx v[8];
+#pragma unroll
+            for(int q = 0; q < 8; ++q)
+              v[q] = t0 + q <= j ? a.V[(size_t)(t0 + q) * a.ldv + idx[k]] : mk(0, 0);
+#pragma unroll
+            for(int q = 0; q < 8; ++q)
+              if(t0 + q <= j) {
+                const cplx c = hs[t0 + q];
+                acc.x = fma(-c.x, v[q].x, acc.x);
+                acc.x = fma(c.y, v[q].y, acc.x);
+                acc.y = fma(-c.x, v[q].y, acc.y);
+                acc.y = fma(-c.y, v[q].x, acc.y);
+              }
           }
           wv[k] = acc;
         }
