@@ -16,8 +16,10 @@ operator, Belos-style GMRES tol 1e-5 / restart 30 / <= 20 restarts.  The same to
 N (strong scaling); rows of particles are sharded across ranks.  `--workload c5` runs the 1000-sphere
 nMax = 10 cluster (8 GPUs).
 
-The matrix (16.4 GB per harmonic) is far larger than the 126 MB L2, so consecutive matvecs / steps
-cannot hit in L2 (config.l2: "inputs larger than L2").
+Operator form: `--operator pairs` (default) streams the compact pair form (unscaled A^T, B^T of the pairs
+i < j: 4.08 GB per harmonic on C4), `--operator dense` the reference's full slab (16.4 GB).  Either is far
+larger than the 126 MB L2, so consecutive matvecs / steps cannot hit in L2 (config.l2: "inputs larger than
+L2").  The roofline numerator is the bytes of the form actually streamed.
 """
 import argparse
 import ctypes as C
