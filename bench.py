@@ -347,10 +347,13 @@ def main():
             v, sample = cpu_reference_time(wl, threads, st[0], st[1])
             out["cpu_baseline"] = {"value": v, "unit": "s", "cores": threads, "kind": "port", "sample": sample}
         tr = os.path.join(ROOT, "profiles", "traffic_matvec.json")
-        if os.path.exists(tr):
+        if os.path.exists(tr) and world == 1:
             try:
                 with open(tr) as f:
-                    out["roofline"]["traffic"] = json.load(f).get("dram_bytes_per_launch")
+                    ent = json.load(f).get("%s_%s" % (args.operator, args.workload))
+                if ent:
+                    out["roofline"]["traffic"] = ent["dram_bytes_per_launch"]
+                    out["roofline"]["traffic_source"] = ent["source"]
             except Exception:
                 pass
         print(json.dumps(out))
