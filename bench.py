@@ -330,7 +330,8 @@ def main():
                        "iters_ff": st[0], "iters_sh": st[1], "l2": "inputs larger than L2",
                        "operator": args.operator,
                        "phases_ms_per_step": {k: acc[k] / args.steps for k in acc
-                                              if k not in ("matvec_count", "launches", "operator_bytes")},
+                                              if k not in ("matvec_count", "launches", "operator_bytes")
+                                              and not (k.startswith("trace_") and acc[k] == 0)},
                        "matvecs_per_step": acc["matvec_count"] / args.steps,
                        "cross_sections": dict(zip(["ext", "sca", "abs", "sca_SH", "abs_SH"], [float(x) for x in cs_t.tolist()])),
                        "wall_s_resident_arm": wall},

@@ -265,7 +265,7 @@ class Context:
         t = (C.c_double * 16)()
         self._lib.ob_timings(self.h, t)
         names = ["factors_source", "assemble_ff", "solve_ff", "source_sh", "assemble_sh", "solve_sh", "cross_sections",
-                 "matvec_ms", "matvec_count", "launches", "operator_bytes"]
+                 "matvec_ms", "matvec_count", "launches", "operator_bytes", "trace_reduce_ms", "trace_arnoldi_ms", "trace_gap_ms"]
         return {k: t[i] for i, k in enumerate(names)}
 
     def set_option(self, name, value):

@@ -147,8 +147,10 @@ struct ob_ctx {
   bool keep_matrices = true;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm0 = nullptr, evm1 = nullptr, evt0 = nullptr, evt1 = nullptr;
   // matvec timing without a host sync per apply: a pool of event pairs, read back lazily (flush_matvec_timing)
-  std::vector<cudaEvent_t> mv_ev;
+  std::vector<cudaEvent_t> mv_ev; // 4 per apply: kernel start, kernel end, [trace: after reduce, after Arnoldi step]
   int mv_ev_used = 0;
+  bool trace = false;             // "trace_iterations": GPU-timeline breakdown of a GMRES iteration into tim[11..13]
+  std::vector<char> mv_ev_arn;    // whether slot 3 of an entry was recorded
   hcd *h_pinned = nullptr; // pinned staging for the per-iteration Hessenberg column read-back
 
   int N(int h) const { return 2 * hs[h - 1].n * nobj; }
@@ -262,12 +264,26 @@ static void assemble(ob_ctx *c, int harmonic) {
 }
 
 static void flush_matvec_timing(ob_ctx *c) {
-  for(int i = 0; i < c->mv_ev_used; i += 2) {
+  for(int i = 0; i < c->mv_ev_used; i += 4) {
     cudaEventSynchronize(c->mv_ev[i + 1]);
     float ms = 0;
     cudaEventElapsedTime(&ms, c->mv_ev[i], c->mv_ev[i + 1]);
     c->tim[7] += ms;
     c->tim[8] += 1;
+    if(c->trace) {
+      cudaEventSynchronize(c->mv_ev[i + 2]);
+      cudaEventElapsedTime(&ms, c->mv_ev[i + 1], c->mv_ev[i + 2]);
+      c->tim[11] += ms; // streaming kernel end -> operator result complete (reduce / all-reduce / finalize)
+      if(c->mv_ev_arn[i / 4]) {
+        cudaEventSynchronize(c->mv_ev[i + 3]);
+        cudaEventElapsedTime(&ms, c->mv_ev[i + 2], c->mv_ev[i + 3]);
+        c->tim[12] += ms; // -> Arnoldi step done
+        if(i + 4 < c->mv_ev_used) {
+          cudaEventElapsedTime(&ms, c->mv_ev[i + 3], c->mv_ev[i + 4]);
+          c->tim[13] += ms; // -> next streaming kernel starts (read-back, host sync, Givens, launch latency)
+        }
+      }
+    }
   }
   c->mv_ev_used = 0;
 }
@@ -276,10 +292,12 @@ static void flush_matvec_timing(ob_ctx *c) {
 static void matvec(ob_ctx *c, int harmonic, const cplx *x, cplx *y, bool x_staged = false) {
   HarmonicState &H = c->hs[harmonic - 1];
   need(H.assembled, "matrix not assembled (call ob_assemble)");
-  if(c->mv_ev_used + 2 > (int)c->mv_ev.size())
+  if(c->mv_ev_used + 4 > (int)c->mv_ev.size())
     flush_matvec_timing(c);
   cudaEvent_t evm0 = c->mv_ev[c->mv_ev_used], evm1 = c->mv_ev[c->mv_ev_used + 1];
-  c->mv_ev_used += 2;
+  cudaEvent_t ev_done = c->mv_ev[c->mv_ev_used + 2];
+  c->mv_ev_arn[c->mv_ev_used / 4] = 0;
+  c->mv_ev_used += 4;
   if(H.mode == 1) {
     const cplx *T = c->fac[harmonic == 1 ? 0 : 1].p;
     const size_t N = (size_t)c->N(harmonic);
@@ -301,6 +319,8 @@ static void matvec(ob_ctx *c, int harmonic, const cplx *x, cplx *y, bool x_stage
     allgather_slices(c, y, 2 * H.n);
     c->tim[10] = 16.0 * (double)c->Mloc(harmonic) * (double)c->N(harmonic) + 32.0 * (double)c->N(harmonic);
   }
+  if(c->trace)
+    cudaEventRecord(ev_done, c->st);
 }
 
 static void ensure_gmres_ws(ob_ctx *c, int N, int basis) {
@@ -327,6 +347,10 @@ static void fused_step(ob_ctx *c, int harmonic, int j, int mode) {
   launch_arnoldi_step(c->V.p, N, j, c->w.p, N, mode, c->h_dev.p, c->arn_partial.p, c->arn_sync.p,
                       c->V.p + (size_t)(j + 1) * N, XP, XS, H.n, c->sm_count, c->st);
   c->launches += 1;
+  if(c->trace && c->mv_ev_used >= 4) {
+    cudaEventRecord(c->mv_ev[c->mv_ev_used - 1], c->st);
+    c->mv_ev_arn[c->mv_ev_used / 4 - 1] = 1;
+  }
 }
 
 static double dev_norm(ob_ctx *c, const cplx *v, int N) {
@@ -797,7 +821,8 @@ int ob_create(int device, ob_ctx **out) {
     OB_CUDA(cudaEventCreate(&c->evm1));
     OB_CUDA(cudaEventCreate(&c->evt0));
     OB_CUDA(cudaEventCreate(&c->evt1));
-    c->mv_ev.resize(128);
+    c->mv_ev.resize(256);
+    c->mv_ev_arn.assign(64, 0);
     for(auto &e : c->mv_ev)
       OB_CUDA(cudaEventCreate(&e));
     OB_CUDA(cudaMallocHost(&c->h_pinned, 512 * sizeof(hcd)));
@@ -1301,6 +1326,8 @@ int ob_set_option(ob_ctx *ctx, const char *name, double value) {
                     ctx->matvec_variant);
   } else if(n == "keep_matrices")
     ctx->keep_matrices = value != 0;
+  else if(n == "trace_iterations")
+    ctx->trace = value != 0;
   else if(n == "fused_arnoldi")
     ctx->fused_arnoldi = value != 0;
   else if(n == "pairs_kb" || n == "pairs_groups") { // tuning: columns per pipeline stage / column groups (0 = auto)

@@ -264,14 +264,14 @@ __global__ void k_pairs_prepare_x(const cplx *__restrict__ x, int nobj, int n, c
 
 // acc_p = sum of the row-side partials of the segments of row p (segment order) + the column-side partials of the
 // local pairs (i, p), i ascending.  finalize != 0: y_p = x_p - T_p .* acc_p written directly (single rank).
-#define OB_REDUCE_THREADS 512
+#define OB_REDUCE_THREADS 1024
 __global__ void __launch_bounds__(OB_REDUCE_THREADS)
 k_pairs_reduce(const cplx *__restrict__ rowpart, const cplx *__restrict__ colpart, const int *__restrict__ row_seg,
-               const int2 *__restrict__ col_range, const long *__restrict__ col_first, int nobj, int n,
+               const int2 *__restrict__ col_range, long p0, int nobj, int n,
                const cplx *__restrict__ x, const cplx *__restrict__ Tdiag, cplx *__restrict__ out, int finalize) {
   // One CTA per particle p.  The up-to-(nobj-1) column-side partials of p are split over `parts` thread groups,
-  // each thread keeps 4 independent running sums (the loads are latency-bound: a serial chain of 199 L2 reads cost
-  // 36 us per apply before); everything is combined in a fixed order (slot 0..3, then part 0..parts-1).
+  // each thread keeps 8 independent running sums (the loads are latency-bound: a serial chain of 199 L2 reads cost
+  // 36 us per apply before); everything is combined in a fixed order (slots pairwise, then part 0..parts-1).
   __shared__ cplx sh[OB_REDUCE_THREADS];
   const int p = blockIdx.x;
   const int n2 = 2 * n;
@@ -283,7 +283,7 @@ k_pairs_reduce(const cplx *__restrict__ rowpart, const cplx *__restrict__ colpar
   for(int eb = 0; eb < n2; eb += (int)blockDim.x) { // n2 <= blockDim.x in practice: one trip
     const int e = n2 <= (int)blockDim.x ? e0 : eb + (int)threadIdx.x;
     const bool live = e < n2 && (n2 > (int)blockDim.x || part < parts);
-    cplx a0 = mk(0, 0), a1 = a0, a2 = a0, a3 = a0;
+    cplx a0 = mk(0, 0), a1 = a0, a2 = a0, a3 = a0, a4 = a0, a5 = a0, a6 = a0, a7 = a0;
     if(live) {
       const int stride = n2 <= (int)blockDim.x ? parts : 1, first = n2 <= (int)blockDim.x ? part : 0;
       int k = first;
@@ -291,19 +291,27 @@ k_pairs_reduce(const cplx *__restrict__ rowpart, const cplx *__restrict__ colpar
         if(t < s1 - s0)
           return rowpart[(size_t)(s0 + t) * n2 + e];
         const int i = cr.x + (t - (s1 - s0));
-        return colpart[(size_t)(col_first[i] + (p - i - 1)) * n2 + e];
+        // local index of pair (i, p): its global index i nobj - i (i + 1) / 2 + (p - i - 1) minus the rank's p0
+        const long q = (long)i * nobj - (long)i * (i + 1) / 2 + (p - i - 1) - p0;
+        return colpart[(size_t)q * n2 + e];
       };
-      for(; k + 3 * stride < nterms; k += 4 * stride) {
+      for(; k + 7 * stride < nterms; k += 8 * stride) {
         const cplx v0 = term(k), v1 = term(k + stride), v2 = term(k + 2 * stride), v3 = term(k + 3 * stride);
+        const cplx v4 = term(k + 4 * stride), v5 = term(k + 5 * stride), v6 = term(k + 6 * stride),
+                   v7 = term(k + 7 * stride);
         a0 = cadd(a0, v0);
         a1 = cadd(a1, v1);
         a2 = cadd(a2, v2);
         a3 = cadd(a3, v3);
+        a4 = cadd(a4, v4);
+        a5 = cadd(a5, v5);
+        a6 = cadd(a6, v6);
+        a7 = cadd(a7, v7);
       }
       for(; k < nterms; k += stride)
         a0 = cadd(a0, term(k));
     }
-    cplx s = cadd(cadd(a0, a1), cadd(a2, a3));
+    cplx s = cadd(cadd(cadd(a0, a1), cadd(a2, a3)), cadd(cadd(a4, a5), cadd(a6, a7)));
     if(n2 <= (int)blockDim.x) {
       sh[threadIdx.x] = s;
       __syncthreads();
@@ -528,7 +536,7 @@ void launch_matvec_pairs(PairPlan const &p, const cplx *AB, const cplx *x, const
   }
   if(e1)
     cudaEventRecord(e1, st);
-  k_pairs_reduce<<<p.nobj, OB_REDUCE_THREADS, 0, st>>>(p.rowpart, p.colpart, p.row_seg, p.col_range, p.col_first, p.nobj, n, x, Tdiag,
+  k_pairs_reduce<<<p.nobj, OB_REDUCE_THREADS, 0, st>>>(p.rowpart, p.colpart, p.row_seg, p.col_range, p.p0, p.nobj, n, x, Tdiag,
                                         acc_or_y, finalize);
   OB_CUDA(cudaGetLastError());
 }

@@ -384,6 +384,34 @@ k_abs_sh(ShInputs in, int j0, const cplx *__restrict__ Xint, const cplx *__restr
     ds[p] = Xint[(size_t)j * 2 * n + n + p];
   }
   __syncthreads();
+  // radial products of Symbol.cpp:80-141 depend on (Gauss point, n1, n2) only: tabulated once per particle
+  // (the reference -- and the first version of this kernel -- re-evaluates them, with their divisions and the
+  // sqrt(n1 n2 (n1+1)(n2+1)), inside the (k, p, q) loops).  Layout [ii][n1][n2][6], orders 1..nMax.
+  extern __shared__ __align__(16) unsigned char ftab_raw[];
+  cplx *ftab = (cplx *)ftab_raw;
+  for(int e = threadIdx.x; e < 4 * nMax * nMax; e += blockDim.x) {
+    const int ii = e / (nMax * nMax), rem = e - ii * nMax * nMax, n1 = rem / nMax + 1, n2 = rem - (n1 - 1) * nMax + 1;
+    const double r = (R / 2.0) * xi[ii] + R / 2.0;
+    const cplx j1 = fj[ii][n1], j2 = fj[ii][n2], e1 = fd[ii][n1], e2 = fd[ii][n2];
+    const cplx g1 = fg[ii][n1], g2 = fg[ii][n2], h1 = fh[ii][n1], h2 = fh[ii][n2];
+    const double sq12 = sqrt((double)(n1 * n2 * (n1 + 1) * (n2 + 1)));
+    const cplx F_00 = cmul(j1, e2);
+    const cplx F_11 = cmul(g2, g1);
+    const cplx j1j2 = cmul(j1, j2);
+    const cplx F_m1m1 = cscale(j1j2, 1.0 / (r * r));
+    const cplx sym = cadd(cmul(j1, e2), cmul(e1, j2));
+    const cplx F_d00 = cmul(waveK_j1, sym);
+    const cplx F_d11 = cadd(cmul(h1, g2), cmul(h2, g1));
+    const cplx F_dm1m1 = csub(cscale(cmul(waveK_j1, sym), 1.0 / (r * r)), cscale(j1j2, 2.0 / (r * r * r)));
+    cplx *o = ftab + (size_t)e * 6;
+    o[0] = F_d00;
+    o[1] = F_d11;
+    o[2] = cscale(F_dm1m1, sq12);
+    o[3] = F_00;
+    o[4] = F_11;
+    o[5] = cscale(F_m1m1, sq12);
+  }
+  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const cplx pref = cmul(cdiv(mk(-eps0, 0), in.eps_SH[j]), in.gamma[j]); // (-eps_0/eps_j2) gamma
   const cplx ik2 = cdiv(mk(1, 0), cmul(waveK_j1, waveK_j1));
@@ -407,28 +435,20 @@ k_abs_sh(ShInputs in, int j0, const cplx *__restrict__ Xint, const cplx *__restr
         const double Wm1m1 = __ldg(in.tab[4] + t), W11 = __ldg(in.tab[5] + t), W00 = __ldg(in.tab[6] + t);
         const cplx cc = cscale(cmul(c1, cs[q]), W00);
         const cplx ddk = cmul(cmul(d1, ds[q]), ik2);
-        const double sq12 = sqrt((double)(n1 * n2 * (n1 + 1) * (n2 + 1)));
+#pragma unroll
         for(int ii = 0; ii < 4; ++ii) {
-          const double r = (R / 2.0) * xi[ii] + R / 2.0;
-          const cplx j1 = fj[ii][n1], j2 = fj[ii][n2], e1 = fd[ii][n1], e2 = fd[ii][n2];
-          const cplx g1 = fg[ii][n1], g2 = fg[ii][n2], h1 = fh[ii][n1], h2 = fh[ii][n2];
-          // Symbol.cpp:80-141
-          const cplx F_00 = cmul(j1, e2);
-          const cplx F_11 = cmul(g2, g1);
-          const cplx j1j2 = cmul(j1, j2);
-          const cplx F_m1m1 = cscale(j1j2, 1.0 / (r * r));
-          const cplx sym = cadd(cmul(j1, e2), cmul(e1, j2));
-          const cplx F_d00 = cmul(waveK_j1, sym);
-          const cplx F_d11 = cadd(cmul(h1, g2), cmul(h2, g1));
-          const cplx F_dm1m1 = csub(cscale(cmul(waveK_j1, sym), 1.0 / (r * r)), cscale(j1j2, 2.0 / (r * r * r)));
-          // Symbol.cpp:440-451
-          cplx a = cadd(cmul(cc, F_d00), cmul(ddk, cadd(cscale(F_d11, W11), cscale(F_dm1m1, Wm1m1 * sq12))));
-          Xm1[ii] = cadd(Xm1[ii], a);
-          cplx b = cadd(cscale(cmul(cc, F_00), sqJ / r),
-                        cmul(ddk, cadd(cscale(F_11, W11 * sqJ / r), cscale(F_m1m1, Wm1m1 * sq12 * sqJ / r))));
-          Xp1[ii] = cadd(Xp1[ii], b);
+          const cplx *f = ftab + ((size_t)(ii * nMax + (n1 - 1)) * nMax + (n2 - 1)) * 6;
+          // Symbol.cpp:440-451 (the common factor sqrt(J(J+1))/r of the +1 component is applied after the sum)
+          cfma(Xm1[ii], cc, f[0]);
+          cfma(Xm1[ii], ddk, cadd(cscale(f[1], W11), cscale(f[2], Wm1m1)));
+          cfma(Xp1[ii], cc, f[3]);
+          cfma(Xp1[ii], ddk, cadd(cscale(f[4], W11), cscale(f[5], Wm1m1)));
         }
       }
+    }
+    for(int ii = 0; ii < 4; ++ii) {
+      const double r = (R / 2.0) * xi[ii] + R / 2.0;
+      Xp1[ii] = cscale(Xp1[ii], sqJ / r);
     }
     cplx integral = mk(0, 0);
     const cplx cmnSH = Xint_SH[(size_t)j * 2 * ns + kk], dmnSH = Xint_SH[(size_t)j * 2 * ns + ns + kk];
@@ -467,7 +487,10 @@ void launch_abs_sh(ShInputs const &in, int j0, int count, const cplx *Xint, cons
                    cudaStream_t st) {
   if(count <= 0)
     return;
-  k_abs_sh<<<count, 512, 0, st>>>(in, j0, Xint, Xint_SH, out);
+  const size_t ftab_bytes = (size_t)4 * in.nMax * in.nMax * 6 * sizeof(cplx);
+  if(ftab_bytes > 48 * 1024)
+    OB_CUDA(cudaFuncSetAttribute((const void *)k_abs_sh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ftab_bytes));
+  k_abs_sh<<<count, 512, ftab_bytes, st>>>(in, j0, Xint, Xint_SH, out);
   OB_CUDA(cudaGetLastError());
 }
 

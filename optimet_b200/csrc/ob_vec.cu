@@ -184,18 +184,17 @@ struct ArnoldiArgs {
 __device__ __forceinline__ void grid_barrier(unsigned *sync, unsigned nblocks) {
   __syncthreads();
   if(threadIdx.x == 0) {
-    volatile unsigned *gen_p = sync + 1;
-    const unsigned gen = *gen_p;
-    __threadfence();
-    if(atomicAdd(sync, 1u) == nblocks - 1) {
-      sync[0] = 0;
-      __threadfence();
-      atomicAdd(sync + 1, 1u);
+    unsigned gen, prev, cur;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(sync + 1) : "memory");
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(sync) : "memory");
+    if(prev == nblocks - 1) {
+      asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(sync), "r"(0u) : "memory");
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(sync + 1) : "memory");
     } else {
-      while(*gen_p == gen) {
-      }
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(sync + 1) : "memory");
+      } while(cur == gen);
     }
-    __threadfence();
   }
   __syncthreads();
 }

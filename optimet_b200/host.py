@@ -137,7 +137,7 @@ class Solver:
         t = (C.c_double * 16)()
         capi.load().ob_timings(C.c_void_p(load().obh_solver_ctx(self.s)), t)
         names = ["factors_source", "assemble_ff", "solve_ff", "source_sh", "assemble_sh", "solve_sh", "cross_sections",
-                 "matvec_ms", "matvec_count", "launches", "operator_bytes"]
+                 "matvec_ms", "matvec_count", "launches", "operator_bytes", "trace_reduce_ms", "trace_arnoldi_ms", "trace_gap_ms"]
         return {k: t[i] for i, k in enumerate(names)}
 
     def set_option(self, name, value):
