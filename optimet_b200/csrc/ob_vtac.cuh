@@ -46,7 +46,9 @@ __host__ __device__ inline size_t vtac_smem_bytes(int NM) {
   b += (size_t)(L + 1) * sizeof(cplx);                          // radial z_l
   b += (size_t)(4 * NM + 1) * sizeof(cplx);                     // phase table
   b += (size_t)((L + 1) * (L + 2) / 2) * sizeof(double);        // Legendre
-  b += (size_t)(NM + 2 + 2) * sizeof(int);                      // chain offsets
+  b += (size_t)((NM + 2 + 2 + 1) & ~1) * sizeof(int);            // chain offsets (even count: doubles follow)
+  b += (size_t)2 * (L + 2) * (L + 2) * sizeof(double);          // a+, a- tables of the general step
+  b += (size_t)(((L + 1) * (L + 1) + 15) & ~15);                // lam of a triangular index (bytes)
   return b;
 }
 
@@ -56,6 +58,8 @@ struct VtacSmem {
   cplx *ph;
   double *nlm;
   int *offs;
+  double *aps, *ams;
+  unsigned char *lamS;
   __device__ VtacSmem(unsigned char *base, int NM) {
     int T = vtac_buffer_entries(NM), L = 2 * NM;
     buf[0] = (cplx *)base;
@@ -64,6 +68,9 @@ struct VtacSmem {
     ph = zl + (L + 1);
     nlm = (double *)(ph + (4 * NM + 1));
     offs = (int *)(nlm + (L + 1) * (L + 2) / 2);
+    aps = (double *)(offs + ((NM + 2 + 2 + 1) & ~1));
+    ams = aps + (L + 2) * (L + 2);
+    lamS = (unsigned char *)(ams + (L + 2) * (L + 2));
   }
 };
 
@@ -120,12 +127,18 @@ __device__ void vtac_block(VtacTables const &tb, unsigned char *smem_raw, double
   }
   if(tid >= 192 && tid < 192 + NM + 2)
     sm.offs[tid - 192] = tb.off[tid - 192];
+  for(int e = tid; e < (L + 2) * (L + 2); e += nthr) { // general-step coefficients and the lam lookup, CTA-local
+    sm.aps[e] = __ldg(tb.ap + e);
+    sm.ams[e] = __ldg(tb.am + e);
+    if(e < (L + 1) * (L + 1))
+      sm.lamS[e] = (unsigned char)__fsqrt_rn((float)e); // e in [lam^2, (lam+1)^2)
+  }
   __syncthreads();
   {
     cplx *G = sm.buf[0];
     const int sz = (L + 1) * (L + 1);
     for(int idx = tid; idx < sz; idx += nthr) {
-      const int lam = (int)__fsqrt_rn((float)idx); // idx in [lam^2, (lam+1)^2)
+      const int lam = sm.lamS[idx];
       int kap = idx - lam * (lam + 1);
       int ak = kap < 0 ? -kap : kap;
       int sg = kap >= 0 ? lam : lam + kap;
@@ -163,57 +176,69 @@ __device__ void vtac_block(VtacTables const &tb, unsigned char *smem_raw, double
   // exactly-zero coefficient (the square roots in Coupling.cpp:33-37, 43-48 vanish there), it only must not be read
   const bool vP0 = rk < rl, vM0 = rk > -rl, vZ1 = (rk < rl) && (rk > -rl), vP1 = rk <= rl - 2, vM1 = rk >= 2 - rl;
 
+  // one shared-memory base with arithmetic offsets (a pointer array indexed by n & 1 makes the compiler fall back to
+  // generic loads with 64-bit address arithmetic)
+  cplx *const buf0 = sm.buf[0];
+  const int Tbuf = tb.T;
+
   auto compute_level = [&](int n) {
     const int Ln = L - n;
     const int sz = (Ln + 1) * (Ln + 1);
     const int items = (n + 1) * sz;
-    const float inv_sz = 1.0f / (float)sz;
-    cplx *dstb = sm.buf[n & 1];
-    const cplx *src = sm.buf[(n - 1) & 1];
+    const int dbase = (n & 1) * Tbuf, sbase = ((n - 1) & 1) * Tbuf;
     const double inv_bp = __ldg(tb.inv_bp_n + n);
+    // (m, idx) of item `it`, advanced incrementally: it += nthr  <=>  m += qm, idx += rm (+ carry)
+    const int qm = nthr / sz, rm = nthr - qm * sz;
+    int m = tid / sz, idx = tid - m * sz;
     for(int it = tid; it < items; it += nthr) {
-      const int m = __float2int_rz(((float)it + 0.5f) * inv_sz);
-      const int idx = it - m * sz;
-      const int lam = (int)__fsqrt_rn((float)idx);
+      const int lam = sm.lamS[idx];
       const int kap = idx - lam * (lam + 1);
+      const int ak = kap < 0 ? -kap : kap;
       cplx v = mk(0, 0);
       const int up = idx + 2 * lam + 2, dn = idx - 2 * lam; // (lam+1, kap) and (lam-1, kap)
       if(m == n) { // sectorial step (TranslationAdditionCoefficients.cpp:113-117)
-        const cplx *s = src + sm.offs[n - 1];
+        const int so = sbase + sm.offs[n - 1];
         const int k1 = kap - 1;
         if(lam >= 1 && (k1 < 0 ? -k1 : k1) <= lam - 1)
-          v = cscale(s[dn - 1], __ldg(tb.bp + dn - 1));
-        const cplx w = s[up - 1];
+          v = cscale(buf0[so + dn - 1], __ldg(tb.bp + dn - 1));
+        const cplx w = buf0[so + up - 1];
         const double c = __ldg(tb.bm + up - 1);
         v.x = fma(w.x, c, v.x);
         v.y = fma(w.y, c, v.y);
         v = cscale(v, inv_bp);
       } else { // general step (:119-124)
         const int om = sm.offs[m];
-        const cplx *s = src + om;
-        if((kap < 0 ? -kap : kap) <= lam - 1)
-          v = cscale(s[dn], __ldg(tb.ap + dn));
-        const cplx w = s[up];
-        const double c = __ldg(tb.am + up);
+        const int so = sbase + om;
+        if(ak <= lam - 1)
+          v = cscale(buf0[so + dn], sm.aps[dn]);
+        const cplx w = buf0[so + up];
+        const double c = sm.ams[up];
         v.x = fma(w.x, c, v.x);
         v.y = fma(w.y, c, v.y);
         if(n - 2 >= m) {
-          const cplx o = dstb[om + idx];
+          const cplx o = buf0[dbase + om + idx];
           const double a = __ldg(tb.am_nm + n * (NM + 1) + m);
           v.x = fma(-o.x, a, v.x);
           v.y = fma(-o.y, a, v.y);
         }
         v = cscale(v, __ldg(tb.inv_ap_nm + n * (NM + 1) + m));
       }
-      dstb[sm.offs[m] + idx] = v;
+      buf0[dbase + sm.offs[m] + idx] = v;
+      m += qm;
+      idx += rm;
+      if(idx >= sz) {
+        idx -= sz;
+        ++m;
+      }
     }
   };
 
   auto emit_level = [&](int n) {
     if(!row_active)
       return;
-    const cplx *G = sm.buf[n & 1];
+    const cplx *G = buf0 + (n & 1) * Tbuf;
     const int pbase = n * (n + 1) - 1; // flat(n, mu) = pbase - mu
+#pragma unroll 2
     for(int mu = n - grp; mu >= -n; mu -= ngroups) {
       const int p = pbase - mu;
       const double *cc = tb.colc + 4 * p;
