@@ -344,6 +344,26 @@ def main():
                          "peak_source": peak_src, "traffic": None,
                          "algorithmic_bytes_per_launch": mv_bytes, "avg_launch_ms": float(mv_t.item())},
         }
+        # assembly (north_star: "achieved FP64 FLOP/s against B200 FP64 peak" + store bandwidth).  Algorithmic flops per
+        # VTAC block from SURVEY.md section 8(d) (replay count of the reference recursion); one block per unit
+        # processed: a pair in the pair form, an off-diagonal block in the dense form.
+        F = {3: 15.8e3, 6: 154.5e3, 8: 427.3e3, 10: 960.5e3, 12: 1883.6e3}.get(nMax)
+        asm_ms = 0.5 * (acc["assemble_ff"] + acc["assemble_sh"]) / args.steps
+        if args.operator == "pairs":
+            units = nobj * (nobj - 1) // 2 // world
+            asm_bytes = 32.0 * (n2 // 2) ** 2 * units
+        else:
+            units = count * (nobj - 1)
+            asm_bytes = 16.0 * n2 * n2 * count * nobj
+        fp64 = C.c_double()
+        lib.ob_measure_fp64_peak(ctx, C.byref(fp64))
+        out["assembly"] = {"kernel": "k_assemble_pairs" if args.operator == "pairs" else "k_assemble",
+                           "ms_per_harmonic": asm_ms, "units_per_launch": units, "stored_bytes_per_launch": asm_bytes,
+                           "store_GBps": asm_bytes / (asm_ms * 1e-3) / 1e9,
+                           "algorithmic_flops_per_unit": F,
+                           "achieved_tflops": (units * F / (asm_ms * 1e-3) / 1e12) if F else None,
+                           "fp64_peak_tflops_measured": fp64.value,
+                           "frac_of_fp64_peak": (units * F / (asm_ms * 1e-3) / 1e12 / fp64.value) if F else None}
         if world == 1 and not args.no_cpu_baseline:
             v, sample = cpu_reference_time(wl, threads, st[0], st[1])
             out["cpu_baseline"] = {"value": v, "unit": "s", "cores": threads, "kind": "port", "sample": sample}

@@ -109,11 +109,17 @@ int ob_cross_sections(ob_ctx *ctx, const double *X_sca, const double *X_int, con
 
 /* ---- instrumentation ---- */
 /* device-event timings (ms) of the last ob_run: 0 factors+source, 1 assemble FF, 2 solve FF, 3 SH source,
- * 4 assemble SH, 5 solve SH, 6 cross sections, 7 matvec total (inside solves), 8 matvec count, 9 kernel launches */
+ * 4 assemble SH, 5 solve SH, 6 cross sections, 7 matvec total (streaming kernel only), 8 matvec count,
+ * 9 kernel launches, 10 algorithmic bytes of one operator apply in the form streamed, 11-13 iteration trace */
 int ob_timings(ob_ctx *ctx, double out[16]);
 /* CUDA-event stopwatch on the library's stream: op 0 = start, op 1 = stop (+ synchronise) -> elapsed ms */
 int ob_timer(ob_ctx *ctx, int op, double *ms);
-int ob_set_option(ob_ctx *ctx, const char *name, double value); /* "matvec_variant", "keep_matrices" */
+/* measured FP64 FMA peak of the device in TFLOP/s (DFMA micro-benchmark): the denominator north_star asks for when
+ * the assembly is reported "as achieved FP64 FLOP/s against B200 FP64 peak" */
+int ob_measure_fp64_peak(ob_ctx *ctx, double *tflops);
+/* options: "operator" (0 dense slab | 1 pair form, default), "keep_matrices", "fused_arnoldi", "matvec_variant",
+ * "pairs_kb", "pairs_groups" (tuning), "trace_iterations", "reset_timings" */
+int ob_set_option(ob_ctx *ctx, const char *name, double value);
 
 #ifdef __cplusplus
 }

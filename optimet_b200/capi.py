@@ -26,6 +26,7 @@ SYMBOLS = [
     "ob_inc_local", "ob_assemble", "ob_release_matrix", "ob_fetch_block", "ob_fetch_matrix", "ob_matvec",
     "ob_source_ff", "ob_set_cg_tables", "ob_build_cg_tables", "ob_fetch_cg_table", "ob_source_sh", "ob_solve",
     "ob_unprecondition_ff", "ob_unprecondition_sh", "ob_run", "ob_cross_sections", "ob_timings", "ob_timer", "ob_set_option",
+    "ob_measure_fp64_peak",
 ]
 
 _lib = None
@@ -270,3 +271,8 @@ class Context:
 
     def set_option(self, name, value):
         self._chk(self._lib.ob_set_option(self.h, name.encode(), C.c_double(value)))
+
+    def measure_fp64_peak(self):
+        v = C.c_double()
+        self._chk(self._lib.ob_measure_fp64_peak(self.h, C.byref(v)))
+        return v.value

@@ -1315,6 +1315,12 @@ int ob_timer(ob_ctx *ctx, int op, double *ms) {
   OB_END
 }
 
+int ob_measure_fp64_peak(ob_ctx *ctx, double *tflops) {
+  OB_BEGIN
+  *tflops = measure_fp64_peak(ctx->sm_count, ctx->st);
+  OB_END
+}
+
 int ob_set_option(ob_ctx *ctx, const char *name, double value) {
   OB_BEGIN
   std::string n(name ? name : "");

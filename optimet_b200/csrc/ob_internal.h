@@ -115,6 +115,7 @@ void launch_hadamard(const cplx *a, const cplx *b, const cplx *c, cplx *out, int
 size_t vec_scratch_elems(int N, int jmax);
 // fused Arnoldi step (one cooperative launch): mode 0 = classical GS + DGKS, 1 = modified GS; h_out[0..j] = h,
 // h_out[j+1] = ||w||^2 before, h_out[j+2] = ||w||^2 after; vnext = w / ||w||; optional XP/XS staging (ob_pairs.cu)
+double measure_fp64_peak(int sm_count, cudaStream_t st); // TFLOP/s, DFMA micro-benchmark
 bool arnoldi_fused_supported(int N, int sm_count);
 size_t arnoldi_scratch_elems(int N, int jmax, int sm_count);
 void launch_arnoldi_step(const cplx *V, size_t ldv, int j, cplx *w, int N, int mode, cplx *h_out, cplx *partial,

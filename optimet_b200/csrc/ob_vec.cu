@@ -449,6 +449,47 @@ __global__ void __launch_bounds__(AR_THREADS, 1) k_arnoldi_step(ArnoldiArgs a) {
     }
 }
 
+// FP64 FMA peak of this device, measured (the assembly roofline denominator; MEASURED_PEAKS.json has no FP64 figure):
+// 8 independent DFMA chains per thread, 8 CTAs of 256 threads per SM.
+__global__ void k_dfma_peak(double *out, int iters, double seed) {
+  double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
+  const double m = 1.0000001, c = 1e-9;
+#pragma unroll 4
+  for(int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c);
+    a1 = fma(a1, m, c);
+    a2 = fma(a2, m, c);
+    a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c);
+    a5 = fma(a5, m, c);
+    a6 = fma(a6, m, c);
+    a7 = fma(a7, m, c);
+  }
+  const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if(s == 12345.678)
+    out[0] = s; // never true: keeps the chains alive
+}
+double measure_fp64_peak(int sm_count, cudaStream_t st) {
+  double *d = nullptr;
+  OB_CUDA(cudaMalloc(&d, 8));
+  cudaEvent_t e0, e1;
+  OB_CUDA(cudaEventCreate(&e0));
+  OB_CUDA(cudaEventCreate(&e1));
+  const int iters = 1 << 15, blocks = sm_count * 8, threads = 256;
+  k_dfma_peak<<<blocks, threads, 0, st>>>(d, 1024, 0.5); // warm-up
+  OB_CUDA(cudaEventRecord(e0, st));
+  k_dfma_peak<<<blocks, threads, 0, st>>>(d, iters, 0.5);
+  OB_CUDA(cudaEventRecord(e1, st));
+  OB_CUDA(cudaEventSynchronize(e1));
+  float ms = 0;
+  OB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  const double flops = 2.0 * 8.0 * (double)iters * (double)blocks * (double)threads;
+  return flops / (ms * 1e-3) / 1e12;
+}
+
 bool arnoldi_fused_supported(int N, int sm_count) {
   const int B = std::max(1, std::min(sm_count, (N + AR_THREADS - 1) / AR_THREADS));
   return (N + B - 1) / B <= AR_THREADS * AR_EPT;
