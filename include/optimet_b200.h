@@ -30,11 +30,15 @@ typedef struct ob_ctx ob_ctx;
 /* GMRES flavours.  ZCOMP = the in-tree Gmres_Zcomp (srcAna/PreconditionedMatrix.cpp:892-985:
  * x0 = 0, modified Gram-Schmidt, |g|/||b|| stopping rule, max_iters per cycle, max_restarts cycles).
  * BELOS = Belos "GMRES" as driven by srcAna/scalapack/LinearSystemSolver.hpp:94-142 (x0 = b, DGKS,
- * ||r||/||r0|| rule, restart = "Num Blocks", max_iters = "Maximum Iterations" total). */
-enum { OB_GMRES_ZCOMP = 1, OB_GMRES_BELOS = 2 };
+ * ||r||/||r0|| rule, restart = "Num Blocks", max_iters = "Maximum Iterations" total).
+ * DIRECT = device dense solve (blocked LU, partial pivoting): the counterpart of the serial
+ * S.colPivHouseholderQr().solve(Q) (srcAna/PreconditionedMatrixSolver.h:58,75, taken when ACA is off) and of pzgesv_
+ * (srcAna/ScalapackSolver.cpp:54-128; Solver = "eigen" | "scalapack", srcAna/Solver.cpp:40-43).  One GPU, needs
+ * 16 N^2 bytes; tol / max_iters / restart are ignored, iters = 0 is returned. */
+enum { OB_GMRES_ZCOMP = 1, OB_GMRES_BELOS = 2, OB_SOLVE_DIRECT = 3 };
 
 typedef struct ob_gmres_opts {
-  int flavour;      /* OB_GMRES_ZCOMP | OB_GMRES_BELOS */
+  int flavour;      /* OB_GMRES_ZCOMP | OB_GMRES_BELOS | OB_SOLVE_DIRECT */
   double tol;       /* "Convergence Tolerance" / Gmres_Zcomp tol */
   int max_iters;    /* ZCOMP: maxit per cycle; BELOS: "Maximum Iterations" */
   int restart;      /* BELOS: "Num Blocks" (ignored by ZCOMP) */
@@ -94,6 +98,10 @@ int ob_source_sh(ob_ctx *ctx, const double *Xint_conj, double *K, double *K1ana)
 /* rhs == NULL: use the resident source of that harmonic (Q or K) */
 int ob_solve(ob_ctx *ctx, int harmonic, const double *rhs, double *x, const ob_gmres_opts *opts, int *iters,
              double *relres);
+/* unit-level surface of OB_SOLVE_DIRECT: x = A^-1 b for a caller-supplied N x N column-major complex matrix (the
+ * arithmetic behind Eigen's colPivHouseholderQr().solve, PreconditionedMatrixSolver.h:58, and pzgesv_,
+ * scalapack/LinearSystemSolver.hpp:84-91).  A is not modified; fails with "singular" on an exactly zero pivot. */
+int ob_dense_solve(ob_ctx *ctx, int N, const double *A, const double *b, double *x);
 int ob_unprecondition_ff(ob_ctx *ctx, const double *X_sca, double *X_int);                          /* Solver.cpp:57-77 */
 int ob_unprecondition_sh(ob_ctx *ctx, const double *X_sca_SH, const double *K1ana, double *X_int_SH); /* Solver.cpp:95-116 */
 

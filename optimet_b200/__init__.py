@@ -5,6 +5,6 @@ The product is the C-ABI library ``liboptimet_b200.so`` (hand-written CUDA kerne
 package is only a thin ctypes loader used by tests and ``bench.py``; there is no CPU fallback:
 every compute entry point fails loudly when no CUDA device / extension is available.
 """
-from .capi import (Library, Context, GmresOpts, OB_GMRES_ZCOMP, OB_GMRES_BELOS, lib_path, load)  # noqa: F401
+from .capi import (Library, Context, GmresOpts, OB_GMRES_ZCOMP, OB_GMRES_BELOS, OB_SOLVE_DIRECT, lib_path, load)  # noqa: F401
 
-__all__ = ["Library", "Context", "GmresOpts", "OB_GMRES_ZCOMP", "OB_GMRES_BELOS", "lib_path", "load"]
+__all__ = ["Library", "Context", "GmresOpts", "OB_GMRES_ZCOMP", "OB_GMRES_BELOS", "OB_SOLVE_DIRECT", "lib_path", "load"]

@@ -6,6 +6,7 @@ import numpy as np
 
 OB_GMRES_ZCOMP = 1
 OB_GMRES_BELOS = 2
+OB_SOLVE_DIRECT = 3
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -26,7 +27,7 @@ SYMBOLS = [
     "ob_inc_local", "ob_assemble", "ob_release_matrix", "ob_fetch_block", "ob_fetch_matrix", "ob_matvec",
     "ob_source_ff", "ob_set_cg_tables", "ob_build_cg_tables", "ob_fetch_cg_table", "ob_source_sh", "ob_solve",
     "ob_unprecondition_ff", "ob_unprecondition_sh", "ob_run", "ob_cross_sections", "ob_timings", "ob_timer", "ob_set_option",
-    "ob_measure_fp64_peak",
+    "ob_measure_fp64_peak", "ob_dense_solve",
 ]
 
 _lib = None
@@ -220,6 +221,17 @@ class Context:
         self._chk(self._lib.ob_solve(self.h, int(harmonic), None if r is None else _p(r), _p(x), C.byref(opts),
                                     C.byref(it), C.byref(rr)))
         return x, it.value, rr.value
+
+    def dense_solve(self, A, b):
+        """x = A^-1 b on the device (OB_SOLVE_DIRECT's LU on a caller-supplied matrix)."""
+        A = np.asfortranarray(A, dtype=np.complex128)
+        n = A.shape[0]
+        if A.shape != (n, n):
+            raise ValueError("square matrix expected")
+        bb = _cz(b, n)
+        x = np.zeros(n, dtype=np.complex128)
+        self._chk(self._lib.ob_dense_solve(self.h, int(n), _p(A), _p(bb), _p(x)))
+        return x
 
     def unprecondition_ff(self, X_sca):
         x = _cz(X_sca, self.N(1))

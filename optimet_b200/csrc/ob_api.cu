@@ -135,6 +135,9 @@ struct ob_ctx {
   DevBuf<cplx> Q, Ksrc, K1ana, Xsca, Xint, XscaSH, XintSH, tmpA, tmpB;
   // GMRES workspace
   DevBuf<cplx> V, w, h_dev, dot_scratch, ycoef, arn_partial;
+  // direct solve (ob_lu.cu): dense N x N work matrix, released after each solve
+  DevBuf<cplx> lu_mat;
+  LuWork lu;
   DevBuf<unsigned> arn_sync;
   bool fused_arnoldi = true;
   DevBuf<double> red_d;
@@ -604,8 +607,43 @@ static GmresOut gmres_belos(ob_ctx *c, int harmonic, const cplx *b, cplx *x, dou
   return out;
 }
 
+// Direct dense solve: the serial reference's S.colPivHouseholderQr().solve(Q) (PreconditionedMatrixSolver.h:58,75) and
+// the pzgesv_ route (ScalapackSolver.cpp:54-128).  The dense matrix is assembled into a work buffer (reference layout,
+// -T_i [[A^T,B^T],[B^T,A^T]] with identity diagonal blocks), factorised in place and released.
+static GmresOut direct_solve(ob_ctx *c, int harmonic, const cplx *rhs, cplx *x) {
+  check_harmonic(harmonic);
+  need(c->world == 1, "direct solve runs on one GPU (use a GMRES flavour when the matrix is row-sharded)");
+  need(c->nobj > 0, "ob_set_cluster has not been called");
+  ensure_factors(c);
+  HarmonicState &H = c->hs[harmonic - 1];
+  const size_t N = (size_t)c->N(harmonic);
+  const cplx k = harmonic == 1 ? c->waveK : cscale(c->waveK, 2.0);
+  if(c->lu_mat.n < N * N) {
+    c->lu_mat.release();
+    size_t free_b = 0, total_b = 0;
+    OB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    if((double)N * (double)N * 16.0 + 64e6 > (double)free_b)
+      throw Error("direct solve needs 16 N^2 = " + std::to_string(16.0 * N * N / 1e9) + " GB of device memory, " +
+                  std::to_string(free_b / 1e9) + " GB free: use a GMRES flavour");
+    c->lu_mat.alloc(N * N);
+  }
+  VtacTableSet &ts = tables_for(c, H.nMax);
+  launch_assemble(ts, c->xyz.p, c->fac[harmonic == 1 ? 0 : 1].p, k, c->nobj, 0, c->nobj, c->lu_mat.p, N, c->st);
+  c->launches += 1;
+  const int info = lu_solve(c->lu_mat.p, (int)N, N, c->lu, rhs, x, c->sm_count, c->st, c->launches);
+  if(!c->keep_matrices)
+    c->lu_mat.release();
+  if(info != 0)
+    throw Error("direct solve: the scattering matrix is singular (zero pivot at column " + std::to_string(info) + ")");
+  GmresOut r;
+  r.converged = true;
+  return r;
+}
+
 static GmresOut solve_dev(ob_ctx *c, int harmonic, const cplx *rhs, cplx *x, const ob_gmres_opts *o) {
   need(o != nullptr, "ob_gmres_opts is NULL");
+  if(o->flavour == OB_SOLVE_DIRECT)
+    return direct_solve(c, harmonic, rhs, x);
   c->tmpA.alloc(c->N(harmonic));
   GmresOut r;
   struct Flush { // matvec timings are read back when the solve ends (also on the error path)
@@ -847,6 +885,7 @@ void ob_destroy(ob_ctx *ctx) {
     matvec_plan_release(ctx->hs[i].plan);
     pair_plan_release(ctx->hs[i].pplan);
   }
+  ctx->lu.release();
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   cudaEventDestroy(ctx->evm0);
@@ -1166,6 +1205,21 @@ int ob_solve(ob_ctx *ctx, int harmonic, const double *rhs, double *x, const ob_g
   OB_END
 }
 
+int ob_dense_solve(ob_ctx *ctx, int N, const double *A, const double *b, double *x) {
+  OB_BEGIN
+  need(N > 0 && A && b && x, "ob_dense_solve: bad arguments");
+  DevBuf<cplx> dA, db;
+  dA.alloc((size_t)N * N);
+  db.alloc(N);
+  OB_CUDA(cudaMemcpyAsync(dA.p, A, sizeof(cplx) * (size_t)N * N, cudaMemcpyHostToDevice, ctx->st));
+  OB_CUDA(cudaMemcpyAsync(db.p, b, sizeof(cplx) * (size_t)N, cudaMemcpyHostToDevice, ctx->st));
+  const int info = lu_solve(dA.p, N, (size_t)N, ctx->lu, db.p, db.p, ctx->sm_count, ctx->st, ctx->launches);
+  if(info != 0)
+    throw Error("direct solve: the matrix is singular (zero pivot at column " + std::to_string(info) + ")");
+  download(ctx, db.p, x, N);
+  OB_END
+}
+
 int ob_unprecondition_ff(ob_ctx *ctx, const double *X_sca, double *X_int) {
   OB_BEGIN
   ensure_factors(ctx);
@@ -1223,7 +1277,8 @@ int ob_run(ob_ctx *ctx, const ob_gmres_opts *opts, int do_sh, double *X_sca, dou
     source_ff(ctx);
     t.stop();
   }
-  {
+  const bool direct = opts && opts->flavour == OB_SOLVE_DIRECT; // the LU assembles its own dense work matrix
+  if(!direct) {
     PhaseTimer t(ctx, 1);
     assemble(ctx, 1);
     t.stop();
@@ -1256,7 +1311,7 @@ int ob_run(ob_ctx *ctx, const ob_gmres_opts *opts, int do_sh, double *X_sca, dou
       source_sh(ctx, ctx->tmpA.p);
       t.stop();
     }
-    {
+    if(!direct) {
       PhaseTimer t(ctx, 4);
       assemble(ctx, 2);
       t.stop();

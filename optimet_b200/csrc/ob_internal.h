@@ -101,6 +101,19 @@ void launch_pairs_expand_block(PairPlan const &p, const cplx *AB, int i, int j, 
 void launch_assemble_pairs(VtacTableSet const &ts, const double *xyz, cplx k, const int2 *pair_ij, long npairs,
                            cplx *AB, cudaStream_t st);
 
+// ---- ob_lu.cu (device direct solve: blocked LU with partial pivoting, zgesv-style) ----
+struct LuWork {
+  int cap = 0;
+  int *ipiv = nullptr, *pivrow = nullptr, *info = nullptr, *part_i = nullptr;
+  unsigned *sync = nullptr;
+  double *part_v = nullptr;
+  cplx *Linv = nullptr, *v1 = nullptr, *v2 = nullptr;
+  void alloc(int N, int sm_count);
+  void release();
+};
+int lu_solve(cplx *A, int N, size_t lda, LuWork &w, const cplx *b, cplx *x, int sm_count, cudaStream_t st,
+             long &launches);
+
 // ---- ob_vec.cu (Krylov vector kernels) ----
 // h[t] = v_t^H w for t < j (V is ldv-strided), deterministic two-stage reduction
 void launch_multi_dot(const cplx *V, size_t ldv, int j, const cplx *w, int N, cplx *h_dev, cplx *scratch,

@@ -664,20 +664,28 @@ Run simulation_input(std::string const &fileName_) {
 // ---------------------------------------------------------------------------------------------
 // solver::B200Matrix
 // ---------------------------------------------------------------------------------------------
+// Solver selection of the reference: solver::factory (Solver.cpp:30-54) returns the Belos GMRES solver when the XML
+// carries a Belos list whose "Solver" is neither "eigen" nor "scalapack"; "scalapack" is pzgesv_ (a dense direct
+// solve) and "eigen" / the serial build run PreconditionedMatrix::solve (PreconditionedMatrixSolver.h:45-79):
+// Gmres_Zcomp(tol 1e-6, maxit 240, 2 cycles) when <ACA compression="yes">, else S.colPivHouseholderQr().solve(Q).
 ob_gmres_opts default_gmres(Run const &run) {
   ob_gmres_opts o;
+  o.tol = 1e-6;
+  o.max_iters = 240;
+  o.restart = 0;
+  o.max_restarts = 2;
   if(run.belos_params.present && run.belos_params.solver != "scalapack" && run.belos_params.solver != "eigen") {
     o.flavour = OB_GMRES_BELOS; // scalapack/LinearSystemSolver.hpp:94-142 with the XML list
     o.tol = run.belos_params.tolerance;
     o.max_iters = run.belos_params.max_iterations;
     o.restart = run.belos_params.num_blocks;
     o.max_restarts = run.belos_params.max_restarts;
+  } else if(run.belos_params.present && run.belos_params.solver == "scalapack") {
+    o.flavour = OB_SOLVE_DIRECT; // ScalapackSolver.cpp:54-128 (pzgesv_)
+  } else if(run.geometry && run.geometry->ACA_cond_) {
+    o.flavour = OB_GMRES_ZCOMP; // PreconditionedMatrixSolver.h:50-52,55,72
   } else {
-    o.flavour = OB_GMRES_ZCOMP; // PreconditionedMatrixSolver.h:50-52
-    o.tol = 1e-6;
-    o.max_iters = 240;
-    o.restart = 0;
-    o.max_restarts = 2;
+    o.flavour = OB_SOLVE_DIRECT; // PreconditionedMatrixSolver.h:58,75
   }
   return o;
 }
@@ -688,7 +696,7 @@ B200Matrix::B200Matrix(std::shared_ptr<Geometry> geometry_, std::shared_ptr<Exci
     : geometry(geometry_), incWave(incWave_), ctx(nullptr), tables_set(false) {
   if(ob_create(device, &ctx) != 0)
     throw std::runtime_error(ob_last_error(nullptr));
-  opts.flavour = OB_GMRES_ZCOMP;
+  opts.flavour = (geometry && geometry->ACA_cond_) ? OB_GMRES_ZCOMP : OB_SOLVE_DIRECT; // PreconditionedMatrixSolver.h:55-58
   opts.tol = 1e-6;
   opts.max_iters = 240;
   opts.restart = 0;

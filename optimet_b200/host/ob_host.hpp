@@ -137,8 +137,8 @@ public:
   ~B200Matrix();
   //! multi-GPU: rank/world of this process and the NCCL id broadcast by the host launcher
   void set_communicator(const char uid[128], int rank, int world);
-  //! GMRES options; default follows the reference's serial solver (PreconditionedMatrixSolver.h:50-52) when the
-  //! XML has no Belos list, else the Belos list
+  //! solver options; the default follows the reference's own selection (Solver.cpp:30-54 and
+  //! PreconditionedMatrixSolver.h:45-79): Belos list -> Belos GMRES; ACA on -> Gmres_Zcomp constants; else direct solve
   void set_gmres(ob_gmres_opts const &o) { opts = o; }
   ob_gmres_opts const &gmres() const { return opts; }
 

@@ -165,3 +165,23 @@ def test_bad_inputs_raise_like_the_reference():
     xml = xmlgen.cluster_xml([[0, 0, 0], [0, 0, 90.0]], 50.0, 3, 800.0)  # overlapping spheres: Geometry.cpp:41-49
     with pytest.raises(RuntimeError, match="overlap"):
         H.Case(xml=xml)
+
+
+def test_solver_selection_follows_the_reference_factory():
+    # Solver.cpp:30-54 + PreconditionedMatrixSolver.h:45-79: Belos list (Solver not eigen/scalapack) -> Belos GMRES;
+    # "scalapack" -> pzgesv_ (direct); serial / "eigen": ACA on -> Gmres_Zcomp(1e-6, 240, 2), ACA off -> QR (direct)
+    xyz = [[0, 0, 0], [0, 0, 200.0]]
+
+    def flavour(**kw):
+        return H.Case(xml=xmlgen.cluster_xml(xyz, 50.0, 3, 1240.0, **kw)).gmres_defaults().flavour
+
+    def belos(solver):
+        return [("Solver", "string", solver), ("Convergence Tolerance", "double", "1.0e-5")]
+
+    assert flavour(aca=False) == capi.OB_SOLVE_DIRECT
+    assert flavour(aca=True) == capi.OB_GMRES_ZCOMP
+    assert flavour(aca=False, belos=belos("GMRES")) == capi.OB_GMRES_BELOS
+    assert flavour(aca=True, belos=belos("GMRES")) == capi.OB_GMRES_BELOS
+    assert flavour(aca=True, belos=belos("scalapack")) == capi.OB_SOLVE_DIRECT
+    assert flavour(aca=True, belos=belos("eigen")) == capi.OB_GMRES_ZCOMP
+    assert flavour(aca=False, belos=belos("eigen")) == capi.OB_SOLVE_DIRECT
