@@ -176,8 +176,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c4")
     ap.add_argument("--matvec-variant", type=int, default=None)
-    ap.add_argument("--operator", default="pairs", choices=["pairs", "dense"],
-                    help="pairs: compact A^T/B^T-of-i<j form (default); dense: the reference's full slab")
+    ap.add_argument("--operator", default="pairs", choices=["pairs", "dense", "aca"],
+                    help="pairs: compact A^T/B^T-of-i<j form (default); dense: the reference's full slab; "
+                         "aca: the reference's ACA-compressed operator (eps 1e-3; results differ at that level)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="library tuning option name=value (ob_set_option)")
     args = ap.parse_args()
@@ -232,7 +233,10 @@ def main():
         solver.comm_init(uid[0], rank, world)
     if args.matvec_variant is not None:
         solver.set_option("matvec_variant", args.matvec_variant)
-    solver.set_option("operator", 1 if args.operator == "pairs" else 0)
+    if args.operator == "aca":
+        solver.set_aca_mode(1)
+    else:
+        solver.set_option("operator", 1 if args.operator == "pairs" else 0)
     for opt in args.opt:
         k, v = opt.split("=")
         solver.set_option(k, float(v))
@@ -338,8 +342,9 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_per_step / 1e3, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(acc["launches"]),
-            "roofline": {"bound": "hbm", "kernel": ("k_matvec_pairs (TMA-streamed complex-FP64 pair-form block matvec)" if args.operator == "pairs"
-                                    else "k_matvec (TMA-streamed complex-FP64 dense block matvec)"),
+            "roofline": {"bound": "hbm", "kernel": {"pairs": "k_matvec_pairs (TMA-streamed complex-FP64 pair-form block matvec)",
+                                                    "dense": "k_matvec (TMA-streamed complex-FP64 dense block matvec)",
+                                                    "aca": "k_matvec_aca (complex-FP64 U(Vx) low-rank + dense near blocks)"}[args.operator],
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "traffic": None,
                          "algorithmic_bytes_per_launch": mv_bytes, "avg_launch_ms": float(mv_t.item())},
@@ -352,12 +357,17 @@ def main():
         if args.operator == "pairs":
             units = nobj * (nobj - 1) // 2 // world
             asm_bytes = 32.0 * (n2 // 2) ** 2 * units
+        elif args.operator == "aca":
+            units = count * (nobj - 1)
+            asm_bytes = solver.ctx().aca_stats(1)["stored_bytes"]
+            out["aca"] = solver.ctx().aca_stats(1)
         else:
             units = count * (nobj - 1)
             asm_bytes = 16.0 * n2 * n2 * count * nobj
         fp64 = C.c_double()
         lib.ob_measure_fp64_peak(ctx, C.byref(fp64))
-        out["assembly"] = {"kernel": "k_assemble_pairs" if args.operator == "pairs" else "k_assemble",
+        out["assembly"] = {"kernel": {"pairs": "k_assemble_pairs", "dense": "k_assemble",
+                                      "aca": "k_assemble + k_aca_compress + pack"}[args.operator],
                            "ms_per_harmonic": asm_ms, "units_per_launch": units, "stored_bytes_per_launch": asm_bytes,
                            "store_GBps": asm_bytes / (asm_ms * 1e-3) / 1e9,
                            "algorithmic_flops_per_unit": F,

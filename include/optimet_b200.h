@@ -87,6 +87,20 @@ int ob_fetch_block(ob_ctx *ctx, int harmonic, int i, int j, double *out); /* 2n 
 int ob_fetch_matrix(ob_ctx *ctx, int harmonic, double *out);              /* local slab, (2n count) x N column-major */
 int ob_matvec(ob_ctx *ctx, int harmonic, const double *x, double *y);     /* y = S x, full length N on every rank */
 
+/* ---- ACA-compressed operator (<ACA compression="yes">; ob_set_option("operator", 2) before ob_assemble) ----
+ * Scattering_matrix_ACA_FF / _SH (srcAna/PreconditionedMatrix.cpp:489-551, 699-759): blocks with
+ * distance >= 2 (r_i + r_j) are stored as U (2n x r) V (r x 2n) from ACA_compression (:760-859, eps 1e-3, pivots by
+ * getMaxInd :861-889), near blocks dense, the diagonal as the identity; ob_matvec / ob_solve / ob_run then apply
+ * matvec (:1058-1085).  ob_fetch_block / ob_fetch_matrix are not available in this form.
+ * ob_aca_block: rank > 0: U = 2n x rank column-major, V = rank rows of 2n entries, I / J = pivot rows / columns in the
+ * order taken (may be NULL); rank = -1: dense near block in U (2n x 2n column-major); rank = 0: identity diagonal.
+ * Buffers must hold 2n x 2n complex (U, V) and 2n ints (I, J).  i must be local to this rank. */
+int ob_aca_block(ob_ctx *ctx, int harmonic, int i, int j, int *rank, double *U, double *V, int *I, int *J);
+/* unit surface of ACA_compression(U, V, CoupMat): caller-supplied dim x dim column-major block, same outputs */
+int ob_aca_compress(ob_ctx *ctx, int dim, const double *C, int *rank, double *U, double *V, int *I, int *J);
+/* out: stored bytes, dense-equivalent bytes of the local slab, low-rank blocks, dense near blocks, mean rank, max rank */
+int ob_aca_stats(ob_ctx *ctx, int harmonic, double out[6]);
+
 /* ---- sources (source_vector, source_vectorSH, source_vectorSH_K1ana; PreconditionedMatrix.cpp:1327-1436) ---- */
 int ob_source_ff(ob_ctx *ctx, double *Q);
 int ob_set_cg_tables(ob_ctx *ctx, const double *const tables[9]); /* order of Simulation.cpp:616 */
@@ -125,7 +139,7 @@ int ob_timer(ob_ctx *ctx, int op, double *ms);
 /* measured FP64 FMA peak of the device in TFLOP/s (DFMA micro-benchmark): the denominator north_star asks for when
  * the assembly is reported "as achieved FP64 FLOP/s against B200 FP64 peak" */
 int ob_measure_fp64_peak(ob_ctx *ctx, double *tflops);
-/* options: "operator" (0 dense slab | 1 pair form, default), "keep_matrices", "fused_arnoldi", "matvec_variant",
+/* options: "operator" (0 dense slab | 1 pair form, default | 2 ACA-compressed), "eps_aca" (1e-3), "aca_budget_mb", "keep_matrices", "fused_arnoldi", "matvec_variant",
  * "pairs_kb", "pairs_groups" (tuning), "trace_iterations", "reset_timings" */
 int ob_set_option(ob_ctx *ctx, const char *name, double value);
 

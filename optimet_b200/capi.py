@@ -27,7 +27,7 @@ SYMBOLS = [
     "ob_inc_local", "ob_assemble", "ob_release_matrix", "ob_fetch_block", "ob_fetch_matrix", "ob_matvec",
     "ob_source_ff", "ob_set_cg_tables", "ob_build_cg_tables", "ob_fetch_cg_table", "ob_source_sh", "ob_solve",
     "ob_unprecondition_ff", "ob_unprecondition_sh", "ob_run", "ob_cross_sections", "ob_timings", "ob_timer", "ob_set_option",
-    "ob_measure_fp64_peak", "ob_dense_solve",
+    "ob_measure_fp64_peak", "ob_dense_solve", "ob_aca_block", "ob_aca_compress", "ob_aca_stats",
 ]
 
 _lib = None
@@ -95,9 +95,21 @@ class Context:
         self.nobj = self.nMax = self.nMaxS = 0
         self.rank, self.world = 0, 1
 
+    @classmethod
+    def view(cls, handle, nobj=0, nMax=0, nMaxS=None):
+        """Wrap an ob_ctx owned by someone else (the host solver); close() does not destroy it."""
+        self = cls.__new__(cls)
+        self._lib = load()
+        self.h = C.c_void_p(handle)
+        self._borrowed = True
+        self.nobj, self.nMax, self.nMaxS = nobj, nMax, nMax if nMaxS is None else nMaxS
+        self.rank, self.world = 0, 1
+        return self
+
     def close(self):
         if getattr(self, "h", None):
-            self._lib.ob_destroy(self.h)
+            if not getattr(self, "_borrowed", False):
+                self._lib.ob_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -182,6 +194,41 @@ class Context:
         out = np.zeros((2 * self.n(harmonic) * cnt, self.N(harmonic)), dtype=np.complex128, order="F")
         self._chk(self._lib.ob_fetch_matrix(self.h, int(harmonic), _p(out)))
         return out
+
+    def aca_block(self, harmonic, i, j):
+        """Block (i, j) of the ACA-compressed operator: (rank, U, V, I, J); rank -1 -> dense block in U, 0 -> identity."""
+        b = 2 * self.n(harmonic)
+        U = np.zeros(b * b, dtype=np.complex128)
+        V = np.zeros((b, b), dtype=np.complex128)
+        I = np.zeros(b, dtype=np.int32)
+        J = np.zeros(b, dtype=np.int32)
+        r = C.c_int()
+        self._chk(self._lib.ob_aca_block(self.h, int(harmonic), int(i), int(j), C.byref(r), _p(U), _p(V), _p(I), _p(J)))
+        r = r.value
+        if r < 0:
+            return -1, U.reshape((b, b), order="F"), None, None, None
+        if r == 0:
+            return 0, None, None, None, None
+        return r, U[:b * r].reshape((b, r), order="F"), V[:r].copy(), I[:r].copy(), J[:r].copy()
+
+    def aca_compress(self, block):
+        """ACA_compression of a caller-supplied square block on the device: U (dim x r), V (r x dim), I, J."""
+        Cm = np.asfortranarray(block, dtype=np.complex128)
+        b = Cm.shape[0]
+        U = np.zeros(b * b, dtype=np.complex128)
+        V = np.zeros((b, b), dtype=np.complex128)
+        I = np.zeros(b, dtype=np.int32)
+        J = np.zeros(b, dtype=np.int32)
+        r = C.c_int()
+        self._chk(self._lib.ob_aca_compress(self.h, int(b), _p(Cm), C.byref(r), _p(U), _p(V), _p(I), _p(J)))
+        r = r.value
+        return U[:b * r].reshape((b, r), order="F"), V[:r].copy(), I[:r].copy(), J[:r].copy()
+
+    def aca_stats(self, harmonic):
+        out = (C.c_double * 6)()
+        self._chk(self._lib.ob_aca_stats(self.h, int(harmonic), out))
+        return dict(stored_bytes=out[0], dense_bytes=out[1], lowrank_blocks=int(out[2]), dense_blocks=int(out[3]),
+                    mean_rank=out[4], max_rank=int(out[5]))
 
     def matvec(self, harmonic, x):
         x = _cz(x, self.N(harmonic))

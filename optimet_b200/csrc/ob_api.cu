@@ -97,7 +97,8 @@ struct HarmonicState {
   bool assembled = false;
   MatvecPlan plan;
   // pair form (ob_pairs.cu): unscaled A^T, B^T of the local pairs i < j
-  int mode = 0; // operator form this harmonic was assembled in (0 dense, 1 pairs)
+  int mode = 0; // operator form this harmonic was assembled in (0 dense, 1 pairs, 2 ACA-compressed)
+  AcaOperator aca;
   DevBuf<cplx> AB;
   PairPlan pplan;
   int pplan_world = -1, pplan_rank = -1;
@@ -117,6 +118,9 @@ struct ob_ctx {
   // cluster
   int nobj = 0, nMax = 0, nMaxS = 0, first = 0, count = 0; // local particle rows [first, first+count)
   DevBuf<double> xyz, radius;
+  std::vector<double> h_xyz, h_radius; // host copies: ACA admissibility test (PreconditionedMatrix.cpp:526)
+  double eps_aca = 1e-3;               // PreconditionedMatrix.cpp:772
+  size_t aca_budget = (size_t)4 << 30; // scratch bytes of one ACA assembly batch
   // frequency / materials
   bool have_freq = false, have_inc = false;
   double omega = 0;
@@ -146,7 +150,7 @@ struct ob_ctx {
   double tim[16] = {0};
   long launches = 0;
   int matvec_variant = 0;
-  int operator_mode = 1; // 0 = dense slab (reference layout), 1 = compact pair form (default)
+  int operator_mode = 1; // 0 = dense slab (reference layout), 1 = compact pair form (default), 2 = ACA-compressed
   bool keep_matrices = true;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm0 = nullptr, evm1 = nullptr, evt0 = nullptr, evt1 = nullptr;
   // matvec timing without a host sync per apply: a pool of event pairs, read back lazily (flush_matvec_timing)
@@ -249,6 +253,7 @@ static void assemble(ob_ctx *c, int harmonic) {
       H.pplan_rank = c->rank;
     }
     H.S.release();
+    H.aca.release();
     H.AB.alloc(std::max<size_t>(1, pair_storage_elems(H.pplan)));
     launch_assemble_pairs(ts, c->xyz.p, H.k, H.pplan.pair_ij, H.pplan.npairs, H.AB.p, c->st);
     c->launches += 1;
@@ -257,6 +262,15 @@ static void assemble(ob_ctx *c, int harmonic) {
     return;
   }
   H.AB.release();
+  if(c->operator_mode == 2) { // Scattering_matrix_ACA_FF / _SH (PreconditionedMatrix.cpp:489-551, 699-759)
+    H.S.release();
+    aca_build(H.aca, ts, c->xyz.p, c->fac[harmonic == 1 ? 0 : 1].p, H.k, c->nobj, c->first, c->count, c->h_xyz.data(),
+              c->h_radius.data(), c->eps_aca, c->aca_budget, c->sm_count, c->st, c->launches);
+    H.mode = 2;
+    H.assembled = true;
+    return;
+  }
+  H.aca.release();
   H.mode = 0;
   H.S.alloc(M * N);
   launch_assemble(ts, c->xyz.p, c->fac[harmonic == 1 ? 0 : 1].p, H.k, c->nobj, c->first, c->count, H.S.p, M, c->st);
@@ -316,6 +330,11 @@ static void matvec(ob_ctx *c, int harmonic, const cplx *x, cplx *y, bool x_stage
       c->launches += 4;
     }
     c->tim[10] = 16.0 * (double)pair_storage_elems(H.pplan) + 32.0 * (double)N;
+  } else if(H.mode == 2) { // matvec of PreconditionedMatrix.cpp:1058-1085 on the compressed blocks
+    launch_matvec_aca(H.aca, x, y + (size_t)c->first * 2 * H.n, c->st, evm0, evm1);
+    c->launches += H.aca.nch > 1 ? 2 : 1;
+    allgather_slices(c, y, 2 * H.n);
+    c->tim[10] = 16.0 * H.aca.stored_elems + 32.0 * (double)c->N(harmonic);
   } else {
     launch_matvec(H.plan, H.S.p, x, y + (size_t)c->first * 2 * H.n, c->st, evm0, evm1);
     c->launches += matvec_launches_per_apply(H.plan);
@@ -884,6 +903,7 @@ void ob_destroy(ob_ctx *ctx) {
     ctx->tabs[i].release();
     matvec_plan_release(ctx->hs[i].plan);
     pair_plan_release(ctx->hs[i].pplan);
+    ctx->hs[i].aca.release();
   }
   ctx->lu.release();
   cudaEventDestroy(ctx->ev0);
@@ -967,6 +987,8 @@ int ob_set_cluster(ob_ctx *ctx, int nobj, const double *xyz_m, const double *rad
   ctx->hs[1].nMax = nMaxS;
   ctx->hs[1].n = flat_max(nMaxS);
   partition(nobj, ctx->world, ctx->rank, ctx->first, ctx->count);
+  ctx->h_xyz.assign(xyz_m, xyz_m + 3 * (size_t)nobj);
+  ctx->h_radius.assign(radius_m, radius_m + nobj);
   ctx->xyz.alloc(3 * (size_t)nobj);
   ctx->radius.alloc(nobj);
   OB_CUDA(cudaMemcpyAsync(ctx->xyz.p, xyz_m, 3 * (size_t)nobj * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
@@ -1069,6 +1091,7 @@ int ob_release_matrix(ob_ctx *ctx, int harmonic) {
   check_harmonic(harmonic);
   ctx->hs[harmonic - 1].S.release();
   ctx->hs[harmonic - 1].AB.release();
+  ctx->hs[harmonic - 1].aca.release();
   ctx->hs[harmonic - 1].assembled = false;
   OB_END
 }
@@ -1078,6 +1101,7 @@ int ob_fetch_block(ob_ctx *ctx, int harmonic, int i, int j, double *out) {
   check_harmonic(harmonic);
   HarmonicState &H = ctx->hs[harmonic - 1];
   need(H.assembled, "matrix not assembled");
+  need(H.mode != 2, "the ACA-compressed operator holds no dense blocks: use ob_aca_block");
   if(H.mode == 1) {
     need(i >= 0 && i < ctx->nobj && j >= 0 && j < ctx->nobj, "block index out of range");
     const size_t b2 = (size_t)4 * H.n * H.n;
@@ -1101,6 +1125,7 @@ int ob_fetch_matrix(ob_ctx *ctx, int harmonic, double *out) {
   check_harmonic(harmonic);
   HarmonicState &H = ctx->hs[harmonic - 1];
   need(H.assembled, "matrix not assembled");
+  need(H.mode != 2, "the ACA-compressed operator holds no dense matrix: use ob_aca_block");
   if(H.mode == 1) { // rebuild the dense reference layout block by block (tests; single rank only)
     need(ctx->world == 1, "ob_fetch_matrix in pair form needs world == 1");
     const size_t b = 2 * (size_t)H.n, ld = (size_t)ctx->N(harmonic);
@@ -1119,6 +1144,77 @@ int ob_fetch_matrix(ob_ctx *ctx, int harmonic, double *out) {
     return 0;
   }
   download(ctx, H.S.p, out, (size_t)ctx->Mloc(harmonic) * ctx->N(harmonic));
+  OB_END
+}
+
+int ob_aca_compress(ob_ctx *ctx, int dim, const double *C, int *rank, double *U, double *V, int *I, int *J) {
+  OB_BEGIN
+  need(dim >= 2 && dim <= 2 * OB_MAX_FLAT, "ob_aca_compress: dim out of range (2..390)");
+  const size_t b2 = (size_t)dim * dim;
+  DevBuf<cplx> dC, dU, dV;
+  DevBuf<int> dr, dp;
+  dC.alloc(b2);
+  dU.alloc(b2);
+  dV.alloc(b2);
+  dr.alloc(1);
+  dp.alloc(2 * (size_t)dim);
+  OB_CUDA(cudaMemcpyAsync(dC.p, C, b2 * sizeof(cplx), cudaMemcpyHostToDevice, ctx->st));
+  aca_compress_single(dC.p, dim, ctx->eps_aca, dU.p, dV.p, dr.p, dp.p, ctx->st);
+  ctx->launches += 1;
+  int r = 0;
+  OB_CUDA(cudaMemcpy(&r, dr.p, sizeof(int), cudaMemcpyDeviceToHost));
+  *rank = r;
+  need(r >= 2, "ACA_compression: no admissible pivot (the reference reads an uninitialised index there)");
+  OB_CUDA(cudaMemcpy(U, dU.p, (size_t)r * dim * sizeof(cplx), cudaMemcpyDeviceToHost));
+  OB_CUDA(cudaMemcpy(V, dV.p, (size_t)r * dim * sizeof(cplx), cudaMemcpyDeviceToHost));
+  std::vector<int> pv(2 * (size_t)dim);
+  OB_CUDA(cudaMemcpy(pv.data(), dp.p, pv.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  for(int p = 0; p < r; ++p) {
+    I[p] = pv[p];
+    J[p] = pv[dim + p];
+  }
+  OB_END
+}
+
+int ob_aca_block(ob_ctx *ctx, int harmonic, int i, int j, int *rank, double *U, double *V, int *I, int *J) {
+  OB_BEGIN
+  check_harmonic(harmonic);
+  HarmonicState &H = ctx->hs[harmonic - 1];
+  need(H.assembled && H.mode == 2 && H.aca.built, "ACA operator not assembled (operator = 2, ob_assemble)");
+  need(i >= ctx->first && i < ctx->first + ctx->count && j >= 0 && j < ctx->nobj, "block is not local to this rank");
+  const int dim = H.aca.dim;
+  const size_t b = (size_t)(i - ctx->first) * ctx->nobj + j;
+  const AcaDesc d = H.aca.h_desc[b];
+  *rank = d.rank;
+  OB_CUDA(cudaStreamSynchronize(ctx->st));
+  if(d.rank < 0) {
+    OB_CUDA(cudaMemcpy(U, d.U, (size_t)dim * dim * sizeof(cplx), cudaMemcpyDeviceToHost));
+  } else if(d.rank > 0) {
+    OB_CUDA(cudaMemcpy(U, d.U, (size_t)d.rank * dim * sizeof(cplx), cudaMemcpyDeviceToHost));
+    OB_CUDA(cudaMemcpy(V, d.V, (size_t)d.rank * dim * sizeof(cplx), cudaMemcpyDeviceToHost));
+    std::vector<int> pv(2 * (size_t)dim);
+    OB_CUDA(cudaMemcpy(pv.data(), H.aca.piv + b * 2 * dim, pv.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    for(int p = 0; p < d.rank; ++p) {
+      if(I)
+        I[p] = pv[p];
+      if(J)
+        J[p] = pv[dim + p];
+    }
+  }
+  OB_END
+}
+
+int ob_aca_stats(ob_ctx *ctx, int harmonic, double out[6]) {
+  OB_BEGIN
+  check_harmonic(harmonic);
+  HarmonicState &H = ctx->hs[harmonic - 1];
+  need(H.assembled && H.mode == 2 && H.aca.built, "ACA operator not assembled (operator = 2, ob_assemble)");
+  out[0] = 16.0 * H.aca.stored_elems;
+  out[1] = 16.0 * (double)ctx->Mloc(harmonic) * (double)ctx->N(harmonic);
+  out[2] = (double)H.aca.n_lowrank;
+  out[3] = (double)H.aca.n_dense;
+  out[4] = H.aca.n_lowrank ? H.aca.rank_sum / (double)H.aca.n_lowrank : 0.0;
+  out[5] = (double)H.aca.rank_max;
   OB_END
 }
 
@@ -1300,6 +1396,7 @@ int ob_run(ob_ctx *ctx, const ob_gmres_opts *opts, int do_sh, double *X_sca, dou
     if(!ctx->keep_matrices) {
       ctx->hs[0].S.release();
       ctx->hs[0].AB.release();
+      ctx->hs[0].aca.release();
       ctx->hs[0].assembled = false;
     }
     {
@@ -1399,10 +1496,16 @@ int ob_set_option(ob_ctx *ctx, const char *name, double value) {
       ctx->hs[h].pplan_world = -1; // force a rebuild of the plan at the next assembly
       ctx->hs[h].assembled = false;
     }
-  } else if(n == "operator") { // 0 = dense slab, 1 = compact pair form
-    need(value == 0 || value == 1, "operator must be 0 (dense) or 1 (pairs)");
+  } else if(n == "operator") { // 0 = dense slab, 1 = compact pair form, 2 = ACA-compressed (reference's ACA path)
+    need(value == 0 || value == 1 || value == 2, "operator must be 0 (dense), 1 (pairs) or 2 (ACA)");
     ctx->operator_mode = (int)value;
     ctx->hs[0].assembled = ctx->hs[1].assembled = false;
+  } else if(n == "eps_aca") {
+    need(value > 0, "eps_aca must be positive");
+    ctx->eps_aca = value;
+    ctx->hs[0].assembled = ctx->hs[1].assembled = false;
+  } else if(n == "aca_budget_mb") {
+    ctx->aca_budget = (size_t)std::max(1.0, value) << 20;
   }
   else if(n == "reset_timings") {
     for(int i = 0; i < 16; ++i)

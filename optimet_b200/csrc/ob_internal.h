@@ -101,6 +101,34 @@ void launch_pairs_expand_block(PairPlan const &p, const cplx *AB, int i, int j, 
 void launch_assemble_pairs(VtacTableSet const &ts, const double *xyz, cplx k, const int2 *pair_ij, long npairs,
                            cplx *AB, cudaStream_t st);
 
+// ---- ob_aca.cu (ACA-compressed operator: U V^T-style low-rank far blocks, dense near blocks) ----
+struct AcaDesc {
+  cplx *U = nullptr; // low rank: dim x rank column-major; dense: dim x dim column-major block
+  cplx *V = nullptr; // low rank: rank rows of dim entries
+  int rank = 0;      // > 0 low rank, -1 dense near block, 0 identity diagonal
+  int pad = 0;
+};
+struct AcaOperator {
+  int nobj = 0, dim = 0, first = 0, count = 0, nch = 1;
+  bool built = false;
+  std::vector<cplx *> chunks; // one exactly sized allocation per assembly batch
+  AcaDesc *desc = nullptr;    // device, [count][nobj]
+  std::vector<AcaDesc> h_desc;
+  int *piv = nullptr;         // device, [count][nobj][2][dim]: pivot rows I then pivot columns J
+  cplx *partial = nullptr;    // [nch][count dim]
+  double stored_elems = 0, rank_sum = 0;
+  long n_lowrank = 0, n_dense = 0;
+  int rank_max = 0;
+  void release();
+};
+void aca_build(AcaOperator &op, VtacTableSet const &ts, const double *d_xyz, const cplx *Tdiag, cplx k, int nobj,
+               int first, int count, const double *h_xyz, const double *h_radius, double eps, size_t budget_bytes,
+               int sm_count, cudaStream_t st, long &launches);
+void launch_matvec_aca(AcaOperator const &op, const cplx *x, cplx *y_slice, cudaStream_t st, cudaEvent_t e0 = nullptr,
+                       cudaEvent_t e1 = nullptr);
+void aca_compress_single(const cplx *C_dev, int dim, double eps, cplx *U_dev, cplx *V_dev, int *rank_dev, int *piv_dev,
+                         cudaStream_t st);
+
 // ---- ob_lu.cu (device direct solve: blocked LU with partial pivoting, zgesv-style) ----
 struct LuWork {
   int cap = 0;

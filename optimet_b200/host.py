@@ -13,7 +13,7 @@ _lib = None
 
 HOST_SYMBOLS = ["obh_load_xml", "obh_load_xml_string", "obh_free", "obh_error", "obh_info", "obh_set_wavelength",
                 "obh_get_arrays", "obh_gmres_defaults", "obh_solver_create", "obh_solver_free", "obh_solver_error",
-                "obh_solver_ctx", "obh_solver_comm", "obh_solver_set_gmres", "obh_solver_step", "obh_scan"]
+                "obh_solver_ctx", "obh_solver_comm", "obh_solver_set_gmres", "obh_solver_set_aca_mode", "obh_solver_step", "obh_scan"]
 
 
 def load():
@@ -132,6 +132,15 @@ class Solver:
 
     def set_gmres(self, opts):
         load().obh_solver_set_gmres(self.s, C.byref(opts))
+
+    def set_aca_mode(self, mode):
+        """-1 follow <ACA compression> (default), 0 never compress, 1 always compress."""
+        load().obh_solver_set_aca_mode(self.s, int(mode))
+
+    def ctx(self):
+        """The ob_ctx of this solver wrapped as a capi.Context view (not owned)."""
+        i = self.case.info()
+        return capi.Context.view(load().obh_solver_ctx(self.s), i["nobj"], i["nMax"], i["nMaxS"])
 
     def ctx_timings(self):
         t = (C.c_double * 16)()

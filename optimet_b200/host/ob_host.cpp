@@ -674,18 +674,29 @@ ob_gmres_opts default_gmres(Run const &run) {
   o.max_iters = 240;
   o.restart = 0;
   o.max_restarts = 2;
-  if(run.belos_params.present && run.belos_params.solver != "scalapack" && run.belos_params.solver != "eigen") {
+  const bool aca = run.geometry && run.geometry->ACA_cond_;
+  const bool belos = run.belos_params.present;
+  std::string const &name = run.belos_params.solver;
+  if(aca) {
+    // <ACA compression="yes"> wins in every solver class: Gmres_Zcomp over the compressed operator with the
+    // constants hard-wired there
+    o.flavour = OB_GMRES_ZCOMP;
+    if(belos && name == "scalapack") { // ScalapackSolver.cpp:57-66
+      o.tol = 1e-7;
+      o.max_iters = 250;
+      o.max_restarts = 3;
+    } else if(belos && name != "eigen") { // MatrixBelosSolver.cpp:33-41
+      o.max_iters = 340;
+      o.max_restarts = 1;
+    } // else PreconditionedMatrixSolver.h:50-56
+  } else if(belos && name != "scalapack" && name != "eigen") {
     o.flavour = OB_GMRES_BELOS; // scalapack/LinearSystemSolver.hpp:94-142 with the XML list
     o.tol = run.belos_params.tolerance;
     o.max_iters = run.belos_params.max_iterations;
     o.restart = run.belos_params.num_blocks;
     o.max_restarts = run.belos_params.max_restarts;
-  } else if(run.belos_params.present && run.belos_params.solver == "scalapack") {
-    o.flavour = OB_SOLVE_DIRECT; // ScalapackSolver.cpp:54-128 (pzgesv_)
-  } else if(run.geometry && run.geometry->ACA_cond_) {
-    o.flavour = OB_GMRES_ZCOMP; // PreconditionedMatrixSolver.h:50-52,55,72
   } else {
-    o.flavour = OB_SOLVE_DIRECT; // PreconditionedMatrixSolver.h:58,75
+    o.flavour = OB_SOLVE_DIRECT; // pzgesv_ (ScalapackSolver.cpp:54-128) / colPivHouseholderQr (PreconditionedMatrixSolver.h:58,75)
   }
   return o;
 }
@@ -693,7 +704,7 @@ ob_gmres_opts default_gmres(Run const &run) {
 namespace solver {
 
 B200Matrix::B200Matrix(std::shared_ptr<Geometry> geometry_, std::shared_ptr<Excitation const> incWave_, int device)
-    : geometry(geometry_), incWave(incWave_), ctx(nullptr), tables_set(false) {
+    : geometry(geometry_), incWave(incWave_), ctx(nullptr), tables_set(false), aca_mode(-1), aca_forced(false) {
   if(ob_create(device, &ctx) != 0)
     throw std::runtime_error(ob_last_error(nullptr));
   opts.flavour = (geometry && geometry->ACA_cond_) ? OB_GMRES_ZCOMP : OB_SOLVE_DIRECT; // PreconditionedMatrixSolver.h:55-58
@@ -750,6 +761,12 @@ void B200Matrix::update() {
     mat[4][j] = s.elmag.ksippp;
     mat[5][j] = s.elmag.ksiparppar;
     mat[6][j] = s.elmag.gamma;
+  }
+  // <ACA compression="yes"> -> the compressed operator (Scattering_matrix_ACA_FF/_SH, PreconditionedMatrixSolver.h:86-97)
+  const bool want_aca = aca_mode < 0 ? geometry->ACA_cond_ : aca_mode != 0;
+  if(want_aca != aca_forced) {
+    check(ob_set_option(ctx, "operator", want_aca ? 2 : 1));
+    aca_forced = want_aca;
   }
   check(ob_set_cluster(ctx, (int)nobj, xyz.data(), radius.data(), nMax, nMaxS));
   const double waveK[2] = {incWave->waveK.real(), incWave->waveK.imag()};

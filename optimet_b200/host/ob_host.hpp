@@ -141,6 +141,9 @@ public:
   //! PreconditionedMatrixSolver.h:45-79): Belos list -> Belos GMRES; ACA on -> Gmres_Zcomp constants; else direct solve
   void set_gmres(ob_gmres_opts const &o) { opts = o; }
   ob_gmres_opts const &gmres() const { return opts; }
+  //! operator form: -1 (default) follows Geometry::ACA_cond_ (compressed operator when <ACA compression="yes">),
+  //! 0 never compress (uncompressed pair / dense form even when the XML asks for ACA), 1 always compress
+  void set_aca_mode(int mode) { aca_mode = mode; }
 
   void update(std::shared_ptr<Geometry> geometry_, std::shared_ptr<Excitation const> incWave_) {
     geometry = geometry_;
@@ -166,6 +169,8 @@ protected:
   mutable double last_cs[5];
   mutable int last_iters[2];
   mutable bool tables_set;
+  int aca_mode;
+  bool aca_forced;
   void check(int rc) const;
 };
 

@@ -137,6 +137,10 @@ int obh_solver_set_gmres(void *s_, const ob_gmres_opts *o) {
   ((HostSolver *)s_)->s->set_gmres(*o);
   return 0;
 }
+int obh_solver_set_aca_mode(void *s_, int mode) {
+  ((HostSolver *)s_)->s->set_aca_mode(mode);
+  return 0;
+}
 // one wavelength: solver->update(run) + solver->solve(...) + cross sections (Simulation.cpp:651-667).
 // lambda_m > 0 first moves the run to that wavelength.  Output vectors may be NULL.
 int obh_solver_step(void *s_, void *h, double lambda_m, double *X_sca, double *X_int, double *X_sca_SH,

@@ -31,6 +31,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
+#include <functional>
 #include <map>
 #include <stdexcept>
 #include <string>
@@ -1447,7 +1448,8 @@ static void zcomp_givens(cd hi1, cd hi2, cd &c, cd &s) {
 
 // In-tree GMRES (PreconditionedMatrix.cpp:892-985, det_approx :1087-1133), dense operator.
 // x0 = 0, modified Gram-Schmidt, err = |g_{n+1}| / ||Y||, restarts as in the reference.
-static GmresResult gmres_zcomp(CMat const &S, std::vector<cd> const &Y, double tol, int maxit, int no_rest) {
+typedef std::function<std::vector<cd>(std::vector<cd> const &)> LinOp;
+static GmresResult gmres_zcomp(LinOp const &apply, std::vector<cd> const &Y, double tol, int maxit, int no_rest) {
   size_t N = Y.size();
   std::vector<cd> x(N, cd(0, 0)), w;
   std::vector<double> err(1, 1.0);
@@ -1456,7 +1458,7 @@ static GmresResult gmres_zcomp(CMat const &S, std::vector<cd> const &Y, double t
   for(int rest = 1; rest <= no_rest; ++rest) {
     if(err[n] <= tol)
       break;
-    w = matvec_dense(S, x);
+    w = apply(x);
     std::vector<cd> res(N);
     for(size_t i = 0; i < N; ++i)
       res[i] = Y[i] - w[i];
@@ -1472,7 +1474,7 @@ static GmresResult gmres_zcomp(CMat const &S, std::vector<cd> const &Y, double t
     err.assign(1, err[0]); // err(0) stays 1 (never overwritten in the reference)
     err[0] = 1.0;
     while((n < maxit) && (err[n] > tol)) {
-      w = matvec_dense(S, v[n]);
+      w = apply(v[n]);
       std::vector<cd> h(n + 2);
       for(int t = 0; t <= n; ++t) {
         h[t] = dotc(v[t], w);
@@ -1529,6 +1531,201 @@ static GmresResult gmres_zcomp(CMat const &S, std::vector<cd> const &Y, double t
   r.relres = err[n];
   r.converged = err[n] <= tol;
   return r;
+}
+
+static GmresResult gmres_zcomp(CMat const &S, std::vector<cd> const &Y, double tol, int maxit, int no_rest) {
+  return gmres_zcomp([&S](std::vector<cd> const &x) { return matvec_dense(S, x); }, Y, tol, maxit, no_rest);
+}
+
+// ---------------------------------------------------------------------------
+// ACA-compressed operator (PreconditionedMatrix.cpp:489-551, 699-759, 760-889, 1058-1085)
+// ---------------------------------------------------------------------------
+// Matrix_ACA (PreconditionedMatrix.h:29-35).  U is dim x r, V is r x dim; I, J are the pivot rows / columns in the
+// order they were taken (kept for the parity tests; the reference discards them).
+struct MatrixACA {
+  CMat U, V, S_sub;
+  int dim;
+  std::vector<int> I, J;
+  MatrixACA() : dim(0) {}
+};
+
+// getMaxInd (PreconditionedMatrix.cpp:861-889): first index of the largest |.| among the entries not listed in
+// K(0 .. K.size()-2) -- the LAST entry of K is never excluded (it is the slot about to be filled).  `imax` is
+// uninitialised in the reference when no entry qualifies (all excluded, all zero or NaN); -1 is returned here.
+static int getMaxInd(std::vector<cd> const &RowCol, std::vector<int> const &K, int kmax) {
+  double max = 0.0;
+  int imax = -1;
+  for(int i = 0; i != kmax; ++i) {
+    bool same = false;
+    for(size_t j = 0; j + 1 < K.size(); ++j)
+      if(i == K[j])
+        same = true;
+    if(!same && std::abs(RowCol[i]) > max) {
+      max = std::abs(RowCol[i]);
+      imax = i;
+    }
+  }
+  return imax;
+}
+
+static double g_eps_ACA = 1e-3; // PreconditionedMatrix.cpp:772
+
+// ACA_compression (PreconditionedMatrix.cpp:760-859), partially pivoted cross approximation with the reference's
+// norm recursion as written: the cross term runs over p = 0 .. k-2 and uses only the first k entries of the
+// columns / rows, without conjugation (:825-838).  The loop always performs k = 0 and k = 1, so rank >= 2.
+// forceI / forceJ (tests only): pivots imposed for the first steps instead of getMaxInd -- used to take the pivot
+// decisions of another run (the device) where near-ties make them rounding-dependent; everything else, including the
+// stopping rule, is still evaluated here.
+static void ACA_compression(CMat &U, CMat &V, CMat const &CoupMat, std::vector<int> *Iout, std::vector<int> *Jout,
+                            std::vector<int> const *forceI = nullptr, std::vector<int> const *forceJ = nullptr) {
+  const int kmax = (int)CoupMat.cols;
+  std::vector<std::vector<cd>> Ucols, Vrows;
+  std::vector<int> I(1, 0), J(1, 0);
+  std::vector<double> NORMA;
+  std::vector<cd> RowCol(kmax);
+  for(int k = 0; k != kmax; ++k) {
+    if(k == 0) {
+      I[0] = 0;
+    } else {
+      J.resize(k + 1, 0);
+    }
+    // residual row I(k): CoupMat.row - sum_p U(I(k),p) V.row(p), the sum accumulated from zero (:795-803)
+    std::vector<cd> sum1(kmax, cd(0, 0));
+    for(int p = 0; p < k; ++p)
+      for(int q = 0; q < kmax; ++q)
+        sum1[q] = sum1[q] + Ucols[p][I[k]] * Vrows[p][q];
+    for(int q = 0; q < kmax; ++q)
+      RowCol[q] = k == 0 ? CoupMat(I[k], q) : CoupMat(I[k], q) - sum1[q];
+    J[k] = (forceJ && k < (int)forceJ->size()) ? (*forceJ)[k] : getMaxInd(RowCol, J, kmax);
+    if(J[k] < 0)
+      throw std::runtime_error("ACA_compression: no admissible column pivot (reference behaviour undefined)");
+    std::vector<cd> Row(kmax);
+    cd piv = RowCol[J[k]];
+    for(int q = 0; q < kmax; ++q)
+      Row[q] = RowCol[q] / piv;
+    Vrows.push_back(Row);
+    // residual column J(k) (:810-818)
+    std::vector<cd> sum2(kmax, cd(0, 0));
+    for(int p = 0; p < k; ++p)
+      for(int i = 0; i < kmax; ++i)
+        sum2[i] = sum2[i] + Vrows[p][J[k]] * Ucols[p][i];
+    std::vector<cd> Col(kmax);
+    for(int i = 0; i < kmax; ++i)
+      Col[i] = k == 0 ? CoupMat(i, J[k]) : CoupMat(i, J[k]) - sum2[i];
+    Ucols.push_back(Col);
+    double cn = norm2(Col), rn = norm2(Row);
+    if(k == 0) {
+      NORMA.push_back(std::pow(cn, 2) * std::pow(rn, 2));
+    } else {
+      double sum = 0.0;
+      for(int p = 0; p != (k - 1); ++p) { // as written: stops before p = k-1
+        cd pom1(0, 0), pom2(0, 0);
+        for(int tt = 0; tt != k; ++tt) {
+          pom1 = pom1 + Ucols[p][tt] * Col[tt];
+          pom2 = pom2 + Vrows[p][tt] * Row[tt];
+        }
+        sum = sum + std::abs(pom1) * std::abs(pom2);
+      }
+      NORMA.push_back(NORMA[k - 1] + std::pow(cn, 2) * std::pow(rn, 2) + 2.0 * sum);
+      if(g_eps_ACA * std::sqrt(NORMA[k]) >= cn * rn)
+        break;
+    }
+    if(k + 1 == kmax)
+      break; // the reference would read an undefined pivot here; its value is never used
+    I.resize(k + 2, 0);
+    I[k + 1] = (forceI && k + 1 < (int)forceI->size()) ? (*forceI)[k + 1] : getMaxInd(Col, I, kmax);
+    if(I[k + 1] < 0)
+      throw std::runtime_error("ACA_compression: no admissible row pivot (reference behaviour undefined)");
+  }
+  const int r = (int)Ucols.size();
+  U = CMat(kmax, r);
+  V = CMat(r, kmax);
+  for(int p = 0; p < r; ++p)
+    for(int i = 0; i < kmax; ++i) {
+      U(i, p) = Ucols[p][i];
+      V(p, i) = Vrows[p][i];
+    }
+  if(Iout) {
+    I.resize(r);
+    *Iout = I;
+  }
+  if(Jout) {
+    J.resize(r);
+    *Jout = J;
+  }
+}
+
+// admissibility criterion of PreconditionedMatrix.cpp:526 / :734 / :1070
+static bool aca_admissible(Geometry const &g, int ii, int jj) {
+  double distance = findDistance(g.objects[ii].vR, g.objects[jj].vR);
+  return distance >= 2.0 * (g.objects[ii].radius + g.objects[jj].radius);
+}
+
+typedef std::map<std::array<int, 3>, std::pair<std::vector<int>, std::vector<int>>> PivotTable; // (harmonic, i, j)
+
+// Scattering_matrix_ACA_FF / _SH (PreconditionedMatrix.cpp:489-551, 699-759)
+static void scattering_matrix_ACA(Geometry const &g, Excitation const &exc, int harmonic, std::vector<MatrixACA> &S_comp,
+                                  PivotTable const *forced = nullptr) {
+  int nm = harmonic == 1 ? g.objects[0].nMax : g.objects[0].nMaxS;
+  int n = flat_max(nm);
+  int nobj = (int)g.objects.size();
+  S_comp.assign((size_t)nobj * nobj, MatrixACA());
+  cd k = harmonic == 1 ? exc.waveK : 2.0 * exc.waveK;
+  parallel_for(nobj, [&](int ii) {
+    std::vector<cd> T = g.objects[ii].getTLocal(harmonic, exc.omega(), g.bground);
+    for(int jj = 0; jj < nobj; ++jj) {
+      MatrixACA &M = S_comp[(size_t)nobj * ii + jj];
+      M.dim = 2 * n;
+      if(ii == jj) {
+        M.S_sub = CMat(2 * n, 2 * n);
+        for(int d = 0; d < 2 * n; ++d)
+          M.S_sub(d, d) = 1;
+        continue;
+      }
+      Coupling AB(sph_minus(g.objects[ii].vR, g.objects[jj].vR), k, nm);
+      CMat blk(2 * n, 2 * n);
+      fill_block(blk, 0, 0, n, AB, T);
+      if(aca_admissible(g, ii, jj)) {
+        PivotTable::const_iterator f;
+        std::array<int, 3> key = {{harmonic, ii, jj}};
+        if(forced && (f = forced->find(key)) != forced->end())
+          ACA_compression(M.U, M.V, blk, &M.I, &M.J, &f->second.first, &f->second.second);
+        else
+          ACA_compression(M.U, M.V, blk, &M.I, &M.J);
+      } else
+        M.S_sub = blk;
+    }
+  });
+}
+
+// matvec (PreconditionedMatrix.cpp:1058-1085): admissible blocks as U (V x_j), the rest (incl. the identity
+// diagonal, distance 0) as S_sub x_j
+static std::vector<cd> matvec_ACA(std::vector<MatrixACA> const &S_comp, std::vector<cd> const &x, Geometry const &g) {
+  int nobj = (int)g.objects.size();
+  int N = S_comp[0].dim;
+  std::vector<cd> Y((size_t)nobj * N, cd(0, 0));
+  parallel_for(nobj, [&](int ii) {
+    for(int jj = 0; jj < nobj; ++jj) {
+      MatrixACA const &M = S_comp[(size_t)ii * nobj + jj];
+      const cd *xj = &x[(size_t)jj * N];
+      cd *yi = &Y[(size_t)ii * N];
+      if(aca_admissible(g, ii, jj)) {
+        int r = (int)M.V.rows;
+        std::vector<cd> t(r, cd(0, 0));
+        for(int q = 0; q < N; ++q)
+          for(int p = 0; p < r; ++p)
+            t[p] += M.V(p, q) * xj[q];
+        for(int p = 0; p < r; ++p)
+          for(int i = 0; i < N; ++i)
+            yi[i] += M.U(i, p) * t[p];
+      } else {
+        for(int q = 0; q < N; ++q)
+          for(int i = 0; i < N; ++i)
+            yi[i] += M.S_sub(i, q) * xj[q];
+      }
+    }
+  });
+  return Y;
 }
 
 // Belos "GMRES" (BlockGmresSolMgr, Block Size 1) as driven by scalapack/LinearSystemSolver.hpp:94-142:
@@ -1861,6 +2058,8 @@ struct Case {
   int iters_ff, iters_sh;
   double relres_ff, relres_sh;
   std::string err;
+  PivotTable aca_forced; // tests: pivot sequences imposed on ACA_compression (see there)
+  std::vector<int> aca_ranks[2]; // ranks of the last solver-3 run, nobj x nobj per harmonic (-1 dense)
   Case() : tables_nmax(-1), iters_ff(0), iters_sh(0), relres_ff(0), relres_sh(0) {}
 };
 
@@ -2121,12 +2320,30 @@ static std::vector<cd> run_solver(CMat const &S, std::vector<cd> const &rhs, int
   return r.x;
 }
 // Solver::update + Solver::solve (PreconditionedMatrixSolver.h:45-100) for the current wavelength
+// solver 3: the ACA-compressed operator + Gmres_Zcomp (PreconditionedMatrixSolver.h:55-56,72-73 when ACA_cond_)
+static std::vector<cd> run_solver_aca(Case *c, int harmonic, std::vector<cd> const &rhs, const double *opts, int *iters,
+                                      double *relres) {
+  std::vector<MatrixACA> S_comp;
+  scattering_matrix_ACA(c->geom, c->exc, harmonic, S_comp, &c->aca_forced);
+  c->aca_ranks[harmonic - 1].assign(S_comp.size(), -1);
+  for(size_t b = 0; b < S_comp.size(); ++b)
+    if(S_comp[b].V.rows > 0)
+      c->aca_ranks[harmonic - 1][b] = (int)S_comp[b].V.rows;
+  Geometry const &g = c->geom;
+  GmresResult r = gmres_zcomp([&](std::vector<cd> const &x) { return matvec_ACA(S_comp, x, g); }, rhs, opts[0],
+                              (int)opts[1], (int)opts[3]);
+  *iters = r.iters;
+  *relres = r.relres;
+  return r.x;
+}
 int orc_case_solve(void *h, int solver, const double *opts) {
   ORC_TRY
   Case *c = (Case *)h;
   int nobj = (int)c->geom.objects.size();
   c->Q = source_vector(c->geom, c->exc);
-  {
+  if(solver == 3) {
+    c->X_sca = run_solver_aca(c, 1, c->Q, opts, &c->iters_ff, &c->relres_ff);
+  } else {
     CMat S = preconditioned_scattering_matrix(c->geom, c->exc, 1, 0, nobj);
     c->X_sca = run_solver(S, c->Q, solver, opts, &c->iters_ff, &c->relres_ff);
   }
@@ -2140,8 +2357,12 @@ int orc_case_solve(void *h, int solver, const double *opts) {
     for(size_t i = 0; i < xc.size(); ++i)
       xc[i] = std::conj(c->X_int[i]);
     source_vectorSH(c->geom, c->exc, xc, T, c->K, c->K1ana);
-    CMat V = preconditioned_scattering_matrix(c->geom, c->exc, 2, 0, nobj);
-    c->X_sca_SH = run_solver(V, c->K, solver, opts, &c->iters_sh, &c->relres_sh);
+    if(solver == 3) {
+      c->X_sca_SH = run_solver_aca(c, 2, c->K, opts, &c->iters_sh, &c->relres_sh);
+    } else {
+      CMat V = preconditioned_scattering_matrix(c->geom, c->exc, 2, 0, nobj);
+      c->X_sca_SH = run_solver(V, c->K, solver, opts, &c->iters_sh, &c->relres_sh);
+    }
     c->X_int_SH = convertInternal_SH(c->X_sca_SH, c->K1ana, c->geom, c->exc);
   }
   ORC_CATCH(h)
@@ -2183,6 +2404,84 @@ int orc_case_cross_sections(void *h, double out[5]) {
     out[3] = getScatteringCrossSection_SH(c->geom, c->exc, c->X_sca_SH);
     out[4] = getAbsorptionCrossSection_SH(c->geom, c->exc, T, c->X_int, c->X_int_SH);
   }
+  ORC_CATCH(h)
+}
+// ---- ACA unit surface ----
+int orc_set_eps_aca(double eps) {
+  g_eps_ACA = eps;
+  return 0;
+}
+// ACA_compression of a caller-supplied dim x dim column-major block.  U: dim x rank column-major, V: rank rows of
+// dim entries (row-major), I / J: pivot rows / columns; all buffers sized for rank = dim.
+int orc_aca_compress(const double *C, int dim, int *rank, double *U, double *V, int *I, int *J) {
+  ORC_TRY
+  CMat M(dim, dim), Um, Vm;
+  memcpy(M.a.data(), C, (size_t)dim * dim * sizeof(cd));
+  std::vector<int> Iv, Jv;
+  ACA_compression(Um, Vm, M, &Iv, &Jv);
+  int r = (int)Um.cols;
+  *rank = r;
+  memcpy(U, Um.a.data(), (size_t)dim * r * sizeof(cd));
+  cd *Vo = (cd *)V;
+  for(int p = 0; p < r; ++p)
+    for(int q = 0; q < dim; ++q)
+      Vo[(size_t)p * dim + q] = Vm(p, q);
+  for(int p = 0; p < r; ++p) {
+    I[p] = Iv[p];
+    J[p] = Jv[p];
+  }
+  ORC_CATCH(nullptr)
+}
+// block (i, j) of Scattering_matrix_ACA_FF/_SH: rank > 0 low rank (U, V, I, J filled as above), rank = -1 dense
+// (S_sub in U, dim x dim column-major; includes the identity diagonal)
+int orc_case_aca_block(void *h, int harmonic, int i, int j, int *rank, double *U, double *V, int *I, int *J) {
+  ORC_TRY
+  Case *c = (Case *)h;
+  Geometry const &g = c->geom;
+  int nm = harmonic == 1 ? g.objects[0].nMax : g.objects[0].nMaxS;
+  int n = flat_max(nm), dim = 2 * n;
+  CMat blk(dim, dim);
+  if(i == j) {
+    for(int d = 0; d < dim; ++d)
+      blk(d, d) = 1;
+  } else {
+    std::vector<cd> T = g.objects[i].getTLocal(harmonic, c->exc.omega(), g.bground);
+    Coupling AB(sph_minus(g.objects[i].vR, g.objects[j].vR), harmonic == 1 ? c->exc.waveK : 2.0 * c->exc.waveK, nm);
+    fill_block(blk, 0, 0, n, AB, T);
+  }
+  if(i != j && aca_admissible(g, i, j))
+    return orc_aca_compress((const double *)blk.a.data(), dim, rank, U, V, I, J);
+  *rank = -1;
+  memcpy(U, blk.a.data(), blk.a.size() * sizeof(cd));
+  ORC_CATCH(h)
+}
+// tests: impose the pivot sequence of block (i, j) for later solver-3 runs / matvecs; rank <= 0 clears the entry
+int orc_case_force_aca_pivots(void *h, int harmonic, int i, int j, int rank, const int *I, const int *J) {
+  Case *c = (Case *)h;
+  std::array<int, 3> key = {{harmonic, i, j}};
+  if(rank <= 0)
+    c->aca_forced.erase(key);
+  else
+    c->aca_forced[key] = std::make_pair(std::vector<int>(I, I + rank), std::vector<int>(J, J + rank));
+  return 0;
+}
+int orc_case_aca_ranks(void *h, int harmonic, int *out) {
+  Case *c = (Case *)h;
+  std::vector<int> const &r = c->aca_ranks[harmonic - 1];
+  for(size_t b = 0; b < r.size(); ++b)
+    out[b] = r[b];
+  return (int)r.size();
+}
+// y = S_comp x for the current wavelength (matvec, PreconditionedMatrix.cpp:1058-1085)
+int orc_case_matvec_aca(void *h, int harmonic, const double *x, double *y) {
+  ORC_TRY
+  Case *c = (Case *)h;
+  std::vector<MatrixACA> S_comp;
+  scattering_matrix_ACA(c->geom, c->exc, harmonic, S_comp, &c->aca_forced);
+  size_t N = (size_t)S_comp[0].dim * c->geom.objects.size();
+  std::vector<cd> xv((cd *)x, (cd *)x + N);
+  std::vector<cd> yv = matvec_ACA(S_comp, xv, c->geom);
+  memcpy(y, yv.data(), N * sizeof(cd));
   ORC_CATCH(h)
 }
 // generic dense helpers for tests / baselines

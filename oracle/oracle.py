@@ -122,7 +122,27 @@ def matvec(S, x):
     return y
 
 
-SOLVER_DIRECT, SOLVER_ZCOMP, SOLVER_BELOS = 0, 1, 2
+SOLVER_DIRECT, SOLVER_ZCOMP, SOLVER_BELOS, SOLVER_ACA_ZCOMP = 0, 1, 2, 3
+
+
+def set_eps_aca(eps):
+    lib().orc_set_eps_aca(C.c_double(eps))
+
+
+def aca_compress(block):
+    """ACA_compression (PreconditionedMatrix.cpp:760-859) of a square block -> U (dim x r), V (r x dim), I, J."""
+    Cm = np.asfortranarray(block, dtype=np.complex128)
+    dim = Cm.shape[0]
+    U = np.zeros((dim, dim), dtype=np.complex128, order="F")
+    V = np.zeros((dim, dim), dtype=np.complex128)
+    I = np.zeros(dim, dtype=np.int32)
+    J = np.zeros(dim, dtype=np.int32)
+    r = C.c_int()
+    rc = lib().orc_aca_compress(_p(Cm), int(dim), C.byref(r), _p(U), _p(V), _p(I), _p(J))
+    if rc:
+        raise RuntimeError("ACA_compression failed (no admissible pivot)")
+    r = r.value
+    return np.asfortranarray(U.ravel(order="F")[:dim * r].reshape((dim, r), order="F")), V[:r].copy(), I[:r].copy(), J[:r].copy()
 
 
 def solve_dense(S, rhs, solver, tol=1e-6, maxit=240, restart=30, max_restarts=2):
@@ -235,6 +255,43 @@ class Case:
     def solve(self, solver=SOLVER_DIRECT, tol=1e-6, maxit=240, restart=30, max_restarts=2):
         opts = (C.c_double * 4)(tol, maxit, restart, max_restarts)
         self._chk(lib().orc_case_solve(self.h, int(solver), opts))
+
+    def aca_block(self, harmonic, i, j):
+        """Block (i, j) of Scattering_matrix_ACA_FF/_SH: (rank, U, V, I, J); rank -1 = dense block in U."""
+        inf = self.info()
+        nm = inf["nMax"] if harmonic == 1 else inf["nMaxS"]
+        dim = 2 * nm * (nm + 2)
+        U = np.zeros(dim * dim, dtype=np.complex128)
+        V = np.zeros((dim, dim), dtype=np.complex128)
+        I = np.zeros(dim, dtype=np.int32)
+        J = np.zeros(dim, dtype=np.int32)
+        r = C.c_int()
+        self._chk(lib().orc_case_aca_block(self.h, int(harmonic), int(i), int(j), C.byref(r), _p(U), _p(V), _p(I), _p(J)))
+        r = r.value
+        if r < 0:
+            return -1, U.reshape((dim, dim), order="F"), None, None, None
+        return r, U[:dim * r].reshape((dim, r), order="F"), V[:r].copy(), I[:r].copy(), J[:r].copy()
+
+    def force_aca_pivots(self, harmonic, i, j, I, J):
+        """Tests: impose the pivot rows / columns of block (i, j) on later ACA runs (None clears)."""
+        if I is None:
+            lib().orc_case_force_aca_pivots(self.h, int(harmonic), int(i), int(j), 0, None, None)
+            return
+        I = np.ascontiguousarray(I, dtype=np.int32)
+        J = np.ascontiguousarray(J, dtype=np.int32)
+        lib().orc_case_force_aca_pivots(self.h, int(harmonic), int(i), int(j), int(I.size), _p(I), _p(J))
+
+    def aca_ranks(self, harmonic):
+        nobj = self.info()["nobj"]
+        out = np.zeros(nobj * nobj, dtype=np.int32)
+        lib().orc_case_aca_ranks(self.h, int(harmonic), _p(out))
+        return out.reshape(nobj, nobj)
+
+    def matvec_aca(self, harmonic, x):
+        x = np.ascontiguousarray(x, dtype=np.complex128)
+        y = np.zeros_like(x)
+        self._chk(lib().orc_case_matvec_aca(self.h, int(harmonic), _p(x), _p(y)))
+        return y
 
     def vector(self, which):
         i = self.info()

@@ -178,10 +178,17 @@ def test_solver_selection_follows_the_reference_factory():
     def belos(solver):
         return [("Solver", "string", solver), ("Convergence Tolerance", "double", "1.0e-5")]
 
+    def opts(**kw):
+        o = H.Case(xml=xmlgen.cluster_xml(xyz, 50.0, 3, 1240.0, **kw)).gmres_defaults()
+        return o.flavour, o.tol, o.max_iters, o.max_restarts
+
     assert flavour(aca=False) == capi.OB_SOLVE_DIRECT
-    assert flavour(aca=True) == capi.OB_GMRES_ZCOMP
     assert flavour(aca=False, belos=belos("GMRES")) == capi.OB_GMRES_BELOS
-    assert flavour(aca=True, belos=belos("GMRES")) == capi.OB_GMRES_BELOS
-    assert flavour(aca=True, belos=belos("scalapack")) == capi.OB_SOLVE_DIRECT
-    assert flavour(aca=True, belos=belos("eigen")) == capi.OB_GMRES_ZCOMP
+    assert flavour(aca=False, belos=belos("scalapack")) == capi.OB_SOLVE_DIRECT
     assert flavour(aca=False, belos=belos("eigen")) == capi.OB_SOLVE_DIRECT
+    # <ACA compression="yes"> wins in every solver class: Gmres_Zcomp over the compressed operator with the constants
+    # hard-wired in PreconditionedMatrixSolver.h:50-52, MatrixBelosSolver.cpp:33-35 and ScalapackSolver.cpp:57-60
+    assert opts(aca=True) == (capi.OB_GMRES_ZCOMP, 1e-6, 240, 2)
+    assert opts(aca=True, belos=belos("eigen")) == (capi.OB_GMRES_ZCOMP, 1e-6, 240, 2)
+    assert opts(aca=True, belos=belos("GMRES")) == (capi.OB_GMRES_ZCOMP, 1e-6, 340, 1)
+    assert opts(aca=True, belos=belos("scalapack")) == (capi.OB_GMRES_ZCOMP, 1e-7, 250, 3)

@@ -115,3 +115,22 @@ def relerr(a, b):
     a, b = np.asarray(a), np.asarray(b)
     nb = np.linalg.norm(b.ravel())
     return np.linalg.norm((a - b).ravel()) / (nb if nb > 0 else 1.0)
+
+
+def impose_device_pivots(orc, ctx, harmonics=(1, 2)):
+    """Step 2 helper: give the oracle the device's pivots where its own differ; returns (blocks, differing blocks)."""
+    total = differ = 0
+    for h in harmonics:
+        for i in range(ctx.nobj):
+            for j in range(ctx.nobj):
+                r, _, _, Ig, Jg = ctx.aca_block(h, i, j)
+                if r <= 0:
+                    continue
+                total += 1
+                ro, _, _, Io, Jo = orc.aca_block(h, i, j)
+                if ro == r and list(Io) == list(Ig) and list(Jo) == list(Jg):
+                    orc.force_aca_pivots(h, i, j, None, None)
+                else:
+                    differ += 1
+                    orc.force_aca_pivots(h, i, j, Ig, Jg)
+    return total, differ
