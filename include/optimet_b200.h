@@ -129,6 +129,17 @@ int ob_run(ob_ctx *ctx, const ob_gmres_opts *opts, int do_sh, double *X_sca, dou
 int ob_cross_sections(ob_ctx *ctx, const double *X_sca, const double *X_int, const double *X_sca_SH,
                       const double *X_int_SH, int do_sh, double cs[5]);
 
+/* ---- near-field maps (Result::setFields / getEHFields with projection = false, srcAna/Result.cpp:74-300, 896-934;
+ * AuxCoefficients M, N, X-1, X+1, srcAna/AuxCoefficients.cpp:108-343; Geometry::checkInner / COEFFpartSH,
+ * srcAna/Geometry.cpp:147-163, 458-495; symbol::CXm1 / CXp1, srcAna/Symbol.cpp:482-635) ----
+ * pts_sph: npts x (r, theta, phi) in metres / radians as OutputGrid::getPoint returns them (OutputGrid.cpp:132-157).
+ * X_*: the four solution vectors of solve(); NULL = the device-resident ones of the last ob_run.
+ * out: npts x 4 x 3 complex = E_FF, H_FF, E_SH, H_SH with Cartesian components x, y, z (the reference stores them in
+ * the rrr / the / phi slots of SphericalP); E_FF, H_FF include the incident field outside the spheres; E_SH includes
+ * the particular solution inside.  inner (may be NULL): index of the sphere containing the point, -1 outside. */
+int ob_fields(ob_ctx *ctx, long npts, const double *pts_sph, const double *X_sca, const double *X_int,
+              const double *X_sca_SH, const double *X_int_SH, int do_sh, double *out, int *inner);
+
 /* ---- instrumentation ---- */
 /* device-event timings (ms) of the last ob_run: 0 factors+source, 1 assemble FF, 2 solve FF, 3 SH source,
  * 4 assemble SH, 5 solve SH, 6 cross sections, 7 matvec total (streaming kernel only), 8 matvec count,

@@ -27,7 +27,7 @@ SYMBOLS = [
     "ob_inc_local", "ob_assemble", "ob_release_matrix", "ob_fetch_block", "ob_fetch_matrix", "ob_matvec",
     "ob_source_ff", "ob_set_cg_tables", "ob_build_cg_tables", "ob_fetch_cg_table", "ob_source_sh", "ob_solve",
     "ob_unprecondition_ff", "ob_unprecondition_sh", "ob_run", "ob_cross_sections", "ob_timings", "ob_timer", "ob_set_option",
-    "ob_measure_fp64_peak", "ob_dense_solve", "ob_aca_block", "ob_aca_compress", "ob_aca_stats",
+    "ob_measure_fp64_peak", "ob_dense_solve", "ob_aca_block", "ob_aca_compress", "ob_aca_stats", "ob_fields",
 ]
 
 _lib = None
@@ -229,6 +229,17 @@ class Context:
         self._chk(self._lib.ob_aca_stats(self.h, int(harmonic), out))
         return dict(stored_bytes=out[0], dense_bytes=out[1], lowrank_blocks=int(out[2]), dense_blocks=int(out[3]),
                     mean_rank=out[4], max_rank=int(out[5]))
+
+    def fields(self, pts_sph, X_sca=None, X_int=None, X_sca_SH=None, X_int_SH=None, do_sh=True):
+        """Result::setFields at spherical points (npts, 3): (npts, 4, 3) complex E_FF, H_FF, E_SH, H_SH (Cartesian
+        components) and checkInner per point.  Vectors left None -> device-resident solution of the last run()."""
+        pts = np.ascontiguousarray(pts_sph, dtype=np.float64).reshape(-1, 3)
+        out = np.zeros((len(pts), 4, 3), dtype=np.complex128)
+        inner = np.zeros(len(pts), dtype=np.int32)
+        vecs = [None if v is None else _cz(v) for v in (X_sca, X_int, X_sca_SH, X_int_SH)]
+        self._chk(self._lib.ob_fields(self.h, C.c_long(len(pts)), _p(pts), *[None if v is None else _p(v) for v in vecs],
+                                      int(bool(do_sh)), _p(out), _p(inner)))
+        return out, inner
 
     def matvec(self, harmonic, x):
         x = _cz(x, self.N(harmonic))

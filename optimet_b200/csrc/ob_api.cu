@@ -1356,6 +1356,68 @@ int ob_cross_sections(ob_ctx *ctx, const double *X_sca, const double *X_int, con
   OB_END
 }
 
+int ob_fields(ob_ctx *ctx, long npts, const double *pts_sph, const double *X_sca, const double *X_int,
+              const double *X_sca_SH, const double *X_int_SH, int do_sh, double *out, int *inner) {
+  OB_BEGIN
+  need(ctx->have_inc && ctx->have_freq, "incident field / frequency not set");
+  need(npts >= 0 && (npts == 0 || (pts_sph && out)), "ob_fields: null buffers");
+  const int N1 = ctx->N(1), N2 = ctx->N(2);
+  // NULL vectors: the resident solution of the last ob_run
+  if(X_sca)
+    upload(ctx, ctx->Xsca, X_sca, N1);
+  if(X_int)
+    upload(ctx, ctx->Xint, X_int, N1);
+  need(ctx->Xsca.p && ctx->Xint.p && ctx->Xsca.n >= (size_t)N1, "ob_fields: no FF solution (pass X_sca / X_int or call ob_run)");
+  if(do_sh) {
+    if(X_sca_SH)
+      upload(ctx, ctx->XscaSH, X_sca_SH, N2);
+    if(X_int_SH)
+      upload(ctx, ctx->XintSH, X_int_SH, N2);
+    need(ctx->XscaSH.p && ctx->XintSH.p && ctx->XscaSH.n >= (size_t)N2,
+         "ob_fields: no SH solution (pass X_sca_SH / X_int_SH or call ob_run)");
+    ensure_cg(ctx);
+  }
+  FieldInputs in;
+  in.nobj = ctx->nobj;
+  in.nMax = ctx->nMax;
+  in.nMaxS = ctx->nMaxS;
+  in.do_sh = do_sh ? 1 : 0;
+  in.omega = ctx->omega;
+  in.waveK = ctx->waveK;
+  in.eps_b = ctx->eps_b;
+  in.mu_b = ctx->mu_b;
+  in.xyz = ctx->xyz.p;
+  in.radius = ctx->radius.p;
+  in.eps = ctx->mat[0].p;
+  in.mu = ctx->mat[1].p;
+  in.eps_SH = ctx->mat[2].p;
+  in.mu_SH = ctx->mat[3].p;
+  in.gamma = ctx->mat[6].p;
+  in.ainc = ctx->ainc.p;
+  in.Xsca = ctx->Xsca.p;
+  in.Xint = ctx->Xint.p;
+  in.XscaSH = ctx->XscaSH.p;
+  in.XintSH = ctx->XintSH.p;
+  for(int t = 0; t < 9; ++t)
+    in.tab[t] = ctx->cg[t].p;
+  DevBuf<double> dpts;
+  DevBuf<cplx> dout;
+  DevBuf<int> dinner;
+  dpts.alloc(3 * (size_t)npts);
+  dout.alloc(12 * (size_t)npts);
+  dinner.alloc((size_t)npts);
+  if(npts > 0) {
+    OB_CUDA(cudaMemcpyAsync(dpts.p, pts_sph, 3 * (size_t)npts * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
+    launch_fields(in, npts, dpts.p, dout.p, dinner.p, ctx->st);
+    ctx->launches += do_sh ? 2 : 1;
+    OB_CUDA(cudaMemcpyAsync(out, dout.p, 12 * (size_t)npts * sizeof(cplx), cudaMemcpyDeviceToHost, ctx->st));
+    if(inner)
+      OB_CUDA(cudaMemcpyAsync(inner, dinner.p, (size_t)npts * sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+    OB_CUDA(cudaStreamSynchronize(ctx->st));
+  }
+  OB_END
+}
+
 int ob_run(ob_ctx *ctx, const ob_gmres_opts *opts, int do_sh, double *X_sca, double *X_int, double *X_sca_SH,
            double *X_int_SH, double cs[5], int stats[2]) {
   OB_BEGIN

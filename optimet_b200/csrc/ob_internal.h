@@ -129,6 +129,21 @@ void launch_matvec_aca(AcaOperator const &op, const cplx *x, cplx *y_slice, cuda
 void aca_compress_single(const cplx *C_dev, int dim, double eps, cplx *U_dev, cplx *V_dev, int *rank_dev, int *piv_dev,
                          cudaStream_t st);
 
+// ---- ob_fields.cu (near-field maps: Result::getEHFields / setFields) ----
+struct FieldInputs {
+  int nobj, nMax, nMaxS, do_sh;
+  double omega;
+  cplx waveK, eps_b, mu_b;
+  const double *xyz, *radius;                      // device
+  const cplx *eps, *mu, *eps_SH, *mu_SH, *gamma;   // device, nobj each (absolute values)
+  const cplx *ainc;                                // [a ; b] incident coefficients at the origin, 2n
+  const cplx *Xsca, *Xint, *XscaSH, *XintSH;       // solution vectors, full length
+  const double *tab[9];                            // CG tables (W_m1m1, W_11, W_00 are used)
+};
+// pts: npts x (r, theta, phi); out: npts x 4 x 3 complex (E_FF, H_FF, E_SH, H_SH; Cartesian); inner: npts
+void launch_fields(FieldInputs const &in, long npts, const double *pts_dev, cplx *out_dev, int *inner_dev,
+                   cudaStream_t st);
+
 // ---- ob_lu.cu (device direct solve: blocked LU with partial pivoting, zgesv-style) ----
 struct LuWork {
   int cap = 0;

@@ -13,7 +13,8 @@ _lib = None
 
 HOST_SYMBOLS = ["obh_load_xml", "obh_load_xml_string", "obh_free", "obh_error", "obh_info", "obh_set_wavelength",
                 "obh_get_arrays", "obh_gmres_defaults", "obh_solver_create", "obh_solver_free", "obh_solver_error",
-                "obh_solver_ctx", "obh_solver_comm", "obh_solver_set_gmres", "obh_solver_set_aca_mode", "obh_solver_step", "obh_scan"]
+                "obh_solver_ctx", "obh_solver_comm", "obh_solver_set_gmres", "obh_solver_set_aca_mode", "obh_solver_step", "obh_scan",
+                "obh_field_simulation", "obh_grid_points"]
 
 
 def load():
@@ -90,6 +91,16 @@ class Case:
         load().obh_gmres_defaults(self.h, C.byref(o))
         return o
 
+    def grid_points(self):
+        """OutputGrid::getPoint enumeration of the case's field grid: (npts, 3) spherical (r, theta, phi)."""
+        p = self.info()["params"]
+        npts = int(p[2]) * int(p[5]) * int(p[8])
+        pts = np.zeros((npts, 3), dtype=np.float64)
+        n = C.c_long()
+        if load().obh_grid_points(self.h, _p(pts), C.c_long(npts), C.byref(n)):
+            raise RuntimeError("obh_grid_points failed")
+        return pts
+
     def scan_wavelengths_list(self):
         """Wavelengths of <scan><wavelength .../> (Simulation.cpp:634-644)."""
         p = self.info()["params"]
@@ -132,6 +143,18 @@ class Solver:
 
     def set_gmres(self, opts):
         load().obh_solver_set_gmres(self.s, C.byref(opts))
+
+    def field_simulation(self, case_file=None):
+        """Simulation::field_simulation on the case's <output type="field"> grid: dict with E_FF, H_FF, E_SH, H_SH
+        (npts, 3) Cartesian components in OutputGrid order (x fastest), inner (npts,), dims (nx, ny, nz)."""
+        p = self.case.info()["params"]
+        npts = int(p[2]) * int(p[5]) * int(p[8])
+        out = np.zeros((npts, 4, 3), dtype=np.complex128)
+        inner = np.zeros(npts, dtype=np.int32)
+        dims = (C.c_int * 3)()
+        self._chk(load().obh_field_simulation(self.s, self.case.h, None if case_file is None else case_file.encode(),
+                                             _p(out), _p(inner), C.c_long(npts), dims))
+        return dict(E_FF=out[:, 0], H_FF=out[:, 1], E_SH=out[:, 2], H_SH=out[:, 3], inner=inner, dims=tuple(dims))
 
     def set_aca_mode(self, mode):
         """-1 follow <ACA compression> (default), 0 never compress, 1 always compress."""

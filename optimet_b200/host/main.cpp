@@ -1,5 +1,5 @@
 // optimet3d_b200 -- command-line driver, same invocation as the reference (`Optimet3D input.xml`,
-// srcAna/main.cpp:23-46): runs the response scan on the B200 path and writes the reference's .dat files.
+// srcAna/main.cpp:23-46): runs the response scan (the reference's .dat files) or the field map on the B200 path.
 #include "ob_host.hpp"
 #include <iostream>
 
@@ -14,8 +14,14 @@ int main(int argc, char *argv[]) {
       caseFile = caseFile.substr(0, caseFile.size() - 4);
     optimet_b200::Run run = optimet_b200::simulation_input(caseFile + ".xml"); // Simulation.cpp:34-46
     optimet_b200::solver::B200Matrix solver(run, argc > 2 ? std::atoi(argv[2]) : 0);
+    if(run.outputType == 0) { // Simulation.cpp:48-53
+      optimet_b200::FieldMap fm = optimet_b200::field_simulation(run, solver, caseFile);
+      std::cout << "Field map " << fm.nx << " x " << fm.ny << " x " << fm.nz << " written to " << caseFile
+                << "_FF.field" << (run.excitation->SH_cond ? " and _SH.field" : "") << std::endl;
+      return 0;
+    }
     if(run.outputType != 11) {
-      std::cerr << "Only <output type=\"response\"> wavelength scans run on the B200 path (field maps are out of scope)"
+      std::cerr << "Only <output type=\"response\"> wavelength scans and <output type=\"field\"> maps run on the B200 path"
                 << std::endl;
       return 2;
     }

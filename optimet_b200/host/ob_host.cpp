@@ -561,7 +561,7 @@ std::shared_ptr<Excitation> read_excitation(const XmlNode &doc, int nMax, Electr
   return result;
 }
 
-// Reader.cpp:836-906 (field grids are parsed for completeness of outputType only)
+// Reader.cpp:836-906
 void read_output(const XmlNode &doc, Run &run) {
   const XmlNode *out = doc.child("output");
   if(!out)
@@ -569,8 +569,20 @@ void read_output(const XmlNode &doc, Run &run) {
   const std::string type = str(out, "type");
   if(type == "coefficients")
     run.outputType = 2;
-  if(type == "field")
+  if(type == "field") { // Reader.cpp:846-874 (grid in nm -> m; single-mode output is not part of the B200 path)
     run.outputType = 0;
+    const XmlNode *grid = ch(out, "grid");
+    const char *axes[3] = {"x", "y", "z"};
+    for(int a = 0; a < 3; ++a) {
+      const XmlNode *ax = ch(grid, axes[a]);
+      if(!ax)
+        throw std::runtime_error("field output: <grid> needs x, y and z axes");
+      run.params[3 * a] = ax->as_double("min") * 1e-9;
+      run.params[3 * a + 1] = ax->as_double("max") * 1e-9;
+      run.params[3 * a + 2] = ax->as_double("steps");
+    }
+    run.projection = str(ch(out, "projection"), "spherical") == "true";
+  }
   if(type == "response") {
     const XmlNode *scan = ch(out, "scan");
     if(const XmlNode *w = ch(scan, "wavelength")) {
@@ -848,6 +860,115 @@ std::vector<ScanLine> scan_wavelengths(Run &run, solver::B200Matrix &solver, std
     }
   }
   return lines;
+}
+
+// OutputGrid::getPoint (OutputGrid.cpp:132-157): regular Cartesian grid, x index fastest, every coordinate shifted by
+// 1e-12 m ("Correct for 0"), returned as Tools::toSpherical
+std::vector<double> grid_points(const double gp[9]) {
+  const int nx = (int)gp[2], ny = (int)gp[5], nz = (int)gp[8];
+  const long npts = (long)(gp[2] * gp[5] * gp[8]);
+  const double ax = std::abs(gp[1] - gp[0]) / (gp[2] - 1), ay = std::abs(gp[4] - gp[3]) / (gp[5] - 1),
+               az = std::abs(gp[7] - gp[6]) / (gp[8] - 1);
+  (void)nz;
+  std::vector<double> pts(3 * (size_t)npts);
+  for(long it = 0; it < npts; ++it) {
+    const int c0 = (int)(it % nx), c1 = (int)((it / nx) % ny), c2 = (int)(it / ((long)nx * ny));
+    Spherical s = toSpherical(Cartesian(gp[0] + c0 * ax + 1e-12, gp[3] + c1 * ay + 1e-12, gp[6] + c2 * az + 1e-12));
+    pts[3 * it] = s.rrr;
+    pts[3 * it + 1] = s.the;
+    pts[3 * it + 2] = s.phi;
+  }
+  return pts;
+}
+
+namespace solver {
+void B200Matrix::fields(std::vector<double> const &pts_sph, bool sh, std::vector<t_complex> &out,
+                        std::vector<int> &inner) const {
+  const long npts = (long)(pts_sph.size() / 3);
+  out.assign(12 * (size_t)npts, t_complex(0, 0));
+  inner.assign((size_t)npts, -1);
+  check(ob_fields(ctx, npts, pts_sph.data(), nullptr, nullptr, nullptr, nullptr, sh ? 1 : 0, (double *)out.data(),
+                  inner.data()));
+}
+} // namespace solver
+
+// Simulation::field_simulation (Simulation.cpp:319-366) + Result::setFields (Result.cpp:896-934)
+FieldMap field_simulation(Run &run, solver::B200Matrix &solver, std::string const &caseFile) {
+  FieldMap fm;
+  fm.nx = (int)run.params[2];
+  fm.ny = (int)run.params[5];
+  fm.nz = (int)run.params[8];
+  if(fm.nx < 1 || fm.ny < 1 || fm.nz < 1)
+    throw std::runtime_error("field output: grid steps must be positive");
+  solver.update(run);
+  Vector X_sca, X_int, X_sca_SH, X_int_SH;
+  solver.solve(X_sca, X_int, X_sca_SH, X_int_SH);
+  const bool sh = run.excitation->SH_cond;
+  std::vector<double> pts = grid_points(run.params);
+  std::vector<t_complex> all;
+  solver.fields(pts, sh, all, fm.inner);
+  const size_t npts = pts.size() / 3;
+  std::vector<t_complex> *dst[4] = {&fm.E_FF, &fm.H_FF, &fm.E_SH, &fm.H_SH};
+  for(int f = 0; f < 4; ++f)
+    dst[f]->assign(3 * npts, t_complex(0, 0));
+  const Cartesian c0 = toCartesian(run.geometry->objects[0].vR);
+  for(size_t i = 0; i < npts; ++i) {
+    for(int f = 0; f < 4; ++f)
+      for(int k = 0; k < 3; ++k)
+        (*dst[f])[3 * i + k] = all[(i * 4 + f) * 3 + k];
+    if(run.projection) { // Result.cpp:286-296: FF fields as spherical components about object 0; SH fields not set
+      const Cartesian p = toCartesian(Spherical(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]));
+      const Spherical rel = toSpherical(Cartesian(p.x - c0.x, p.y - c0.y, p.z - c0.z));
+      const double st = std::sin(rel.the), ct = std::cos(rel.the), sp = std::sin(rel.phi), cp = std::cos(rel.phi);
+      for(int f = 0; f < 2; ++f) { // Tools::fromProjection (Tools.cpp:290-301)
+        t_complex *v = &(*dst[f])[3 * i];
+        const t_complex x = v[0], y = v[1], z = v[2];
+        v[0] = st * cp * x + st * sp * y + ct * z;
+        v[1] = ct * cp * x + ct * sp * y - st * z;
+        v[2] = cp * y - sp * x;
+      }
+      for(int f = 2; f < 4; ++f)
+        for(int k = 0; k < 3; ++k)
+          (*dst[f])[3 * i + k] = t_complex(0, 0);
+    }
+  }
+  if(!caseFile.empty()) {
+    write_field_file(caseFile + "_FF.field", fm, fm.E_FF, fm.H_FF);
+    if(sh)
+      write_field_file(caseFile + "_SH.field", fm, fm.E_SH, fm.H_SH);
+  }
+  return fm;
+}
+
+// The reference writes <case>_FF.h5 / <case>_SH.h5 with groups Field_E, Field_H, each holding X, Y, Z/{real, imag}
+// and ABS/abs as [nx][ny][nz] doubles (Output.cpp:25-54, OutputGrid.cpp:41-92).  HDF5 is not available to this
+// build, so the same fourteen datasets are written, in that order and in the same C order (z index fastest), to a raw
+// little-endian file behind a one-line text header; scripts/field_to_h5.py rebuilds the reference's layout with h5py.
+void write_field_file(std::string const &path, FieldMap const &fm, std::vector<t_complex> const &E,
+                      std::vector<t_complex> const &H) {
+  std::ofstream f(path.c_str(), std::ios::binary);
+  if(!f)
+    throw std::runtime_error("cannot open " + path);
+  f << "OPTIMET_B200_FIELD 1 " << fm.nx << " " << fm.ny << " " << fm.nz
+    << " Field_E/X/real Field_E/X/imag Field_E/Y/real Field_E/Y/imag Field_E/Z/real Field_E/Z/imag Field_E/ABS/abs"
+    << " Field_H/X/real Field_H/X/imag Field_H/Y/real Field_H/Y/imag Field_H/Z/real Field_H/Z/imag Field_H/ABS/abs\n";
+  const size_t npts = (size_t)fm.nx * fm.ny * fm.nz;
+  std::vector<double> buf(npts);
+  std::vector<t_complex> const *src[2] = {&E, &H};
+  for(int g = 0; g < 2; ++g)
+    for(int d = 0; d < 7; ++d) {
+      for(size_t it = 0; it < npts; ++it) {
+        const size_t ix = it % fm.nx, iy = (it / fm.nx) % fm.ny, iz = it / ((size_t)fm.nx * fm.ny);
+        const t_complex *v = &(*src[g])[3 * it];
+        double val;
+        if(d == 6) // OutputGrid.cpp:174
+          val = std::sqrt(std::pow(std::abs(v[0]), 2) + std::pow(std::abs(v[1]), 2) + std::pow(std::abs(v[2]), 2));
+        else
+          val = (d & 1) ? v[d / 2].imag() : v[d / 2].real();
+        buf[(ix * fm.ny + iy) * fm.nz + iz] = val;
+      }
+      f.write((const char *)buf.data(), (std::streamsize)(npts * sizeof(double)));
+    }
 }
 
 } // namespace optimet_b200

@@ -37,6 +37,7 @@ struct Spherical {
 };
 struct Cartesian {
   t_real x, y, z;
+  Cartesian(t_real x_ = 0, t_real y_ = 0, t_real z_ = 0) : x(x_), y(y_), z(z_) {}
 };
 Spherical toSpherical(Cartesian const &p); // Tools.cpp:250-258
 Cartesian toCartesian(Spherical const &p); // Tools.cpp:38-42
@@ -117,8 +118,9 @@ public:
   int nMax, nMaxS;
   double params[9];
   int outputType; // 0 field, 2 coefficients, 11 wavelength scan, 12 radius scan, 112 both
+  bool projection; // field output: spherical projection about object 0 (Reader.cpp:860-861)
   BelosParams belos_params;
-  Run() : geometry(new Geometry), nMax(0), nMaxS(0), outputType(-1) {
+  Run() : geometry(new Geometry), nMax(0), nMaxS(0), outputType(-1), projection(false) {
     for(int i = 0; i < 9; ++i)
       params[i] = 0;
   }
@@ -156,6 +158,9 @@ public:
   void solve(Vector &X_sca_, Vector &X_int_, Vector &X_sca_SH, Vector &X_int_SH,
              std::vector<double *> CGcoeff = std::vector<double *>()) const;
   size_t scattering_size() const;
+  //! Result::setFields on the solution of the last solve(): pts_sph = npts x (r, theta, phi); out = npts x 4 x 3
+  //! (E_FF, H_FF, E_SH, H_SH, Cartesian components); inner = Geometry::checkInner per point
+  void fields(std::vector<double> const &pts_sph, bool sh, std::vector<t_complex> &out, std::vector<int> &inner) const;
   //! cross sections of the last solve, device reductions: ext, sca, abs(=ext-sca), sca_SH, abs_SH
   void cross_sections(double cs[5]) const { for(int i = 0; i < 5; ++i) cs[i] = last_cs[i]; }
   int iterations(int harmonic) const { return last_iters[harmonic - 1]; }
@@ -183,6 +188,19 @@ struct ScanLine {
 };
 //! Simulation::scan_wavelengths (Simulation.cpp:604-685); writes the four .dat files when caseFile != ""
 std::vector<ScanLine> scan_wavelengths(Run &run, solver::B200Matrix &solver, std::string const &caseFile);
+//! Field map of one run (Simulation::field_simulation): grid dims and npts x 3 Cartesian components per field, points
+//! in OutputGrid order (x index fastest)
+struct FieldMap {
+  int nx, ny, nz;
+  std::vector<t_complex> E_FF, H_FF, E_SH, H_SH;
+  std::vector<int> inner;
+};
+//! OutputGrid::getPoint enumeration of Run::params (OutputGrid.cpp:132-157): npts x (r, theta, phi)
+std::vector<double> grid_points(const double gp[9]);
+//! Simulation::field_simulation (Simulation.cpp:319-366); writes <case>_FF.field / <case>_SH.field when caseFile != ""
+FieldMap field_simulation(Run &run, solver::B200Matrix &solver, std::string const &caseFile);
+void write_field_file(std::string const &path, FieldMap const &fm, std::vector<t_complex> const &E,
+                      std::vector<t_complex> const &H);
 //! default GMRES options for a Run (see B200Matrix::set_gmres)
 ob_gmres_opts default_gmres(Run const &run);
 

@@ -188,4 +188,35 @@ int obh_scan(void *s_, void *h, const char *caseFile, double *lines, int maxline
   }
   OBH_CATCH(s)
 }
+// Simulation::field_simulation: out = npts x 4 x 3 complex (E_FF, H_FF, E_SH, H_SH), inner = npts, dims = nx, ny, nz
+int obh_field_simulation(void *s_, void *h, const char *caseFile, double *out, int *inner, long maxpts, int dims[3]) {
+  HostSolver *s = (HostSolver *)s_;
+  HostCase *c = (HostCase *)h;
+  OBH_TRY(s)
+  FieldMap fm = field_simulation(c->run, *s->s, caseFile ? caseFile : "");
+  dims[0] = fm.nx;
+  dims[1] = fm.ny;
+  dims[2] = fm.nz;
+  const long npts = (long)fm.nx * fm.ny * fm.nz;
+  if(npts > maxpts)
+    throw std::runtime_error("obh_field_simulation: output buffer too small");
+  t_complex *o = (t_complex *)out;
+  std::vector<t_complex> const *src[4] = {&fm.E_FF, &fm.H_FF, &fm.E_SH, &fm.H_SH};
+  for(long i = 0; i < npts; ++i) {
+    for(int f = 0; f < 4; ++f)
+      for(int k = 0; k < 3; ++k)
+        o[(i * 4 + f) * 3 + k] = (*src[f])[3 * i + k];
+    inner[i] = fm.inner[i];
+  }
+  OBH_CATCH(s)
+}
+int obh_grid_points(void *h, double *pts, long maxpts, long *npts) {
+  HostCase *c = (HostCase *)h;
+  std::vector<double> p = grid_points(c->run.params);
+  *npts = (long)(p.size() / 3);
+  if(*npts > maxpts)
+    return 1;
+  std::memcpy(pts, p.data(), p.size() * sizeof(double));
+  return 0;
+}
 } // extern "C"

@@ -21,7 +21,9 @@ def _material(m):
 
 
 def cluster_xml(xyz_nm, radius_nm, nMax, wavelength_nm, material=("silicon",), theta_deg=45.0, phi_deg=90.0,
-                Eth=1.0, Eph=0.0, sh=True, aca=False, scan=None, belos=None, mu=1.0, background=None):
+                Eth=1.0, Eph=0.0, sh=True, aca=False, scan=None, belos=None, mu=1.0, background=None, field=None,
+                projection=False):
+    """field = ((xmin, xmax, nx), (ymin, ymax, ny), (zmin, zmax, nz)) in nm selects <output type="field">."""
     xyz = np.asarray(xyz_nm, dtype=float).reshape(-1, 3)
     rad = np.broadcast_to(np.asarray(radius_nm, dtype=float), (len(xyz),))
     mats = material if isinstance(material, list) else [material] * len(xyz)
@@ -49,6 +51,12 @@ def cluster_xml(xyz_nm, radius_nm, nMax, wavelength_nm, material=("silicon",), t
         out.append('  <background type="absolute">\n    <epsilon value.real="%r" value.imag="%r" />\n'
                    '    <mu value.real="%r" value.imag="%r" />\n  </background>\n' % (eb.real, eb.imag, mb.real, mb.imag))
     out.append('</geometry>\n')
+    if field is not None:
+        out.append('<output type="field">\n  <grid type="cartesian">\n')
+        for ax, (lo, hi, steps) in zip("xyz", field):
+            out.append('    <%s min="%r" max="%r" steps="%d" />\n' % (ax, float(lo), float(hi), int(steps)))
+        out.append('  </grid>\n  <projection spherical="%s" />\n</output>\n' % ("true" if projection else "false"))
+        return "".join(out)
     if scan is None:
         scan = (wavelength_nm, wavelength_nm + 1, 1)
     out.append('<output type="response">\n  <scan type="A+E">\n    <wavelength initial="%r" final="%r" stepsize="%r" />\n'

@@ -2047,6 +2047,218 @@ static double getAbsorptionCrossSection_SH(Geometry const &g, Excitation const &
 }
 
 // ---------------------------------------------------------------------------
+// Field maps (Result.cpp:74-300, 896-934; AuxCoefficients.cpp:108-343; Geometry.cpp:147-163, 458-495;
+// Symbol.cpp:482-635; OutputGrid.cpp:132-157)
+// ---------------------------------------------------------------------------
+// AuxCoefficients ctor (AuxCoefficients.cpp:292-343): vector spherical wave functions M, N and the auxiliary
+// X-1, X+1 at R, projected onto Cartesian axes; regular = j_n, else h1_n
+struct AuxCoef {
+  std::vector<Vec3c> M, N, Xm, Xp;
+};
+static Vec3c v_scale(Vec3c const &v, cd s) { return Vec3c{v.rrr * s, v.the * s, v.phi * s}; }
+static Vec3c v_add(Vec3c const &a, Vec3c const &b) { return Vec3c{a.rrr + b.rrr, a.the + b.the, a.phi + b.phi}; }
+static AuxCoef aux_coefficients(Sph const &R, cd waveK, bool regular, int nMax) {
+  int N = flat_max(nMax);
+  AuxCoef out;
+  Vec3c zero{cd(0, 0), cd(0, 0), cd(0, 0)};
+  out.M.assign(N, zero);
+  out.N.assign(N, zero);
+  out.Xm.assign(N, zero);
+  out.Xp.assign(N, zero);
+  std::vector<cd> data, ddata;
+  bessel(regular ? Bessel : Hankel1, R.rrr * waveK, nMax, data, ddata);
+  const cd Kr = waveK * R.rrr;
+  for(int m = nMax; m >= -nMax; --m) {
+    std::vector<double> W, dW;
+    VIGdVIG(nMax, m, R, W, dW);
+    const double dm = std::pow(-1.0, m);
+    const cd exp_imphi(std::cos(m * R.phi), std::sin(m * R.phi));
+    for(int n = std::abs(m); n <= nMax; ++n) {
+      if(n == 0)
+        continue;
+      double A;
+      if(m == 0)
+        A = 0.0;
+      else if(std::abs(R.the) < 1e-10 || (std::abs(R.the) - consPi + 1e-10) > 0.0)
+        A = m / std::cos(R.the) * dW[n];
+      else
+        A = m / std::sin(R.the) * W[n];
+      const double dn = std::sqrt((2.0 * n + 1.0) / (4.0 * consPi * (n * (n + 1))));
+      Vec3c Pn{cd(W[n], 0), cd(0, 0), cd(0, 0)};
+      Vec3c Cn{cd(0, 0), cd(0.0, A), cd(-dW[n], 0.0)};
+      Vec3c Bn{cd(0, 0), cd(dW[n], 0.0), cd(0.0, A)};
+      const cd c_temp = dm * dn * exp_imphi;
+      Vec3c Mn = v_scale(Cn, c_temp * data[n]);                                   // compute_Mn :108-130
+      Vec3c Xm1 = v_scale(Pn, dm * dn * std::sqrt((double)(n * (n + 1))) * exp_imphi); // compute_Xm1 :134-152
+      Vec3c Xp1 = v_scale(Bn, c_temp);                                            // compute_Xp1 :155-175
+      Vec3c Nn;                                                                   // compute_Nn :179-213
+      const cd pre = (1.0 / Kr) * dm * dn;
+      Nn.rrr = pre * (((double)(n * (n + 1)) * data[n] * Pn.rrr) + ((Kr * ddata[n] + data[n]) * Bn.rrr)) * exp_imphi;
+      Nn.the = pre * (((double)(n * (n + 1)) * data[n] * Pn.the) + ((Kr * ddata[n] + data[n]) * Bn.the)) * exp_imphi;
+      Nn.phi = pre * (((double)(n * (n + 1)) * data[n] * Pn.phi) + ((Kr * ddata[n] + data[n]) * Bn.phi)) * exp_imphi;
+      int p = flatten_indices(n, m);
+      out.M[p] = toProjection(R, Mn);
+      out.N[p] = toProjection(R, Nn);
+      out.Xm[p] = toProjection(R, Xm1);
+      out.Xp[p] = toProjection(R, Xp1);
+    }
+  }
+  return out;
+}
+// Tools.cpp:303-308
+static Sph toPoint(Sph R, Sph P) {
+  Cart a = toCartesian(R), b = toCartesian(P);
+  return toSpherical(Cart{a.x - b.x, a.y - b.y, a.z - b.z});
+}
+// Geometry.cpp:147-163 (spheres): first object containing the point, else -1
+static int checkInner(Geometry const &g, Sph R_) {
+  for(size_t j = 0; j < g.objects.size(); ++j)
+    if(toPoint(R_, g.objects[j].vR).rrr <= g.objects[j].radius)
+      return (int)j;
+  return -1;
+}
+// Geometry::COEFFpartSH (Geometry.cpp:458-495) with symbol::CXm1 / CXp1 (Symbol.cpp:482-635): coefficients of the
+// particular solution of the SH problem inside object `obj` at radius r, one per SH harmonic
+static void COEFFpartSH(Geometry const &g, double *const CG[9], int obj, Excitation const &exc,
+                        std::vector<cd> const &internalCoef_FF, double r, std::vector<cd> &coefXmn,
+                        std::vector<cd> &coefXpl) {
+  const double *W_m1m1 = CG[4], *W_11 = CG[5], *W_00 = CG[6];
+  int nMax = g.nMax(), nMaxS = g.nMaxS();
+  int pMax = flat_max(nMax), pMaxS = flat_max(nMaxS);
+  size_t size1 = (size_t)pMax * pMax;
+  Scatterer const &object = g.objects[obj];
+  const cd eps_0 = consEpsilon0, mu_j = object.elmag.mu, eps_j = object.elmag.epsilon;
+  const cd gamma = object.elmag.gamma, eps_j2 = object.elmag.epsilon_SH;
+  const cd waveK_j1 = exc.omega() * std::sqrt(eps_j * mu_j);
+  std::vector<cd> data, ddata, dddata;
+  bessel(Bessel, r * waveK_j1, nMax, data, ddata);
+  bessel3der(r * waveK_j1, nMax, dddata);
+  std::vector<int> nn(pMax);
+  for(int p = 0; p < pMax; ++p) {
+    int n, m;
+    unflatten(p, n, m);
+    nn[p] = n;
+  }
+  coefXmn.assign(pMaxS, cd(0, 0));
+  coefXpl.assign(pMaxS, cd(0, 0));
+  for(int kk = 0; kk < pMaxS; ++kk) {
+    int n, m;
+    unflatten(kk, n, m);
+    cd COEFFXm1(0, 0), COEFFXp1(0, 0);
+    size_t brojac = 0;
+    for(int p = 0; p < pMax; ++p) {
+      cd cmn_1 = internalCoef_FF[(size_t)obj * 2 * pMax + p], dmn_1 = internalCoef_FF[pMax + (size_t)obj * 2 * pMax + p];
+      for(int q = 0; q < pMax; ++q, ++brojac) {
+        cd cmn_2 = internalCoef_FF[(size_t)obj * 2 * pMax + q], dmn_2 = internalCoef_FF[pMax + (size_t)obj * 2 * pMax + q];
+        size_t t = (size_t)kk * size1 + brojac;
+        double Wm1m1 = W_m1m1[t], W11 = W_11[t], W00 = W_00[t];
+        if(Wm1m1 == 0.0 && W11 == 0.0 && W00 == 0.0)
+          continue; // exact zeros of the tables (M1 + M2 != M): the reference adds 0 here
+        int n1 = nn[p], n2 = nn[q];
+        cd F_00 = data[n1] * ddata[n2];                                                                  // Symbol.cpp:80-88
+        cd F_11 = (waveK_j1 * ddata[n2] + data[n2] / r) * (waveK_j1 * ddata[n1] + data[n1] / r);       // :90-97
+        cd F_m1m1 = (1.0 / (std::pow(r, 2.0))) * (data[n1] * data[n2]);                                  // :99-107
+        cd F_d00 = data[n1] * ddata[n2] * waveK_j1 + waveK_j1 * ddata[n1] * data[n2];                    // :109-117
+        cd F_d11 = (std::pow(waveK_j1, 2.0) * dddata[n1] - (1.0 / std::pow(r, 2.0)) * data[n1] +
+                    (1.0 / r) * waveK_j1 * ddata[n1]) *
+                       (waveK_j1 * ddata[n2] + data[n2] / r) +
+                   (std::pow(waveK_j1, 2.0) * dddata[n2] - (1.0 / std::pow(r, 2.0)) * data[n2] +
+                    (1.0 / r) * waveK_j1 * ddata[n2]) *
+                       (waveK_j1 * ddata[n1] + data[n1] / r);                                             // :119-130
+        cd F_dm1m1 = (1.0 / (std::pow(r, 2.0))) * (waveK_j1 * ddata[n1] * data[n2] + data[n1] * waveK_j1 * ddata[n2]) -
+                     (2.0 / (std::pow(r, 3.0))) * (data[n1] * data[n2]);                                 // :132-141
+        const double sq = std::sqrt((double)(n1 * n2 * (n1 + 1) * (n2 + 1)));
+        COEFFXm1 += (-eps_0 / eps_j2) * gamma *
+                    (cmn_1 * cmn_2 * W00 * F_d00 +
+                     dmn_1 * dmn_2 * (1.0 / (std::pow(waveK_j1, 2.0))) * (W11 * F_d11 + Wm1m1 * sq * F_dm1m1)); // :540-546
+        COEFFXp1 += (-eps_0 / eps_j2) * gamma *
+                    (cmn_1 * cmn_2 * W00 * std::sqrt((double)(n * (n + 1))) * (1.0 / r) * F_00 +
+                     dmn_1 * dmn_2 * (1.0 / (std::pow(waveK_j1, 2.0))) *
+                         (W11 * std::sqrt((double)(n * (n + 1))) * (1.0 / r) * F_11 +
+                          Wm1m1 * sq * std::sqrt((double)(n * (n + 1))) * (1.0 / r) * F_m1m1));          // :618-626
+      }
+    }
+    coefXmn[kk] = COEFFXm1;
+    coefXpl[kk] = COEFFXp1;
+  }
+}
+// Result::getEHFields with projection_ = false (Result.cpp:74-300): E_FF, H_FF, E_SH, H_SH, Cartesian components
+static void getEHFields(Geometry const &g, Excitation const &exc, double *const CG[9], std::vector<cd> const &scatter_coef,
+                        std::vector<cd> const &internal_coef, std::vector<cd> const &scatter_coef_SH,
+                        std::vector<cd> const &internal_coef_SH, Sph R_, Vec3c out[4]) {
+  const Vec3c zero{cd(0, 0), cd(0, 0), cd(0, 0)};
+  Vec3c Efield_FF = zero, Einc_FF = zero, Hfield_FF = zero, Hinc_FF = zero, Efield_SH = zero, Egamma_SH = zero,
+        Hfield_SH = zero;
+  const int nMax = g.nMax(), nMaxS = g.nMaxS(), pMax = flat_max(nMax), pMaxS = flat_max(nMaxS);
+  const double omega = exc.omega();
+  const cd waveK = exc.waveK;
+  const cd waveK_0 = omega * std::sqrt(consEpsilon0 * consMu0);
+  const cd iZ = consCmi / std::sqrt(g.bground.mu / g.bground.epsilon);
+  const int intInd = checkInner(g, R_);
+  if(intInd < 0) {
+    AuxCoef inc = aux_coefficients(R_, waveK, true, nMax);
+    for(int p = 0; p < pMax; ++p) {
+      Einc_FF = v_add(Einc_FF, v_add(v_scale(inc.M[p], exc.dataIncAp[p]), v_scale(inc.N[p], exc.dataIncBp[p])));
+      Hinc_FF = v_add(Hinc_FF, v_scale(v_add(v_scale(inc.N[p], exc.dataIncAp[p]), v_scale(inc.M[p], exc.dataIncBp[p])), iZ));
+    }
+    for(size_t j = 0; j < g.objects.size(); ++j) {
+      Sph Rrel = toPoint(R_, g.objects[j].vR);
+      AuxCoef a = aux_coefficients(Rrel, waveK, false, nMax);
+      for(int p = 0; p < pMax; ++p) {
+        cd c1 = scatter_coef[j * 2 * pMax + p], c2 = scatter_coef[pMax + j * 2 * pMax + p];
+        Efield_FF = v_add(Efield_FF, v_add(v_scale(a.M[p], c1), v_scale(a.N[p], c2)));
+        Hfield_FF = v_add(Hfield_FF, v_scale(v_add(v_scale(a.N[p], c1), v_scale(a.M[p], c2)), iZ));
+      }
+    }
+    if(exc.SH_cond)
+      for(size_t j = 0; j < g.objects.size(); ++j) {
+        Sph Rrel = toPoint(R_, g.objects[j].vR);
+        AuxCoef a = aux_coefficients(Rrel, cd(2.0, 0.0) * waveK, false, nMaxS);
+        for(int p = 0; p < pMaxS; ++p) {
+          cd bmnSH = scatter_coef_SH[j * 2 * pMaxS + p], amnSH = scatter_coef_SH[j * 2 * pMaxS + pMaxS + p];
+          Efield_SH = v_add(Efield_SH, v_scale(v_add(v_scale(a.M[p], bmnSH), v_scale(a.N[p], amnSH)), waveK_0));
+          Hfield_SH = v_add(Hfield_SH, v_scale(v_add(v_scale(a.N[p], bmnSH), v_scale(a.M[p], amnSH)), iZ * waveK_0));
+        }
+      }
+  } else {
+    Scatterer const &o = g.objects[intInd];
+    Sph Rrel = toPoint(R_, o.vR);
+    AuxCoef a = aux_coefficients(Rrel, waveK_0 * std::sqrt(o.elmag.epsilon_r * o.elmag.mu_r), true, nMax);
+    const cd iZ_object = consCmi / std::sqrt(o.elmag.mu / o.elmag.epsilon);
+    for(int p = 0; p < pMax; ++p) {
+      cd c1 = internal_coef[intInd * 2 * pMax + p], c2 = internal_coef[pMax + intInd * 2 * pMax + p];
+      Efield_FF = v_add(Efield_FF, v_add(v_scale(a.M[p], c1), v_scale(a.N[p], c2)));
+      Hfield_FF = v_add(Hfield_FF, v_scale(v_add(v_scale(a.N[p], c1), v_scale(a.M[p], c2)), iZ_object));
+    }
+    if(exc.SH_cond) {
+      std::vector<cd> coeffXmn, coeffXpl;
+      COEFFpartSH(g, CG, intInd, exc, internal_coef, Rrel.rrr, coeffXmn, coeffXpl); // Result.cpp:916-919
+      AuxCoef s = aux_coefficients(Rrel, cd(2.0, 0.0) * waveK_0 * std::sqrt(o.elmag.epsilon_r_SH * o.elmag.mu_r_SH),
+                                   true, nMaxS);
+      const cd iZ_object_SH = consCmi / std::sqrt(o.elmag.mu_SH / o.elmag.epsilon_SH);
+      for(int p = 0; p < pMaxS; ++p) {
+        cd cmnSH = internal_coef_SH[intInd * 2 * pMaxS + p], dmnSH = internal_coef_SH[pMaxS + intInd * 2 * pMaxS + p];
+        Efield_SH = v_add(Efield_SH, v_scale(v_add(v_scale(s.M[p], cmnSH), v_scale(s.N[p], dmnSH)), waveK_0));
+        Egamma_SH = v_add(Egamma_SH, v_add(v_scale(s.Xm[p], coeffXmn[p]), v_scale(s.Xp[p], coeffXpl[p])));
+        Hfield_SH = v_add(Hfield_SH, v_scale(v_add(v_scale(s.N[p], cmnSH), v_scale(s.M[p], dmnSH)), iZ_object_SH * waveK_0));
+      }
+    }
+  }
+  out[0] = v_add(Einc_FF, Efield_FF);
+  out[1] = v_add(Hinc_FF, Hfield_FF);
+  out[2] = v_add(Efield_SH, Egamma_SH);
+  out[3] = Hfield_SH;
+}
+// OutputGrid::getPoint (OutputGrid.cpp:132-157): point `it` of the regular Cartesian grid, x fastest, + 1e-12
+static Sph grid_point(const double gp[9], long it) {
+  const int nx = (int)gp[2], ny = (int)gp[5];
+  const double ax = std::abs(gp[1] - gp[0]) / (gp[2] - 1), ay = std::abs(gp[4] - gp[3]) / (gp[5] - 1),
+               az = std::abs(gp[7] - gp[6]) / (gp[8] - 1);
+  const int c0 = (int)(it % nx), c1 = (int)((it / nx) % ny), c2 = (int)(it / ((long)nx * ny));
+  return toSpherical(Cart{gp[0] + c0 * ax + 1e-12, gp[3] + c1 * ay + 1e-12, gp[6] + c2 * az + 1e-12});
+}
+
+// ---------------------------------------------------------------------------
 // A complete case (what Simulation::scan_wavelengths drives, Simulation.cpp:604-685)
 // ---------------------------------------------------------------------------
 struct Case {
@@ -2404,6 +2616,73 @@ int orc_case_cross_sections(void *h, double out[5]) {
     out[3] = getScatteringCrossSection_SH(c->geom, c->exc, c->X_sca_SH);
     out[4] = getAbsorptionCrossSection_SH(c->geom, c->exc, T, c->X_int, c->X_int_SH);
   }
+  ORC_CATCH(h)
+}
+// ---- field maps ----
+// AuxCoefficients(R, waveK, regular, nMax): out = 4 x n x 3 complex (M, N, Xm, Xp; Cartesian components)
+int orc_aux_coefficients(const double R[3], const double k[2], int regular, int nMax, double *out) {
+  ORC_TRY
+  AuxCoef a = aux_coefficients(Sph{R[0], R[1], R[2]}, cd(k[0], k[1]), regular != 0, nMax);
+  cd *o = (cd *)out;
+  int N = flat_max(nMax);
+  std::vector<Vec3c> const *v[4] = {&a.M, &a.N, &a.Xm, &a.Xp};
+  for(int t = 0; t < 4; ++t)
+    for(int p = 0; p < N; ++p) {
+      o[((size_t)t * N + p) * 3 + 0] = (*v[t])[p].rrr;
+      o[((size_t)t * N + p) * 3 + 1] = (*v[t])[p].the;
+      o[((size_t)t * N + p) * 3 + 2] = (*v[t])[p].phi;
+    }
+  ORC_CATCH(nullptr)
+}
+// Result::setFields on the case's current solution vectors (X_sca, X_int, X_sca_SH, X_int_SH).
+// pts_sph: npts x (r, theta, phi) as OutputGrid::getPoint returns them; out: npts x 4 x 3 complex
+// (E_FF, H_FF, E_SH, H_SH Cartesian components); inner: npts ints (checkInner)
+int orc_case_fields(void *h, long npts, const double *pts_sph, double *out, int *inner) {
+  ORC_TRY
+  Case *c = (Case *)h;
+  double *T[9] = {0};
+  if(c->exc.SH_cond) {
+    ensure_tables(c);
+    for(int t = 0; t < 9; ++t)
+      T[t] = c->tables[t].data();
+  }
+  cd *o = (cd *)out;
+  parallel_for((int)npts, [&](int i) {
+    Sph R{pts_sph[3 * i], pts_sph[3 * i + 1], pts_sph[3 * i + 2]};
+    Vec3c f[4];
+    getEHFields(c->geom, c->exc, T, c->X_sca, c->X_int, c->X_sca_SH, c->X_int_SH, R, f);
+    for(int t = 0; t < 4; ++t) {
+      o[((size_t)i * 4 + t) * 3 + 0] = f[t].rrr;
+      o[((size_t)i * 4 + t) * 3 + 1] = f[t].the;
+      o[((size_t)i * 4 + t) * 3 + 2] = f[t].phi;
+    }
+    if(inner)
+      inner[i] = checkInner(c->geom, R);
+  });
+  ORC_CATCH(h)
+}
+// OutputGrid point enumeration: gp = {x0, x1, nx, y0, y1, ny, z0, z1, nz} (Run::params, metres); out: npts x 3
+int orc_grid_points(const double gp[9], double *out) {
+  long n = (long)(gp[2] * gp[5] * gp[8]);
+  for(long i = 0; i < n; ++i) {
+    Sph p = grid_point(gp, i);
+    out[3 * i] = p.rrr;
+    out[3 * i + 1] = p.the;
+    out[3 * i + 2] = p.phi;
+  }
+  return 0;
+}
+int orc_case_coeff_part_sh(void *h, int obj, double r, double *xmn, double *xpl) {
+  ORC_TRY
+  Case *c = (Case *)h;
+  ensure_tables(c);
+  double *T[9];
+  for(int t = 0; t < 9; ++t)
+    T[t] = c->tables[t].data();
+  std::vector<cd> a, b;
+  COEFFpartSH(c->geom, T, obj, c->exc, c->X_int, r, a, b);
+  memcpy(xmn, a.data(), a.size() * sizeof(cd));
+  memcpy(xpl, b.data(), b.size() * sizeof(cd));
   ORC_CATCH(h)
 }
 // ---- ACA unit surface ----

@@ -114,6 +114,23 @@ def cg_tables(nMax, nMaxS):
     return T
 
 
+def aux_coefficients(R_sph, k, regular, nMax):
+    """AuxCoefficients(R, waveK, regular, nMax) -> dict of M, N, Xm, Xp, each (n, 3) complex (Cartesian components)."""
+    n = nMax * (nMax + 2)
+    out = np.zeros((4, n, 3), dtype=np.complex128)
+    lib().orc_aux_coefficients((C.c_double * 3)(*R_sph), _c2(k), int(bool(regular)), int(nMax), _p(out))
+    return dict(M=out[0], N=out[1], Xm=out[2], Xp=out[3])
+
+
+def grid_points(params):
+    """OutputGrid::getPoint enumeration of Run::params = (x0, x1, nx, y0, y1, ny, z0, z1, nz) -> (npts, 3) spherical."""
+    gp = (C.c_double * 9)(*[float(v) for v in params])
+    n = int(params[2]) * int(params[5]) * int(params[8])
+    out = np.zeros((n, 3), dtype=np.float64)
+    lib().orc_grid_points(gp, _p(out))
+    return out
+
+
 def matvec(S, x):
     S = np.asfortranarray(S, dtype=np.complex128)
     x = np.ascontiguousarray(x, dtype=np.complex128)
@@ -292,6 +309,22 @@ class Case:
         y = np.zeros_like(x)
         self._chk(lib().orc_case_matvec_aca(self.h, int(harmonic), _p(x), _p(y)))
         return y
+
+    def fields(self, pts_sph):
+        """Result::setFields at spherical points (npts, 3) on the current solution vectors:
+        (npts, 4, 3) complex = E_FF, H_FF, E_SH, H_SH Cartesian components, and checkInner per point."""
+        pts = np.ascontiguousarray(pts_sph, dtype=np.float64).reshape(-1, 3)
+        out = np.zeros((len(pts), 4, 3), dtype=np.complex128)
+        inner = np.zeros(len(pts), dtype=np.int32)
+        self._chk(lib().orc_case_fields(self.h, C.c_long(len(pts)), _p(pts), _p(out), _p(inner)))
+        return out, inner
+
+    def coeff_part_sh(self, obj, r):
+        nm = self.info()["nMaxS"]
+        a = np.zeros(nm * (nm + 2), dtype=np.complex128)
+        b = np.zeros_like(a)
+        self._chk(lib().orc_case_coeff_part_sh(self.h, int(obj), C.c_double(r), _p(a), _p(b)))
+        return a, b
 
     def vector(self, which):
         i = self.info()
