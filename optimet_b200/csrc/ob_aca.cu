@@ -369,19 +369,29 @@ template <class T> static T *dev_alloc(size_t n) {
   return p;
 }
 
+void AcaScratch::release() {
+  void *ptrs[] = {slab, scrU, scrV, d_jobs, d_jobs_dense, d_rank};
+  for(void *p : ptrs)
+    if(p)
+      cudaFree(p);
+  slab = scrU = scrV = nullptr;
+  d_jobs = d_jobs_dense = nullptr;
+  d_rank = nullptr;
+  elems = blocks = 0;
+}
 void AcaOperator::release() {
   for(cplx *p : chunks)
     cudaFree(p);
   chunks.clear();
-  if(desc)
-    cudaFree(desc);
-  if(piv)
-    cudaFree(piv);
-  if(partial)
-    cudaFree(partial);
+  chunk_cap.clear();
+  void *ptrs[] = {desc, piv, partial};
+  for(void *p : ptrs)
+    if(p)
+      cudaFree(p);
   desc = nullptr;
   piv = nullptr;
   partial = nullptr;
+  partial_elems = desc_blocks = 0;
   h_desc.clear();
   built = false;
 }
@@ -393,21 +403,42 @@ static bool admissible(const double *xyz, const double *radius, int i, int j) {
   return distance >= 2.0 * (radius[i] + radius[j]);
 }
 
-void aca_build(AcaOperator &op, VtacTableSet const &ts, const double *d_xyz, const cplx *Tdiag, cplx k, int nobj,
+void aca_build(AcaOperator &op, AcaScratch &scr, VtacTableSet const &ts, const double *d_xyz, const cplx *Tdiag, cplx k, int nobj,
                int first, int count, const double *h_xyz, const double *h_radius, double eps, size_t budget_bytes,
                int sm_count, cudaStream_t st, long &launches) {
-  op.release();
+  // device buffers persist across builds (a wavelength sweep rebuilds the operator at every step): scratch, job lists
+  // and the per-batch storage chunks are reused whenever they are large enough
   const int dim = 2 * flat_max(ts.nMax);
+  const size_t nblocks = (size_t)count * nobj;
+  if(op.dim != dim || op.nobj != nobj || op.count != count)
+    op.release();
+  op.built = false;
   op.nobj = nobj;
   op.dim = dim;
   op.first = first;
   op.count = count;
-  op.h_desc.assign((size_t)count * nobj, AcaDesc());
-  op.desc = dev_alloc<AcaDesc>((size_t)count * nobj);
-  op.piv = dev_alloc<int>((size_t)count * nobj * 2 * dim);
-  OB_CUDA(cudaMemsetAsync(op.piv, 0xff, (size_t)count * nobj * 2 * dim * sizeof(int), st));
-  op.nch = std::max(1, std::min(nobj, (2 * sm_count + count - 1) / std::max(1, count)));
-  op.partial = op.nch > 1 ? dev_alloc<cplx>((size_t)op.nch * count * dim) : nullptr;
+  op.h_desc.assign(nblocks, AcaDesc());
+  if(op.desc_blocks < nblocks) {
+    if(op.desc)
+      cudaFree(op.desc);
+    if(op.piv)
+      cudaFree(op.piv);
+    op.desc = dev_alloc<AcaDesc>(nblocks);
+    op.piv = dev_alloc<int>(nblocks * 2 * dim);
+    op.desc_blocks = nblocks;
+  }
+  OB_CUDA(cudaMemsetAsync(op.piv, 0xff, nblocks * 2 * dim * sizeof(int), st));
+  // ~8 CTAs per SM: the U (V x) blocks are short dependent phases, latency is hidden by residency, not by ILP
+  const int nch = std::max(1, std::min(nobj, (8 * sm_count + count - 1) / std::max(1, count)));
+  if(op.partial && (nch != op.nch || op.partial_elems < (size_t)nch * count * dim)) {
+    cudaFree(op.partial);
+    op.partial = nullptr;
+  }
+  op.nch = nch;
+  if(nch > 1 && !op.partial) {
+    op.partial_elems = (size_t)nch * count * dim;
+    op.partial = dev_alloc<cplx>(op.partial_elems);
+  }
   op.stored_elems = 0;
   op.n_lowrank = op.n_dense = 0;
   op.rank_sum = 0;
@@ -416,12 +447,21 @@ void aca_build(AcaOperator &op, VtacTableSet const &ts, const double *d_xyz, con
   const size_t blk = (size_t)dim * dim;
   const size_t per_row = 3 * blk * nobj * sizeof(cplx);
   int rows_b = (int)std::max<size_t>(1, std::min<size_t>(count, budget_bytes / std::max<size_t>(1, per_row)));
-  cplx *slab = dev_alloc<cplx>((size_t)rows_b * nobj * blk);
-  cplx *scrU = dev_alloc<cplx>((size_t)rows_b * nobj * blk);
-  cplx *scrV = dev_alloc<cplx>((size_t)rows_b * nobj * blk);
-  int2 *d_jobs = dev_alloc<int2>((size_t)rows_b * nobj);
-  int2 *d_jobs_dense = dev_alloc<int2>((size_t)rows_b * nobj);
-  int *d_rank = dev_alloc<int>((size_t)rows_b * nobj);
+  if(scr.blocks < (size_t)rows_b * nobj || scr.elems < (size_t)rows_b * nobj * blk) { // shared by both harmonics
+    scr.release();
+    scr.blocks = (size_t)rows_b * nobj;
+    scr.elems = scr.blocks * blk;
+    scr.slab = dev_alloc<cplx>(scr.elems);
+    scr.scrU = dev_alloc<cplx>(scr.elems);
+    scr.scrV = dev_alloc<cplx>(scr.elems);
+    scr.d_jobs = dev_alloc<int2>(scr.blocks);
+    scr.d_jobs_dense = dev_alloc<int2>(scr.blocks);
+    scr.d_rank = dev_alloc<int>(scr.blocks);
+  }
+  cplx *slab = scr.slab, *scrU = scr.scrU, *scrV = scr.scrV;
+  int2 *d_jobs = scr.d_jobs, *d_jobs_dense = scr.d_jobs_dense;
+  int *d_rank = scr.d_rank;
+  size_t batch_index = 0;
   std::vector<int2> jobs, jobs_dense;
   std::vector<int> ranks;
   std::string fail;
@@ -468,8 +508,21 @@ void aca_build(AcaOperator &op, VtacTableSet const &ts, const double *d_xyz, con
     }
     if(!fail.empty())
       break;
-    cplx *chunk = dev_alloc<cplx>(total);
-    op.chunks.push_back(chunk);
+    // storage chunk of this batch: reuse the previous build's allocation when it is large enough (5 % slack on new ones)
+    if(batch_index < op.chunks.size() && op.chunk_cap[batch_index] < total) {
+      cudaFree(op.chunks[batch_index]);
+      op.chunks[batch_index] = nullptr;
+    }
+    if(batch_index >= op.chunks.size()) {
+      op.chunks.push_back(nullptr);
+      op.chunk_cap.push_back(0);
+    }
+    if(!op.chunks[batch_index]) {
+      op.chunk_cap[batch_index] = total + total / 20;
+      op.chunks[batch_index] = dev_alloc<cplx>(op.chunk_cap[batch_index]);
+    }
+    cplx *chunk = op.chunks[batch_index];
+    ++batch_index;
     size_t off = 0;
     for(size_t t = 0; t < jobs.size(); ++t) {
       AcaDesc &d = op.h_desc[(size_t)(il0 + jobs[t].x) * nobj + jobs[t].y];
@@ -504,12 +557,11 @@ void aca_build(AcaOperator &op, VtacTableSet const &ts, const double *d_xyz, con
     }
     OB_CUDA(cudaStreamSynchronize(st)); // jobs / ranks are reused by the next batch
   }
-  cudaFree(slab);
-  cudaFree(scrU);
-  cudaFree(scrV);
-  cudaFree(d_jobs);
-  cudaFree(d_jobs_dense);
-  cudaFree(d_rank);
+  while(op.chunks.size() > batch_index) { // fewer batches than the previous build
+    cudaFree(op.chunks.back());
+    op.chunks.pop_back();
+    op.chunk_cap.pop_back();
+  }
   if(!fail.empty()) {
     op.release();
     throw Error(fail);

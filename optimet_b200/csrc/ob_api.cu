@@ -121,6 +121,7 @@ struct ob_ctx {
   std::vector<double> h_xyz, h_radius; // host copies: ACA admissibility test (PreconditionedMatrix.cpp:526)
   double eps_aca = 1e-3;               // PreconditionedMatrix.cpp:772
   size_t aca_budget = (size_t)4 << 30; // scratch bytes of one ACA assembly batch
+  AcaScratch aca_scratch;
   // frequency / materials
   bool have_freq = false, have_inc = false;
   double omega = 0;
@@ -254,6 +255,7 @@ static void assemble(ob_ctx *c, int harmonic) {
     }
     H.S.release();
     H.aca.release();
+    c->aca_scratch.release();
     H.AB.alloc(std::max<size_t>(1, pair_storage_elems(H.pplan)));
     launch_assemble_pairs(ts, c->xyz.p, H.k, H.pplan.pair_ij, H.pplan.npairs, H.AB.p, c->st);
     c->launches += 1;
@@ -264,13 +266,14 @@ static void assemble(ob_ctx *c, int harmonic) {
   H.AB.release();
   if(c->operator_mode == 2) { // Scattering_matrix_ACA_FF / _SH (PreconditionedMatrix.cpp:489-551, 699-759)
     H.S.release();
-    aca_build(H.aca, ts, c->xyz.p, c->fac[harmonic == 1 ? 0 : 1].p, H.k, c->nobj, c->first, c->count, c->h_xyz.data(),
+    aca_build(H.aca, c->aca_scratch, ts, c->xyz.p, c->fac[harmonic == 1 ? 0 : 1].p, H.k, c->nobj, c->first, c->count, c->h_xyz.data(),
               c->h_radius.data(), c->eps_aca, c->aca_budget, c->sm_count, c->st, c->launches);
     H.mode = 2;
     H.assembled = true;
     return;
   }
   H.aca.release();
+  c->aca_scratch.release();
   H.mode = 0;
   H.S.alloc(M * N);
   launch_assemble(ts, c->xyz.p, c->fac[harmonic == 1 ? 0 : 1].p, H.k, c->nobj, c->first, c->count, H.S.p, M, c->st);
@@ -906,6 +909,7 @@ void ob_destroy(ob_ctx *ctx) {
     ctx->hs[i].aca.release();
   }
   ctx->lu.release();
+  ctx->aca_scratch.release();
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   cudaEventDestroy(ctx->evm0);

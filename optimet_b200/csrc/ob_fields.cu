@@ -6,10 +6,12 @@
 //   Geometry::checkInner, COEFFpartSH        srcAna/Geometry.cpp:147-163, 458-495
 //   symbol::CXm1 / CXp1 (+ F_x radial terms) srcAna/Symbol.cpp:80-141, 482-635
 //
-// k_fields: one warp per grid point.  Lane <-> azimuthal order m in [-nMax, nMax]; every lane runs the Wigner-d
-// recursion of its m upward in n (VIGdVIG streamed: only three consecutive values live in registers) and adds the
-// (n, m) vector spherical waves times the solved coefficients, already projected onto Cartesian axes, into its own
-// accumulators; one warp reduction per point at the end.  Outside the spheres: incident (regular, about the origin) +
+// k_fields: one warp per grid point.  The Wigner-d recursion of one azimuthal order m runs upward in n (VIGdVIG
+// streamed: only three consecutive values live in registers) and adds the (n, m) vector spherical waves times the
+// solved coefficients, already projected onto Cartesian axes, into per-lane accumulators; one warp reduction per
+// point at the end.  Two lane layouts: lane <-> particle for clusters of >= 16 particles (every lane sums all (n, m)
+// of its own particles: no redundant radial functions, all 32 lanes busy), lane <-> m in [-nMax, nMax] otherwise and
+// for the single-centre sums (incident field, interior points).  Outside the spheres: incident (regular, about the origin) +
 // scattered FF and SH (Hankel, about every particle).  Inside a sphere: internal FF and SH (regular, k of the sphere).
 // k_field_egamma: one CTA per interior point; the bilinear coefficients of the SH particular solution at the point's
 // radius (CXm1 / CXp1: n_S x n x nMax table-driven terms) are built in shared memory, then contracted with X-1, X+1.
@@ -54,35 +56,46 @@ __device__ void radial_set(cplx z, int L, bool regular, cplx *data, cplx *ddata)
     ddata[i] = csub(cscale(cmul(iz, data[i]), (double)i), data[i + 1]);
 }
 
-// Adds sum_n [M_nm c1 + N_nm c2] to E and sum_n [N_nm c1 + M_nm c2] to H for this lane's m (Cartesian components),
-// and optionally sum_n [X-1_nm g1 + X+1_nm g2] to G.  c1 / c2 / g1 / g2 are indexed by the flat harmonic index.
-// (r, the, phi) = point relative to the expansion centre; data / ddata = radial set of k r.
-__device__ void add_waves(int m, int nMax, double r, double the, double phi, cplx k, const cplx *data, const cplx *ddata,
-                          const cplx *__restrict__ c1, const cplx *__restrict__ c2, Acc3 &E, Acc3 &H,
-                          const cplx *g1, const cplx *g2, Acc3 *G) {
-  // VIGdVIG (AuxCoefficients.cpp:216-290), streamed upward in n
-  const int ma = m < 0 ? -m : m;
-  const bool pole = (fabs(the) < 1e-10) || (fabs(the) - FLD_PI + 1e-10 > 0.0);
-  double vig_the = m < 0 ? FLD_PI - the : the;
-  if(pole)
-    vig_the += 1e-6;
-  const double vx = cos(vig_the), vs = sin(vig_the);
-  double W = 1.0; // 2^-m sqrt((2m)!)/m! (1-x)^(m/2) (1+x)^(m/2)
-  for(int i = 1; i <= ma; ++i)
-    W *= sqrt((2.0 * i - 1.0) / (2.0 * i));
-  W *= pow(1.0 - vx, 0.5 * ma) * pow(1.0 + vx, 0.5 * ma);
-  double Wm1 = 0.0;
+// Everything about one (point, expansion centre) pair that does not depend on m
+struct WaveSetup {
   Proj P;
-  sincos(the, &P.st, &P.ct);
-  sincos(phi, &P.sp, &P.cp);
-  double em_s, em_c;
-  sincos((double)m * phi, &em_s, &em_c);
+  double the, cos_the, sin_the;
+  bool pole;
+  double vx[2], vs[2], base[2]; // Wigner argument cos / sin and sqrt(1-x) sqrt(1+x) for m >= 0 ([0]) and m < 0 ([1])
+  cplx Kr, iKr;
+};
+__device__ __forceinline__ void wave_setup(WaveSetup &S, double r, double the, double phi, cplx k) {
+  sincos(the, &S.P.st, &S.P.ct);
+  sincos(phi, &S.P.sp, &S.P.cp);
+  S.the = the;
+  S.cos_the = S.P.ct;
+  S.sin_the = S.P.st;
+  S.pole = (fabs(the) < 1e-10) || (fabs(the) - FLD_PI + 1e-10 > 0.0);
+  for(int neg = 0; neg < 2; ++neg) { // VIGdVIG (AuxCoefficients.cpp:216-232): m < 0 runs on pi - theta
+    double vig_the = neg ? FLD_PI - the : the;
+    if(S.pole)
+      vig_the += 1e-6;
+    sincos(vig_the, &S.vs[neg], &S.vx[neg]);
+    S.base[neg] = pow(1.0 - S.vx[neg], 0.5) * pow(1.0 + S.vx[neg], 0.5);
+  }
+  S.Kr = cscale(k, r);
+  S.iKr = cdiv(mk(1, 0), S.Kr);
+}
+
+// Adds sum_n [M_nm c1 + N_nm c2] to E and sum_n [N_nm c1 + M_nm c2] to H for one azimuthal order m (Cartesian
+// components), and optionally sum_n [X-1_nm g1 + X+1_nm g2] to G.  c1 / c2 / g1 / g2 are indexed by the flat harmonic
+// index; data / ddata = radial set of k r; Wmm = d^{|m|}_{0|m|} seed; (em_c, em_s) = exp(i m phi).
+__device__ __forceinline__ void wave_column(WaveSetup const &S, int m, int nMax, double Wmm, double em_c, double em_s,
+                                            const cplx *data, const cplx *ddata, const cplx *__restrict__ c1,
+                                            const cplx *__restrict__ c2, Acc3 &E, Acc3 &H, const cplx *g1,
+                                            const cplx *g2, Acc3 *G) {
+  const int ma = m < 0 ? -m : m, neg = m < 0 ? 1 : 0;
+  const double vx = S.vx[neg], vs = S.vs[neg];
+  double W = Wmm, Wm1 = 0.0;
   const double dm = (ma & 1) ? -1.0 : 1.0;
-  const cplx Kr = cscale(k, r);
-  const cplx iKr = cdiv(mk(1, 0), Kr);
   const double m2 = (double)(ma * ma);
   for(int s = ma; s <= nMax; ++s) {
-    // B.22 / B.26 with W[s-1] = 0 below n_min
+    // B.22 / B.26 streamed upward in n (W[s-1] = 0 below n_min); the last step is the reference's Wn_max formula
     const double Wp1 = ((2 * s + 1) * vx * W - sqrt((double)(s * s) - m2) * Wm1) / sqrt((double)((s + 1) * (s + 1)) - m2);
     if(s >= 1) {
       double dW = (((s * sqrt((double)((s + 1) * (s + 1)) - m2) * Wp1) / (2 * s + 1)) -
@@ -97,10 +110,10 @@ __device__ void add_waves(int m, int nMax, double r, double the, double phi, cpl
       double A; // compute_Cn / compute_Bn (AuxCoefficients.cpp:54-106)
       if(m == 0)
         A = 0.0;
-      else if(pole)
-        A = m / cos(the) * dW;
+      else if(S.pole)
+        A = m / S.cos_the * dW;
       else
-        A = m / sin(the) * Wn;
+        A = m / S.sin_the * Wn;
       const double dn = sqrt((2.0 * s + 1.0) / (4.0 * FLD_PI * (double)(s * (s + 1))));
       const cplx ct = mk(dm * dn * em_c, dm * dn * em_s); // dm dn exp(i m phi)
       const cplx zn = data[s], dzn = ddata[s];
@@ -108,23 +121,62 @@ __device__ void add_waves(int m, int nMax, double r, double the, double phi, cpl
       const cplx cz = cmul(ct, zn);
       const cplx Mt = cmuli(cscale(cz, A)), Mp = cscale(cz, -dW);
       // N = (1/Kr) dm dn [n(n+1) z_n P_n + (Kr z'_n + z_n) B_n] e^{im phi}, P_n = (W,0,0), B_n = (0, dW, iA)
-      const cplx pre = cmul(iKr, ct);
-      const cplx rad = cadd(cmul(Kr, dzn), zn);
+      const cplx pre = cmul(S.iKr, ct);
+      const cplx rad = cadd(cmul(S.Kr, dzn), zn);
       const cplx Nr = cscale(cmul(pre, zn), (double)(s * (s + 1)) * Wn);
       const cplx pr = cmul(pre, rad);
       const cplx Nt = cscale(pr, dW), Np = cmuli(cscale(pr, A));
       const int p = s * (s + 1) - m - 1;
       const cplx a = c1[p], b = c2[p];
-      add_projected(E, P, cmul(Nr, b), cadd(cmul(Mt, a), cmul(Nt, b)), cadd(cmul(Mp, a), cmul(Np, b)));
-      add_projected(H, P, cmul(Nr, a), cadd(cmul(Nt, a), cmul(Mt, b)), cadd(cmul(Np, a), cmul(Mp, b)));
+      add_projected(E, S.P, cmul(Nr, b), cadd(cmul(Mt, a), cmul(Nt, b)), cadd(cmul(Mp, a), cmul(Np, b)));
+      add_projected(H, S.P, cmul(Nr, a), cadd(cmul(Nt, a), cmul(Mt, b)), cadd(cmul(Np, a), cmul(Mp, b)));
       if(G) { // X-1 = dm dn sqrt(n(n+1)) e^{im phi} P_n ; X+1 = dm dn e^{im phi} B_n
         const cplx xm = cscale(cmul(ct, g1[p]), sqrt((double)(s * (s + 1))) * Wn);
         const cplx xb = cmul(ct, g2[p]);
-        add_projected(*G, P, xm, cscale(xb, dW), cmuli(cscale(xb, A)));
+        add_projected(*G, S.P, xm, cscale(xb, dW), cmuli(cscale(xb, A)));
       }
     }
     Wm1 = W;
     W = Wp1;
+  }
+}
+// d^{m}_{0m} seed (AuxCoefficients.cpp:236-241): 2^-m sqrt((2m)!)/m! (1-x)^(m/2) (1+x)^(m/2)
+__device__ __forceinline__ double wigner_seed(int ma, double base) {
+  double W = 1.0;
+  for(int i = 1; i <= ma; ++i)
+    W *= sqrt((2.0 * i - 1.0) / (2.0 * i)) * base;
+  return W;
+}
+// one azimuthal order (lane <-> m layout: small clusters, incident field, interior points)
+__device__ void add_waves(int m, int nMax, double r, double the, double phi, cplx k, const cplx *data, const cplx *ddata,
+                          const cplx *__restrict__ c1, const cplx *__restrict__ c2, Acc3 &E, Acc3 &H,
+                          const cplx *g1, const cplx *g2, Acc3 *G) {
+  WaveSetup S;
+  wave_setup(S, r, the, phi, k);
+  double em_s, em_c;
+  sincos((double)m * phi, &em_s, &em_c);
+  const int ma = m < 0 ? -m : m;
+  wave_column(S, m, nMax, wigner_seed(ma, S.base[m < 0 ? 1 : 0]), em_c, em_s, data, ddata, c1, c2, E, H, g1, g2, G);
+}
+// all azimuthal orders of one expansion centre in one thread (lane <-> particle layout: large clusters)
+__device__ void add_waves_all_m(int nMax, double r, double the, double phi, cplx k, const cplx *data, const cplx *ddata,
+                                const cplx *__restrict__ c1, const cplx *__restrict__ c2, Acc3 &E, Acc3 &H) {
+  WaveSetup S;
+  wave_setup(S, r, the, phi, k);
+  const double c0 = S.P.cp, s0 = S.P.sp;
+  double em_c = 1.0, em_s = 0.0, seed_p = 1.0, seed_n = 1.0; // exp(i m phi) and the seeds by recurrence in |m|
+  for(int ma = 0; ma <= nMax; ++ma) {
+    if(ma > 0) {
+      const double t = em_c * c0 - em_s * s0;
+      em_s = em_s * c0 + em_c * s0;
+      em_c = t;
+      const double f = sqrt((2.0 * ma - 1.0) / (2.0 * ma));
+      seed_p *= f * S.base[0];
+      seed_n *= f * S.base[1];
+    }
+    wave_column(S, ma, nMax, seed_p, em_c, em_s, data, ddata, c1, c2, E, H, nullptr, nullptr, nullptr);
+    if(ma > 0)
+      wave_column(S, -ma, nMax, seed_n, em_c, -em_s, data, ddata, c1, c2, E, H, nullptr, nullptr, nullptr);
   }
 }
 
@@ -192,19 +244,36 @@ k_fields(FieldInputs in, long npts, const double *__restrict__ pts, cplx *__rest
     radial_set(cscale(in.waveK, Rr), nMax, true, data, ddata);
     if(lane <= 2 * nMax)
       add_waves(m1, nMax, Rr, Rt, Rp, in.waveK, data, ddata, in.ainc, in.ainc + n, E1, H1, nullptr, nullptr, nullptr);
-    for(int j = 0; j < in.nobj; ++j) { // scattered field (Result.cpp:154-176, 181-212)
-      double r, the, phi;
-      to_rel(px - in.xyz[3 * j], py - in.xyz[3 * j + 1], pz - in.xyz[3 * j + 2], r, the, phi);
-      radial_set(cscale(in.waveK, r), nMax, false, data, ddata);
-      if(lane <= 2 * nMax)
-        add_waves(m1, nMax, r, the, phi, in.waveK, data, ddata, in.Xsca + (size_t)j * 2 * n,
-                  in.Xsca + (size_t)j * 2 * n + n, E1, H1, nullptr, nullptr, nullptr);
-      if(in.do_sh) {
-        const cplx k2 = cscale(in.waveK, 2.0);
-        radial_set(cscale(k2, r), nMaxS, false, data, ddata);
-        if(lane <= 2 * nMaxS)
-          add_waves(m2, nMaxS, r, the, phi, k2, data, ddata, in.XscaSH + (size_t)j * 2 * ns,
-                    in.XscaSH + (size_t)j * 2 * ns + ns, E2, H2, nullptr, nullptr, nullptr);
+    // scattered field (Result.cpp:154-176, 181-212)
+    if(in.nobj >= 16) { // lane <-> particle: every lane sums all (n, m) of its own particles, no redundant radial work
+      for(int j = lane; j < in.nobj; j += 32) {
+        double r, the, phi;
+        to_rel(px - in.xyz[3 * j], py - in.xyz[3 * j + 1], pz - in.xyz[3 * j + 2], r, the, phi);
+        radial_set(cscale(in.waveK, r), nMax, false, data, ddata);
+        add_waves_all_m(nMax, r, the, phi, in.waveK, data, ddata, in.Xsca + (size_t)j * 2 * n,
+                        in.Xsca + (size_t)j * 2 * n + n, E1, H1);
+        if(in.do_sh) {
+          const cplx k2 = cscale(in.waveK, 2.0);
+          radial_set(cscale(k2, r), nMaxS, false, data, ddata);
+          add_waves_all_m(nMaxS, r, the, phi, k2, data, ddata, in.XscaSH + (size_t)j * 2 * ns,
+                          in.XscaSH + (size_t)j * 2 * ns + ns, E2, H2);
+        }
+      }
+    } else { // lane <-> azimuthal order
+      for(int j = 0; j < in.nobj; ++j) {
+        double r, the, phi;
+        to_rel(px - in.xyz[3 * j], py - in.xyz[3 * j + 1], pz - in.xyz[3 * j + 2], r, the, phi);
+        radial_set(cscale(in.waveK, r), nMax, false, data, ddata);
+        if(lane <= 2 * nMax)
+          add_waves(m1, nMax, r, the, phi, in.waveK, data, ddata, in.Xsca + (size_t)j * 2 * n,
+                    in.Xsca + (size_t)j * 2 * n + n, E1, H1, nullptr, nullptr, nullptr);
+        if(in.do_sh) {
+          const cplx k2 = cscale(in.waveK, 2.0);
+          radial_set(cscale(k2, r), nMaxS, false, data, ddata);
+          if(lane <= 2 * nMaxS)
+            add_waves(m2, nMaxS, r, the, phi, k2, data, ddata, in.XscaSH + (size_t)j * 2 * ns,
+                      in.XscaSH + (size_t)j * 2 * ns + ns, E2, H2, nullptr, nullptr, nullptr);
+        }
       }
     }
     hscale1 = cdiv(mk(0, -1), csqrt_(cdiv(in.mu_b, in.eps_b))); // iZ (Result.cpp:118)

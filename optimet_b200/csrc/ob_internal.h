@@ -108,10 +108,19 @@ struct AcaDesc {
   int rank = 0;      // > 0 low rank, -1 dense near block, 0 identity diagonal
   int pad = 0;
 };
+struct AcaScratch { // assembly scratch of one batch of block-rows: dense slab + full-rank U, V; kept by the context
+  cplx *slab = nullptr, *scrU = nullptr, *scrV = nullptr;
+  int2 *d_jobs = nullptr, *d_jobs_dense = nullptr;
+  int *d_rank = nullptr;
+  size_t elems = 0, blocks = 0;
+  void release();
+};
 struct AcaOperator {
   int nobj = 0, dim = 0, first = 0, count = 0, nch = 1;
   bool built = false;
-  std::vector<cplx *> chunks; // one exactly sized allocation per assembly batch
+  std::vector<cplx *> chunks; // one allocation per assembly batch, sized from the ranks, reused across builds
+  std::vector<size_t> chunk_cap;
+  size_t partial_elems = 0, desc_blocks = 0;
   AcaDesc *desc = nullptr;    // device, [count][nobj]
   std::vector<AcaDesc> h_desc;
   int *piv = nullptr;         // device, [count][nobj][2][dim]: pivot rows I then pivot columns J
@@ -121,7 +130,7 @@ struct AcaOperator {
   int rank_max = 0;
   void release();
 };
-void aca_build(AcaOperator &op, VtacTableSet const &ts, const double *d_xyz, const cplx *Tdiag, cplx k, int nobj,
+void aca_build(AcaOperator &op, AcaScratch &scr, VtacTableSet const &ts, const double *d_xyz, const cplx *Tdiag, cplx k, int nobj,
                int first, int count, const double *h_xyz, const double *h_radius, double eps, size_t budget_bytes,
                int sm_count, cudaStream_t st, long &launches);
 void launch_matvec_aca(AcaOperator const &op, const cplx *x, cplx *y_slice, cudaStream_t st, cudaEvent_t e0 = nullptr,

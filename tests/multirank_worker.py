@@ -11,6 +11,7 @@ sys.path.insert(0, ROOT)
 
 def main():
     out_path, nobj, nMax = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+    mode = sys.argv[4] if len(sys.argv) > 4 else "pairs"
     import torch
     import torch.distributed as dist
     from optimet_b200 import host as H, sharding, xmlgen
@@ -23,6 +24,10 @@ def main():
     case = H.Case(xml=xmlgen.cluster_xml(xyz, 50.0, nMax, 800.0, belos=belos))
     solver = H.Solver(case, device=lr)
     sharding.attach(solver, dist, rank, world)
+    if mode == "aca":      # compressed operator, block-rows sharded, all-gather of the y slices
+        solver.set_aca_mode(1)
+    elif mode == "dense":  # the reference's slab, same sharding
+        solver.set_option("operator", 0)
     res = solver.step()
     cs = sharding.sum_partials(dist, torch, [res[k] for k in ("ext", "sca", "abs", "sca_SH", "abs_SH")], device="cuda")
     # replicated vectors must be bit-identical on all ranks

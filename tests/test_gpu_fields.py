@@ -110,6 +110,8 @@ SPECS = {
     "two_si": lambda: U.two_si(nMax=6),
     "three_au": lambda: U.three_au(nMax=3),
     "random5": lambda: U.random_cluster(5, 5, seed=7),
+    "random20": lambda: U.random_cluster(20, 3, seed=9),    # >= 16 particles: the lane <-> particle layout of k_fields
+    "random40": lambda: U.random_cluster(40, 2, seed=10),   # more particles than lanes
     "lossy_bg": lambda: U.Spec("lossy_bg", [[0, 0, 0], [260, 40, -90], [-30, 310, 120]], [60, 80, 70],
                                U.fixed(9.0 + 0.4j, 7.0 + 0.9j), 4, 700.0, theta_deg=30, phi_deg=20, Eth=0.6, Eph=0.8j,
                                background=(1.7 + 0.0j, 1.0 + 0.0j)),

@@ -27,8 +27,9 @@ def _port():
     return p
 
 
-@pytest.mark.parametrize("world,nobj", [(2, 7), (4, 10), (8, 11)])
-def test_sharded_step_matches_single_gpu(tmp_path, world, nobj):
+@pytest.mark.parametrize("world,nobj,mode", [(2, 7, "pairs"), (2, 7, "dense"), (2, 7, "aca"), (4, 10, "pairs"),
+                                             (4, 9, "aca"), (8, 11, "pairs")])
+def test_sharded_step_matches_single_gpu(tmp_path, world, nobj, mode):
     if _ngpu() < world:
         pytest.skip("needs %d GPUs" % world)
     nMax = 4
@@ -37,7 +38,7 @@ def test_sharded_step_matches_single_gpu(tmp_path, world, nobj):
         out = str(tmp_path / ("w%d.npz" % w))
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(w), "--master-addr",
                "127.0.0.1", "--master-port", str(_port()), os.path.join(ROOT, "tests", "multirank_worker.py"), out,
-               str(nobj), str(nMax)]
+               str(nobj), str(nMax), mode]
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
         assert r.returncode == 0, r.stderr[-3000:]
         outs[w] = np.load(out)
