@@ -488,8 +488,8 @@ void launch_abs_sh(ShInputs const &in, int j0, int count, const cplx *Xint, cons
   if(count <= 0)
     return;
   const size_t ftab_bytes = (size_t)4 * in.nMax * in.nMax * 6 * sizeof(cplx);
-  if(ftab_bytes > 48 * 1024)
-    OB_CUDA(cudaFuncSetAttribute((const void *)k_abs_sh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ftab_bytes));
+  // static (~12 KB) + dynamic shared memory crosses the 48 KB default already at nMax = 10: always opt in
+  OB_CUDA(cudaFuncSetAttribute((const void *)k_abs_sh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ftab_bytes));
   k_abs_sh<<<count, 512, ftab_bytes, st>>>(in, j0, Xint, Xint_SH, out);
   OB_CUDA(cudaGetLastError());
 }
