@@ -122,6 +122,7 @@ struct ob_ctx {
   double eps_aca = 1e-3;               // PreconditionedMatrix.cpp:772
   size_t aca_budget = (size_t)4 << 30; // scratch bytes of one ACA assembly batch
   AcaScratch aca_scratch;
+  DevBuf<cplx> spare_AB; // parked pair storage (keep_matrices = 0)
   // frequency / materials
   bool have_freq = false, have_inc = false;
   double omega = 0;
@@ -256,6 +257,10 @@ static void assemble(ob_ctx *c, int harmonic) {
     H.S.release();
     H.aca.release();
     c->aca_scratch.release();
+    if(!H.AB.p && c->spare_AB.p && c->spare_AB.n >= std::max<size_t>(1, pair_storage_elems(H.pplan))) {
+      std::swap(H.AB.p, c->spare_AB.p);
+      std::swap(H.AB.n, c->spare_AB.n);
+    }
     H.AB.alloc(std::max<size_t>(1, pair_storage_elems(H.pplan)));
     launch_assemble_pairs(ts, c->xyz.p, H.k, H.pplan.pair_ij, H.pplan.npairs, H.AB.p, c->st);
     c->launches += 1;
@@ -264,6 +269,7 @@ static void assemble(ob_ctx *c, int harmonic) {
     return;
   }
   H.AB.release();
+  c->spare_AB.release();
   if(c->operator_mode == 2) { // Scattering_matrix_ACA_FF / _SH (PreconditionedMatrix.cpp:489-551, 699-759)
     H.S.release();
     aca_build(H.aca, c->aca_scratch, ts, c->xyz.p, c->fac[harmonic == 1 ? 0 : 1].p, H.k, c->nobj, c->first, c->count, c->h_xyz.data(),
@@ -1360,6 +1366,20 @@ int ob_cross_sections(ob_ctx *ctx, const double *X_sca, const double *X_int, con
   OB_END
 }
 
+static void release_harmonic(ob_ctx *ctx, int harmonic) {
+  HarmonicState &H = ctx->hs[harmonic - 1];
+  H.S.release();
+  // keep_matrices = 0 alternates the two harmonics in the same storage: park the pair buffer instead of paying a
+  // cudaFree + cudaMalloc of ~100 GB per harmonic and step (the next assemble() picks it up when it is large enough)
+  if(H.AB.p && !ctx->spare_AB.p) {
+    std::swap(H.AB.p, ctx->spare_AB.p);
+    std::swap(H.AB.n, ctx->spare_AB.n);
+  }
+  H.AB.release();
+  H.aca.release();
+  H.assembled = false;
+}
+
 int ob_fields(ob_ctx *ctx, long npts, const double *pts_sph, const double *X_sca, const double *X_int,
               const double *X_sca_SH, const double *X_int_SH, int do_sh, double *out, int *inner) {
   OB_BEGIN
@@ -1440,6 +1460,8 @@ int ob_run(ob_ctx *ctx, const ob_gmres_opts *opts, int do_sh, double *X_sca, dou
     t.stop();
   }
   const bool direct = opts && opts->flavour == OB_SOLVE_DIRECT; // the LU assembles its own dense work matrix
+  if(!ctx->keep_matrices) // one harmonic resident at a time: drop what an earlier step left behind
+    release_harmonic(ctx, 2);
   if(!direct) {
     PhaseTimer t(ctx, 1);
     assemble(ctx, 1);
@@ -1459,12 +1481,8 @@ int ob_run(ob_ctx *ctx, const ob_gmres_opts *opts, int do_sh, double *X_sca, dou
     (void)t0;
   }
   if(do_sh) {
-    if(!ctx->keep_matrices) {
-      ctx->hs[0].S.release();
-      ctx->hs[0].AB.release();
-      ctx->hs[0].aca.release();
-      ctx->hs[0].assembled = false;
-    }
+    if(!ctx->keep_matrices)
+      release_harmonic(ctx, 1);
     {
       PhaseTimer t(ctx, 3);
       ctx->tmpA.alloc(std::max(N1, N2));
@@ -1489,6 +1507,8 @@ int ob_run(ob_ctx *ctx, const ob_gmres_opts *opts, int do_sh, double *X_sca, dou
       ctx->launches += 1;
       t.stop();
     }
+    if(!ctx->keep_matrices)
+      release_harmonic(ctx, 2);
   }
   {
     PhaseTimer t(ctx, 6);
