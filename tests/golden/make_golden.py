@@ -10,6 +10,7 @@ cannot drift silently and (b) the GPU box, which has no /root/reference, still c
 AMOS-backed numbers.
 
     python tests/golden/make_golden.py        (run in the build container; needs oracle/_ref)
+    python tests/golden/make_golden.py 8f     (only the fixtures of the SURVEY 8f rows: ACA operator, field maps)
 """
 import os
 import sys
@@ -77,5 +78,52 @@ def main():
         O.set_bessel_backend(0)
 
 
+def field_points(spec, seed=11):
+    """Fixed sample of points around and inside the spheres of a case (spherical coordinates, as OutputGrid returns)."""
+    rng = np.random.RandomState(seed)
+    lo, hi = spec.xyz.min(0) - 200e-9, spec.xyz.max(0) + 200e-9
+    pts = [rng.uniform(lo, hi) for _ in range(12)]
+    for c, r in zip(spec.xyz, spec.radius):
+        for frac in (0.3, 0.8):
+            d = rng.standard_normal(3)
+            pts.append(c + frac * r * d / np.linalg.norm(d))
+    pts = np.array(pts)
+    r = np.linalg.norm(pts, axis=1)
+    return np.stack([r, np.arccos(pts[:, 2] / r), np.arctan2(pts[:, 1], pts[:, 0])], 1)
+
+
+def main_8f():
+    """ACA operator (block compression of the golden FF block, cross sections of the compressed solve) and field maps
+    (E/H at fixed points from the golden solution vectors) -- same provenance as above (oracle on the reference's AMOS)."""
+    if not O.have_amos():
+        raise SystemExit("oracle/_ref/libamos_ref.so missing: run `make -C oracle` with /root/reference present")
+    O.set_bessel_backend(1)
+    try:
+        for name, make in CASES.items():
+            spec = make()
+            orc = U.oracle_case(spec)
+            g = np.load(os.path.join(HERE, name + ".npz"))
+            Um, Vm, I, J = O.aca_compress(g["block_ff_10"])
+            nobj = orc.info()["nobj"]
+            ranks = np.array([[orc.aca_block(1, i, j)[0] for j in range(nobj)] for i in range(nobj)])
+            orc.solve(O.SOLVER_ACA_ZCOMP, tol=1e-13, maxit=200, max_restarts=3)
+            cs = orc.cross_sections()
+            x_aca = orc.vector(0)
+            pts = field_points(spec)
+            for w, key in enumerate(("X_sca", "X_int", "X_sca_SH", "X_int_SH")):
+                orc.set_vector(w, g[key])
+            fields, inner = orc.fields(pts)
+            np.savez_compressed(os.path.join(HERE, "rows8f_" + name + ".npz"), aca_U=Um, aca_V=Vm, aca_I=I, aca_J=J,
+                                aca_ranks=ranks, aca_X_sca=x_aca,
+                                aca_cs=np.array([cs["ext"], cs["sca"], cs["sca_SH"], cs["abs_SH"]]), field_points=pts,
+                                fields=fields, inner=inner)
+            print(name, "rank", len(I), "ranks", ranks.tolist(), cs, "inner", inner.tolist())
+    finally:
+        O.set_bessel_backend(0)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "8f":
+        main_8f()
+        sys.exit(0)
     main()
