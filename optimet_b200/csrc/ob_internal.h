@@ -98,6 +98,7 @@ void launch_pairs_finalize(const cplx *x, const cplx *Tdiag, const cplx *acc, si
 void launch_pairs_expand_block(PairPlan const &p, const cplx *AB, int i, int j, const cplx *Tdiag, cplx *out,
                                cudaStream_t st);
 // ob_vtac.cu: assembly of the pair storage (one CTA per local pair)
+void assemble_pairs_tuning(int minb); // 0 auto, 2 or 3 resident CTAs per SM
 void launch_assemble_pairs(VtacTableSet const &ts, const double *xyz, cplx k, const int2 *pair_ij, long npairs,
                            cplx *AB, cudaStream_t st);
 

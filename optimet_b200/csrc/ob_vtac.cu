@@ -188,7 +188,10 @@ struct EmitPair {
     __stcs(B + (size_t)p * n + r, b);
   }
 };
-__global__ void __launch_bounds__(OB_VTAC_THREADS, 2)
+// MINB = resident CTAs per SM the register allocation is bounded for: 3 (56 registers, no spills) when three level-buffer
+// sets fit the shared memory of an SM (nMax <= 8: 58 KB per CTA), else 2.
+template <int MINB>
+__global__ void __launch_bounds__(OB_VTAC_THREADS, MINB)
 k_assemble_pairs(VtacTables tb, const double *__restrict__ xyz, cplx k, const int2 *__restrict__ pair_ij,
                  cplx *__restrict__ AB) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -359,12 +362,20 @@ void launch_assemble(VtacTableSet const &ts, const double *xyz, const cplx *Tdia
   k_assemble<<<grid, OB_VTAC_THREADS, ts.smem, st>>>(ts.tb, xyz, Tdiag, k, row0, S, ld);
   OB_CUDA(cudaGetLastError());
 }
+static int g_pairs_minb = 0; // 0 = auto, 2 / 3 = forced (tuning option "assemble_minb")
+void assemble_pairs_tuning(int minb) { g_pairs_minb = minb; }
 void launch_assemble_pairs(VtacTableSet const &ts, const double *xyz, cplx k, const int2 *pair_ij, long npairs,
                            cplx *AB, cudaStream_t st) {
   if(npairs <= 0)
     return;
-  set_smem((const void *)k_assemble_pairs, ts.smem);
-  k_assemble_pairs<<<(unsigned)npairs, OB_VTAC_THREADS, ts.smem, st>>>(ts.tb, xyz, k, pair_ij, AB);
+  const bool three = g_pairs_minb == 3 || (g_pairs_minb == 0 && 3 * (ts.smem + 1024) <= 227 * 1024);
+  if(three) {
+    set_smem((const void *)k_assemble_pairs<3>, ts.smem);
+    k_assemble_pairs<3><<<(unsigned)npairs, OB_VTAC_THREADS, ts.smem, st>>>(ts.tb, xyz, k, pair_ij, AB);
+  } else {
+    set_smem((const void *)k_assemble_pairs<2>, ts.smem);
+    k_assemble_pairs<2><<<(unsigned)npairs, OB_VTAC_THREADS, ts.smem, st>>>(ts.tb, xyz, k, pair_ij, AB);
+  }
   OB_CUDA(cudaGetLastError());
 }
 void launch_vtac_single(VtacTableSet const &ts, double r, double the, double phi, cplx k, int regular, cplx *A, cplx *B,

@@ -43,7 +43,7 @@ __host__ __device__ inline int vtac_buffer_entries(int NM) {
 __host__ __device__ inline size_t vtac_smem_bytes(int NM) {
   int L = 2 * NM;
   size_t b = 2 * (size_t)vtac_buffer_entries(NM) * sizeof(cplx); // two level buffers
-  b += (size_t)(L + 1) * sizeof(cplx);                          // radial z_l
+  b += (size_t)(L + 2) * sizeof(cplx);                          // radial z_l + one zero entry (target of masked reads)
   b += (size_t)(4 * NM + 1) * sizeof(cplx);                     // phase table
   b += (size_t)((L + 1) * (L + 2) / 2) * sizeof(double);        // Legendre
   b += (size_t)((NM + 2 + 2 + 1) & ~1) * sizeof(int);            // chain offsets (even count: doubles follow)
@@ -65,7 +65,7 @@ struct VtacSmem {
     buf[0] = (cplx *)base;
     buf[1] = buf[0] + T;
     zl = buf[1] + T;
-    ph = zl + (L + 1);
+    ph = zl + (L + 2);
     nlm = (double *)(ph + (4 * NM + 1));
     offs = (int *)(nlm + (L + 1) * (L + 2) / 2);
     aps = (double *)(offs + ((NM + 2 + 2 + 1) & ~1));
@@ -90,6 +90,7 @@ __device__ void vtac_block(VtacTables const &tb, unsigned char *smem_raw, double
 
   // ---- seeds: radial sequence (one thread), Legendre (one thread per order m), phases, chain offsets ----
   if(tid == 0) {
+    sm.zl[L + 1] = mk(0, 0);
     cplx z = cscale(k, r);
     if(regular)
       sph_bessel_j(z, L, sm.zl);
@@ -233,58 +234,61 @@ __device__ void vtac_block(VtacTables const &tb, unsigned char *smem_raw, double
     }
   };
 
+  // One (column mu, row) item: six shared-memory reads (masked ones hit the zero slot), A and B, phase, store.
+  auto emit_item = [&](const cplx *G, int p, int mu, int i_z0, int i_y0, int i_zp, int i_yp, int i_zm, int i_ym,
+                       double f0, double fp, double fm) {
+    const double *cc = tb.colc + 4 * p;
+    const double gn = __ldg(cc), s1 = __ldg(cc + 1), s2 = __ldg(cc + 2);
+    const cplx z0 = G[i_z0], y0 = G[i_y0], zp = G[i_zp], yp = G[i_yp], zm = G[i_zm], ym = G[i_ym];
+    const double k0 = gn * (double)mu * f0, k1 = gn * s1 * fp, k2 = gn * s2 * fm;
+    // A (Coupling.cpp:30-38) and B (Coupling.cpp:40-51; factor -i/2 sqrt(...))
+    const double ca0 = rA0 * k0, ca1 = rA1 * k1, ca2 = rA2 * k2;
+    const double cb0 = rB0 * k0, cb1 = rB1 * k1, cb2 = -(rB2 * k2);
+    cplx a, b;
+    a.x = ca0 * z0.x + ca1 * zp.x + ca2 * zm.x;
+    a.y = ca0 * z0.y + ca1 * zp.y + ca2 * zm.y;
+    b.x = cb0 * y0.x + cb1 * yp.x + cb2 * ym.x;
+    b.y = cb0 * y0.y + cb1 * yp.y + cb2 * ym.y;
+    b = mk(b.y, -b.x); // times -i
+    const cplx phs = sm.ph[mu - rk + 2 * NM];
+    emit.item(p, row, cmul(a, phs), cmul(b, phs));
+  };
+
   auto emit_level = [&](int n) {
     if(!row_active)
       return;
     const cplx *G = buf0 + (n & 1) * Tbuf;
-    const int pbase = n * (n + 1) - 1; // flat(n, mu) = pbase - mu
-#pragma unroll 2
+    const int ZI = (int)(sm.zl + (L + 1) - G); // index of the zero entry seen from this level buffer
+    const int pbase = n * (n + 1) - 1;         // flat(n, mu) = pbase - mu
+    // Masked entries (outside the chain, or with an exactly vanishing coefficient: the square roots in
+    // Coupling.cpp:33-37, 43-48 vanish there) read the zero slot.  Entries with mu' < 0 come from the mirrored entry of
+    // chain |mu'| with sign (-1)^(mu'+kappa'); the parity of mu' + kappa' = 2 mu' + k - mu is the same for
+    // mu' = mu-1, mu, mu+1.  All threads of a warp share mu (a warp is 32 consecutive rows of one column group), so
+    // the three cases below do not diverge.
+#pragma unroll 1
     for(int mu = n - grp; mu >= -n; mu -= ngroups) {
       const int p = pbase - mu;
-      const double *cc = tb.colc + 4 * p;
-      const double gn = __ldg(cc), s1 = __ldg(cc + 1), s2 = __ldg(cc + 2);
-      // entries with mu' < 0 come from the mirrored entry of chain |mu'| with sign (-1)^(mu'+kappa'); the parity of
-      // mu' + kappa' = 2 mu' + k - mu is the same for mu' = mu-1, mu, mu+1
-      const double flip = ((rk - mu) & 1) ? -1.0 : 1.0;
-      cplx z0 = mk(0, 0), zp = z0, zm = z0, y0 = z0, yp = z0, ym = z0;
-      double k0 = gn * (double)mu, k1 = gn * s1, k2 = gn * s2;
-      { // mu' = mu
-        const int am = mu < 0 ? -mu : mu, o = sm.offs[am];
-        z0 = G[o + (mu >= 0 ? b0 : b0n)];
-        if(vZ1)
-          y0 = G[o + (mu >= 0 ? b1 : b1n)];
-        if(mu < 0)
-          k0 *= flip;
+      if(mu >= 1 && mu < n) { // mu - 1, mu, mu + 1 all in [0, n]: direct entries, no sign
+        const int o0 = sm.offs[mu], op = sm.offs[mu + 1], om = sm.offs[mu - 1];
+        emit_item(G, p, mu, o0 + b0, vZ1 ? o0 + b1 : ZI, vP0 ? op + b0 + 1 : ZI, vP1 ? op + b1 + 1 : ZI,
+                  vM0 ? om + b0 - 1 : ZI, vM1 ? om + b1 - 1 : ZI, 1.0, 1.0, 1.0);
+      } else if(mu <= -2 && mu > -n) { // all three mirrored
+        const int a0 = -mu;
+        const int o0 = sm.offs[a0], op = sm.offs[a0 - 1], om = sm.offs[a0 + 1];
+        const double flip = ((rk - mu) & 1) ? -1.0 : 1.0;
+        emit_item(G, p, mu, o0 + b0n, vZ1 ? o0 + b1n : ZI, vP0 ? op + b0n - 1 : ZI, vP1 ? op + b1n - 1 : ZI,
+                  vM0 ? om + b0n + 1 : ZI, vM1 ? om + b1n + 1 : ZI, flip, flip, flip);
+      } else { // mu in {n, 0, -1, -n}: mixed signs and the chain ends
+        const double flip = ((rk - mu) & 1) ? -1.0 : 1.0;
+        const int mp = mu + 1, mm = mu - 1;
+        const int a0 = mu < 0 ? -mu : mu, ap = mp < 0 ? -mp : mp, am = mm < 0 ? -mm : mm;
+        const int o0 = sm.offs[a0], op = sm.offs[ap], om = sm.offs[am]; // offs has NM + 2 entries: |mu'| = n + 1 is readable
+        const bool hp = mu < n, hm = mu > -n;
+        emit_item(G, p, mu, o0 + (mu >= 0 ? b0 : b0n), vZ1 ? o0 + (mu >= 0 ? b1 : b1n) : ZI,
+                  (hp && vP0) ? op + (mp >= 0 ? b0 + 1 : b0n - 1) : ZI, (hp && vP1) ? op + (mp >= 0 ? b1 + 1 : b1n - 1) : ZI,
+                  (hm && vM0) ? om + (mm >= 0 ? b0 - 1 : b0n + 1) : ZI, (hm && vM1) ? om + (mm >= 0 ? b1 - 1 : b1n + 1) : ZI,
+                  mu < 0 ? flip : 1.0, mp < 0 ? flip : 1.0, mm < 0 ? flip : 1.0);
       }
-      if(mu < n) { // mu' = mu + 1, kappa' = k + 1
-        const int mp = mu + 1, am = mp < 0 ? -mp : mp, o = sm.offs[am];
-        if(vP0)
-          zp = G[o + (mp >= 0 ? b0 + 1 : b0n - 1)];
-        if(vP1)
-          yp = G[o + (mp >= 0 ? b1 + 1 : b1n - 1)];
-        if(mp < 0)
-          k1 *= flip;
-      }
-      if(mu > -n) { // mu' = mu - 1, kappa' = k - 1
-        const int mp = mu - 1, am = mp < 0 ? -mp : mp, o = sm.offs[am];
-        if(vM0)
-          zm = G[o + (mp >= 0 ? b0 - 1 : b0n + 1)];
-        if(vM1)
-          ym = G[o + (mp >= 0 ? b1 - 1 : b1n + 1)];
-        if(mp < 0)
-          k2 *= flip;
-      }
-      // A (Coupling.cpp:30-38) and B (Coupling.cpp:40-51; factor -i/2 sqrt(...))
-      const double ca0 = rA0 * k0, ca1 = rA1 * k1, ca2 = rA2 * k2;
-      const double cb0 = rB0 * k0, cb1 = rB1 * k1, cb2 = -(rB2 * k2);
-      cplx a, b;
-      a.x = ca0 * z0.x + ca1 * zp.x + ca2 * zm.x;
-      a.y = ca0 * z0.y + ca1 * zp.y + ca2 * zm.y;
-      b.x = cb0 * y0.x + cb1 * yp.x + cb2 * ym.x;
-      b.y = cb0 * y0.y + cb1 * yp.y + cb2 * ym.y;
-      b = mk(b.y, -b.x); // times -i
-      const cplx phs = sm.ph[mu - rk + 2 * NM];
-      emit.item(p, row, cmul(a, phs), cmul(b, phs));
     }
   };
 
