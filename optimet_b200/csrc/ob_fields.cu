@@ -217,7 +217,7 @@ __device__ int check_inner(FieldInputs const &in, double px, double py, double p
 }
 
 // out: npts x 4 x 3 complex (E_FF, H_FF, E_SH without the particular solution, H_SH); inner: npts
-__global__ void __launch_bounds__(FLD_WARPS * 32)
+__global__ void __launch_bounds__(FLD_WARPS * 32, 2)
 k_fields(FieldInputs in, long npts, const double *__restrict__ pts, cplx *__restrict__ out, int *__restrict__ inner) {
   const int lane = threadIdx.x & 31;
   const long pt = (long)blockIdx.x * FLD_WARPS + (threadIdx.x >> 5);
