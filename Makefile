@@ -3,7 +3,7 @@ NVCC ?= nvcc
 ARCH := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := -std=c++17 -O3 -lineinfo $(ARCH) -Xcompiler -fPIC -Xcompiler -Wall -Xcompiler -Wno-unused-function
 CSRC := optimet_b200/csrc
-OBJS := $(CSRC)/ob_vtac.o $(CSRC)/ob_mie.o $(CSRC)/ob_matvec.o $(CSRC)/ob_pairs.o $(CSRC)/ob_vec.o $(CSRC)/ob_sh.o $(CSRC)/ob_lu.o $(CSRC)/ob_aca.o $(CSRC)/ob_fields.o $(CSRC)/ob_api.o
+OBJS := $(CSRC)/ob_vtac.o $(CSRC)/ob_mie.o $(CSRC)/ob_matvec.o $(CSRC)/ob_pairs.o $(CSRC)/ob_vec.o $(CSRC)/ob_sh.o $(CSRC)/ob_lu.o $(CSRC)/ob_aca.o $(CSRC)/ob_fields.o $(CSRC)/ob_rot.o $(CSRC)/ob_api.o
 HDRS := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh) include/optimet_b200.h
 LIB := optimet_b200/liboptimet_b200.so
 

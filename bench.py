@@ -176,10 +176,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c4")
     ap.add_argument("--matvec-variant", type=int, default=None)
-    ap.add_argument("--operator", default="pairs", choices=["pairs", "dense", "aca"],
+    ap.add_argument("--operator", default="pairs", choices=["pairs", "dense", "aca", "rot"],
                     help="pairs: compact A^T/B^T-of-i<j form (default); dense: the reference's full slab; "
-                         "aca: the reference's ACA-compressed operator (eps 1e-3; results differ at that level)")
+                         "aca: the reference's ACA-compressed operator (eps 1e-3; results differ at that level); "
+                         "rot: rotated-axial form (exact; phases + axial A/B + Wigner small-d per pair, csrc/ob_rot.cu)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-alt", action="store_true", help="skip the extra end-to-end steps in the rotated-axial form")
     ap.add_argument("--opt", action="append", default=[], help="library tuning option name=value (ob_set_option)")
     args = ap.parse_args()
 
@@ -236,7 +238,7 @@ def main():
     if args.operator == "aca":
         solver.set_aca_mode(1)
     else:
-        solver.set_option("operator", 1 if args.operator == "pairs" else 0)
+        solver.set_option("operator", {"pairs": 1, "dense": 0, "rot": 3}[args.operator])
     for opt in args.opt:
         k, v = opt.split("=")
         solver.set_option(k, float(v))
@@ -302,6 +304,33 @@ def main():
     e2e_per_step = float(e2e_ms.item()) / args.steps
     clocks = sampler.stop() if sampler else None
 
+    # ---------------- extra (not the headline): the same end-to-end steps in the rotated-axial operator form ----------------
+    # (csrc/ob_rot.cu: exact, 12-15x fewer operator bytes than the pair form; bound by shared-memory wavefronts rather
+    # than HBM, so it is reported beside the TMA-streamed pair form the north star specifies, not instead of it)
+    alt = None
+    if args.operator == "pairs" and not args.no_alt:
+        solver.set_option("operator", 3)
+        for _ in range(max(1, args.warmup)):
+            r2 = solver.step(fetch=True)
+        barrier()
+        lib.ob_timer(ctx, 0, None)
+        for _ in range(args.steps):
+            r2 = solver.step(fetch=True)
+        lib.ob_timer(ctx, 1, C.byref(ms))
+        barrier()
+        a_ms = torch.tensor([ms.value], dtype=torch.float64, device="cuda")
+        cs2 = torch.tensor([r2[k] for k in ("ext", "sca", "abs", "sca_SH", "abs_SH")], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(a_ms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(cs2, op=dist.ReduceOp.SUM)
+        tm2 = solver.ctx_timings()
+        alt = {"operator": "rot (phases + axial A/B + Wigner small-d per pair, k_matvec_rot)",
+               "e2e_ms_per_step": float(a_ms.item()) / args.steps,
+               "matvec_ms_per_apply": tm2["matvec_ms"] / max(1.0, tm2["matvec_count"]),
+               "operator_bytes_per_apply": tm2["operator_bytes"], "iters_ff": r2["iters_ff"], "iters_sh": r2["iters_sh"],
+               "cross_sections": [float(v) for v in cs2.tolist()]}
+        solver.set_option("operator", 1)
+
     # cross sections are per-rank partial sums over the rank's own particles (linear): add them up
     cs_t = torch.tensor([res[k] for k in ("ext", "sca", "abs", "sca_SH", "abs_SH")], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -312,6 +341,10 @@ def main():
         dist.all_reduce(mv_t, op=dist.ReduceOp.MAX)
 
     if rank == 0:
+        if alt is not None:
+            ref_cs = [float(v) for v in cs_t.tolist()]
+            alt["max_rel_diff_of_cross_sections_vs_headline_form"] = max(
+                abs(a_ / b_ - 1.0) for a_, b_ in zip(alt["cross_sections"], ref_cs) if b_ != 0.0)
         peak, peak_src = measured_peaks()
         m_loc = n2 * count
         # dense 16 M_loc N + 32 N per apply; pair form 32 n^2 per local pair + 32 N
@@ -342,9 +375,11 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_per_step / 1e3, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(acc["launches"]),
+            "alt_operator": alt,
             "roofline": {"bound": "hbm", "kernel": {"pairs": "k_matvec_pairs (TMA-streamed complex-FP64 pair-form block matvec)",
                                                     "dense": "k_matvec (TMA-streamed complex-FP64 dense block matvec)",
-                                                    "aca": "k_matvec_aca (complex-FP64 U(Vx) low-rank + dense near blocks)"}[args.operator],
+                                                    "aca": "k_matvec_aca (complex-FP64 U(Vx) low-rank + dense near blocks)",
+                                                    "rot": "k_matvec_rot (rotation - axial translation - rotation per pair; FP64 latency bound, not HBM)"}[args.operator],
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "traffic": None,
                          "algorithmic_bytes_per_launch": mv_bytes, "avg_launch_ms": float(mv_t.item())},
@@ -357,6 +392,9 @@ def main():
         if args.operator == "pairs":
             units = nobj * (nobj - 1) // 2 // world
             asm_bytes = 32.0 * (n2 // 2) ** 2 * units
+        elif args.operator == "rot":
+            units = nobj * (nobj - 1) // 2 // world
+            asm_bytes = acc["operator_bytes"] - 32.0 * N
         elif args.operator == "aca":
             units = count * (nobj - 1)
             asm_bytes = solver.ctx().aca_stats(1)["stored_bytes"]
@@ -366,7 +404,7 @@ def main():
             asm_bytes = 16.0 * n2 * n2 * count * nobj
         fp64 = C.c_double()
         lib.ob_measure_fp64_peak(ctx, C.byref(fp64))
-        out["assembly"] = {"kernel": {"pairs": "k_assemble_pairs", "dense": "k_assemble",
+        out["assembly"] = {"kernel": {"pairs": "k_assemble_pairs", "dense": "k_assemble", "rot": "k_assemble_axial + k_rot_tables",
                                       "aca": "k_assemble + k_aca_compress + pack"}[args.operator],
                            "ms_per_harmonic": asm_ms, "units_per_launch": units, "stored_bytes_per_launch": asm_bytes,
                            "store_GBps": asm_bytes / (asm_ms * 1e-3) / 1e9,

@@ -99,6 +99,11 @@ struct HarmonicState {
   // pair form (ob_pairs.cu): unscaled A^T, B^T of the local pairs i < j
   int mode = 0; // operator form this harmonic was assembled in (0 dense, 1 pairs, 2 ACA-compressed)
   AcaOperator aca;
+  // rotated-axial form (ob_rot.cu): one record per local pair i < j
+  DevBuf<unsigned char> rot;
+  RotLayout rl;
+  PairPlan rplan;
+  int rplan_world = -1, rplan_rank = -1;
   DevBuf<cplx> AB;
   PairPlan pplan;
   int pplan_world = -1, pplan_rank = -1;
@@ -256,6 +261,7 @@ static void assemble(ob_ctx *c, int harmonic) {
     }
     H.S.release();
     H.aca.release();
+    H.rot.release();
     c->aca_scratch.release();
     if(!H.AB.p && c->spare_AB.p && c->spare_AB.n >= std::max<size_t>(1, pair_storage_elems(H.pplan))) {
       std::swap(H.AB.p, c->spare_AB.p);
@@ -270,6 +276,23 @@ static void assemble(ob_ctx *c, int harmonic) {
   }
   H.AB.release();
   c->spare_AB.release();
+  if(c->operator_mode == 3) { // rotated-axial form: phases, axial A/B and Wigner small-d per pair (ob_rot.cu)
+    H.S.release();
+    H.aca.release();
+    if(H.rplan.nobj != c->nobj || H.rplan.n != H.n || H.rplan_world != c->world || H.rplan_rank != c->rank) {
+      pair_plan_build(H.rplan, c->nobj, H.n, c->world, c->rank, 4 * c->sm_count); // latency-bound: ~4 CTAs per SM
+      H.rplan_world = c->world;
+      H.rplan_rank = c->rank;
+    }
+    H.rl = rot_layout(H.nMax);
+    H.rot.alloc(std::max<size_t>(16, (size_t)H.rplan.npairs * H.rl.rec_bytes));
+    launch_assemble_rot(ts, c->xyz.p, H.k, H.rplan.pair_ij, H.rplan.npairs, H.rot.p, H.rl, c->st);
+    c->launches += 2;
+    H.mode = 3;
+    H.assembled = true;
+    return;
+  }
+  H.rot.release();
   if(c->operator_mode == 2) { // Scattering_matrix_ACA_FF / _SH (PreconditionedMatrix.cpp:489-551, 699-759)
     H.S.release();
     aca_build(H.aca, c->aca_scratch, ts, c->xyz.p, c->fac[harmonic == 1 ? 0 : 1].p, H.k, c->nobj, c->first, c->count, c->h_xyz.data(),
@@ -339,6 +362,21 @@ static void matvec(ob_ctx *c, int harmonic, const cplx *x, cplx *y, bool x_stage
       c->launches += 4;
     }
     c->tim[10] = 16.0 * (double)pair_storage_elems(H.pplan) + 32.0 * (double)N;
+  } else if(H.mode == 3) {
+    const cplx *T = c->fac[harmonic == 1 ? 0 : 1].p;
+    const size_t N = (size_t)c->N(harmonic);
+    if(c->world == 1) {
+      launch_matvec_rot(H.rplan, H.rl, H.rot.p, x, T, y, 1, c->st, evm0, evm1);
+      c->launches += 2;
+    } else {
+      need(c->comm != nullptr, "world > 1 but ob_comm_init has not been called");
+      launch_matvec_rot(H.rplan, H.rl, H.rot.p, x, T, H.rplan.acc, 0, c->st, evm0, evm1);
+      OB_NCCL(g_nccl.AllReduce((const void *)H.rplan.acc, (void *)H.rplan.acc, 2 * N, ncclDouble, ncclSum, c->comm,
+                               c->st));
+      launch_pairs_finalize(x, T, H.rplan.acc, N, y, c->st);
+      c->launches += 4;
+    }
+    c->tim[10] = (double)H.rplan.npairs * (double)H.rl.rec_bytes + 32.0 * (double)N;
   } else if(H.mode == 2) { // matvec of PreconditionedMatrix.cpp:1058-1085 on the compressed blocks
     launch_matvec_aca(H.aca, x, y + (size_t)c->first * 2 * H.n, c->st, evm0, evm1);
     c->launches += H.aca.nch > 1 ? 2 : 1;
@@ -912,6 +950,7 @@ void ob_destroy(ob_ctx *ctx) {
     ctx->tabs[i].release();
     matvec_plan_release(ctx->hs[i].plan);
     pair_plan_release(ctx->hs[i].pplan);
+    pair_plan_release(ctx->hs[i].rplan);
     ctx->hs[i].aca.release();
   }
   ctx->lu.release();
@@ -1102,6 +1141,7 @@ int ob_release_matrix(ob_ctx *ctx, int harmonic) {
   ctx->hs[harmonic - 1].S.release();
   ctx->hs[harmonic - 1].AB.release();
   ctx->hs[harmonic - 1].aca.release();
+  ctx->hs[harmonic - 1].rot.release();
   ctx->hs[harmonic - 1].assembled = false;
   OB_END
 }
@@ -1112,6 +1152,7 @@ int ob_fetch_block(ob_ctx *ctx, int harmonic, int i, int j, double *out) {
   HarmonicState &H = ctx->hs[harmonic - 1];
   need(H.assembled, "matrix not assembled");
   need(H.mode != 2, "the ACA-compressed operator holds no dense blocks: use ob_aca_block");
+  need(H.mode != 3, "the rotated-axial operator holds no dense blocks (operator 0 or 1 rebuild them)");
   if(H.mode == 1) {
     need(i >= 0 && i < ctx->nobj && j >= 0 && j < ctx->nobj, "block index out of range");
     const size_t b2 = (size_t)4 * H.n * H.n;
@@ -1136,6 +1177,7 @@ int ob_fetch_matrix(ob_ctx *ctx, int harmonic, double *out) {
   HarmonicState &H = ctx->hs[harmonic - 1];
   need(H.assembled, "matrix not assembled");
   need(H.mode != 2, "the ACA-compressed operator holds no dense matrix: use ob_aca_block");
+  need(H.mode != 3, "the rotated-axial operator holds no dense matrix (operator 0 or 1 rebuild it)");
   if(H.mode == 1) { // rebuild the dense reference layout block by block (tests; single rank only)
     need(ctx->world == 1, "ob_fetch_matrix in pair form needs world == 1");
     const size_t b = 2 * (size_t)H.n, ld = (size_t)ctx->N(harmonic);
@@ -1377,6 +1419,7 @@ static void release_harmonic(ob_ctx *ctx, int harmonic) {
   }
   H.AB.release();
   H.aca.release();
+  H.rot.release();
   H.assembled = false;
 }
 
@@ -1583,7 +1626,8 @@ int ob_set_option(ob_ctx *ctx, const char *name, double value) {
       ctx->hs[h].assembled = false;
     }
   } else if(n == "operator") { // 0 = dense slab, 1 = compact pair form, 2 = ACA-compressed (reference's ACA path)
-    need(value == 0 || value == 1 || value == 2, "operator must be 0 (dense), 1 (pairs) or 2 (ACA)");
+    need(value == 0 || value == 1 || value == 2 || value == 3,
+         "operator must be 0 (dense), 1 (pairs), 2 (ACA) or 3 (rotated-axial)");
     ctx->operator_mode = (int)value;
     ctx->hs[0].assembled = ctx->hs[1].assembled = false;
   } else if(n == "assemble_minb") { // tuning: resident CTAs per SM k_assemble_pairs is compiled for (0 auto, 2, 3)

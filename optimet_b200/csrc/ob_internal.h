@@ -94,6 +94,8 @@ size_t pair_storage_elems(PairPlan const &p);
 void launch_matvec_pairs(PairPlan const &p, const cplx *AB, const cplx *x, const cplx *Tdiag, cplx *acc_or_y,
                          int finalize, cudaStream_t st, cudaEvent_t e0 = nullptr, cudaEvent_t e1 = nullptr,
                          bool x_staged = false);
+void launch_pairs_reduce(PairPlan const &p, const cplx *x, const cplx *Tdiag, cplx *acc_or_y, int finalize,
+                         cudaStream_t st);
 void launch_pairs_finalize(const cplx *x, const cplx *Tdiag, const cplx *acc, size_t N, cplx *y, cudaStream_t st);
 void launch_pairs_expand_block(PairPlan const &p, const cplx *AB, int i, int j, const cplx *Tdiag, cplx *out,
                                cudaStream_t st);
@@ -101,6 +103,17 @@ void launch_pairs_expand_block(PairPlan const &p, const cplx *AB, int i, int j, 
 void assemble_pairs_tuning(int minb); // 0 auto, 2 or 3 resident CTAs per SM
 void launch_assemble_pairs(VtacTableSet const &ts, const double *xyz, cplx k, const int2 *pair_ij, long npairs,
                            cplx *AB, cudaStream_t st);
+
+// ---- ob_rot.cu (rotated-axial operator: per pair phases, axial A/B, Wigner small-d; see the file header) ----
+struct RotLayout {
+  int NM = 0, n = 0, X = 0, Dn = 0;          // nMax, harmonics per polarisation, axial entries, small-d reals
+  size_t offA = 0, offB = 0, offD = 0, rec_bytes = 0; // byte offsets inside one pair record (phases at 0)
+};
+RotLayout rot_layout(int NM);
+void launch_assemble_rot(VtacTableSet const &ts, const double *xyz, cplx k, const int2 *pair_ij, long npairs,
+                         unsigned char *recs, RotLayout const &L, cudaStream_t st);
+void launch_matvec_rot(PairPlan const &p, RotLayout const &L, const unsigned char *recs, const cplx *x, const cplx *Tdiag,
+                       cplx *acc_or_y, int finalize, cudaStream_t st, cudaEvent_t e0 = nullptr, cudaEvent_t e1 = nullptr);
 
 // ---- ob_aca.cu (ACA-compressed operator: U V^T-style low-rank far blocks, dense near blocks) ----
 struct AcaDesc {

@@ -536,8 +536,14 @@ void launch_matvec_pairs(PairPlan const &p, const cplx *AB, const cplx *x, const
   }
   if(e1)
     cudaEventRecord(e1, st);
-  k_pairs_reduce<<<p.nobj, OB_REDUCE_THREADS, 0, st>>>(p.rowpart, p.colpart, p.row_seg, p.col_range, p.p0, p.nobj, n, x, Tdiag,
-                                        acc_or_y, finalize);
+  launch_pairs_reduce(p, x, Tdiag, acc_or_y, finalize, st);
+}
+
+// fixed-order sum of rowpart / colpart (shared with the rotated-axial form, ob_rot.cu)
+void launch_pairs_reduce(PairPlan const &p, const cplx *x, const cplx *Tdiag, cplx *acc_or_y, int finalize,
+                         cudaStream_t st) {
+  k_pairs_reduce<<<p.nobj, OB_REDUCE_THREADS, 0, st>>>(p.rowpart, p.colpart, p.row_seg, p.col_range, p.p0, p.nobj, p.n, x,
+                                                        Tdiag, acc_or_y, finalize);
   OB_CUDA(cudaGetLastError());
 }
 

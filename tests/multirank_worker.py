@@ -28,6 +28,8 @@ def main():
         solver.set_aca_mode(1)
     elif mode == "dense":  # the reference's slab, same sharding
         solver.set_option("operator", 0)
+    elif mode == "rot":    # rotated-axial form: pair list sharded, all-reduce of the partial sums
+        solver.set_option("operator", 3)
     res = solver.step()
     cs = sharding.sum_partials(dist, torch, [res[k] for k in ("ext", "sca", "abs", "sca_SH", "abs_SH")], device="cuda")
     # replicated vectors must be bit-identical on all ranks

@@ -27,7 +27,7 @@ def _port():
     return p
 
 
-@pytest.mark.parametrize("world,nobj,mode", [(2, 7, "pairs"), (2, 7, "dense"), (2, 7, "aca"), (4, 10, "pairs"),
+@pytest.mark.parametrize("world,nobj,mode", [(2, 7, "pairs"), (2, 7, "dense"), (2, 7, "aca"), (2, 7, "rot"), (4, 10, "pairs"),
                                              (4, 9, "aca"), (8, 11, "pairs")])
 def test_sharded_step_matches_single_gpu(tmp_path, world, nobj, mode):
     if _ngpu() < world:

@@ -1,0 +1,81 @@
+"""GPU parity of the rotated-axial operator form (operator = 3, optimet_b200/csrc/ob_rot.cu) against the oracle's dense
+operator: same reference operator as the dense / pair forms (srcAna/PreconditionedMatrix.cpp:350-400, 555-610 applied
+by srcAna/scalapack/Belos.hpp:74-90), stored per pair as phases, axial A/B and Wigner small-d matrices.  Complex FP64;
+matvec 1e-12 against the oracle's dense product, full step 1e-9 (BASELINE.json), iteration counts +-1."""
+import numpy as np
+import pytest
+
+import optimet_b200 as ob
+from oracle import oracle as O
+from tests import util as U
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture
+def rot_ctx(gpu_ctx):
+    gpu_ctx.set_option("operator", 3)
+    yield gpu_ctx
+    gpu_ctx.set_option("operator", 1)
+
+
+CLUSTERS = {
+    "random40_n3": lambda: U.random_cluster(40, 3, seed=43),
+    "random12_n6": lambda: U.random_cluster(12, 6, seed=18),
+    "random3_n13": lambda: U.random_cluster(3, 13, seed=16),
+    "random23_n8": lambda: U.random_cluster(23, 8, seed=31),
+    "pair_n1": lambda: U.random_cluster(2, 1, seed=3),
+    "single_n4": lambda: U.random_cluster(1, 4, seed=5),
+    "two_si_z_axis": lambda: U.two_si(nMax=6),                       # theta = 0 / pi
+    "cube27_n4": lambda: U.cube_lattice(3, 4),                       # axis-aligned pairs: theta, phi at 0, pi/2, pi
+    "three_au": lambda: U.three_au(nMax=3),
+    "lossy_bg": lambda: U.Spec("lossy_bg", [[0, 0, 0], [260, 40, -90], [-30, 310, 120]], [60, 80, 70],
+                               U.fixed(9.0 + 0.4j, 7.0 + 0.9j), 4, 700.0, theta_deg=30, phi_deg=20, Eth=0.6, Eph=0.8j,
+                               background=(1.7 + 0.0j, 1.0 + 0.0j)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CLUSTERS))
+@pytest.mark.parametrize("harmonic", [1, 2])
+def test_rot_operator_matvec(rot_ctx, name, harmonic):
+    spec = CLUSTERS[name]()
+    orc = U.oracle_case(spec)
+    U.configure_ctx(rot_ctx, spec, orc)
+    rot_ctx.assemble(harmonic)
+    So = orc.matrix(harmonic)
+    rng = np.random.RandomState(7)
+    for _ in range(2):
+        x = rng.standard_normal(So.shape[1]) + 1j * rng.standard_normal(So.shape[1])
+        assert U.relerr(rot_ctx.matvec(harmonic, x), O.matvec(So, x)) < 1e-12
+    with pytest.raises(RuntimeError, match="rotated-axial"):
+        rot_ctx.fetch_block(harmonic, 0, 0)
+
+
+@pytest.mark.parametrize("name", ["random12_n6", "two_si_z_axis", "three_au", "lossy_bg", "cube27_n4"])
+def test_rot_operator_full_step(rot_ctx, name):
+    spec = CLUSTERS[name]()
+    orc = U.oracle_case(spec)
+    U.configure_ctx(rot_ctx, spec, orc)
+    res = rot_ctx.run(ob.GmresOpts(ob.OB_GMRES_BELOS, 1e-13, 400, 100, 5))
+    orc.solve(O.SOLVER_DIRECT)
+    cs = orc.cross_sections()
+    for key in ("ext", "sca", "sca_SH", "abs_SH"):
+        assert abs(res[key] / cs[key] - 1) < 1e-9, key
+    assert U.relerr(res["X_sca"], orc.vector(0)) < 1e-9 and U.relerr(res["X_sca_SH"], orc.vector(2)) < 1e-9
+
+
+@pytest.mark.parametrize("flavour", ["zcomp", "belos"])
+def test_rot_operator_iteration_counts(rot_ctx, flavour):
+    spec = U.random_cluster(9, 5, seed=21)
+    orc = U.oracle_case(spec)
+    U.configure_ctx(rot_ctx, spec, orc)
+    rot_ctx.assemble(1)
+    So, Q = orc.matrix(1), orc.source()
+    if flavour == "zcomp":
+        opts = ob.GmresOpts(ob.OB_GMRES_ZCOMP, 1e-6, 240, 0, 2)
+        xo, ito, _ = O.solve_dense(So, Q, O.SOLVER_ZCOMP, tol=1e-6, maxit=240, max_restarts=2)
+    else:
+        opts = ob.GmresOpts(ob.OB_GMRES_BELOS, 1e-5, 50, 30, 20)
+        xo, ito, _ = O.solve_dense(So, Q, O.SOLVER_BELOS, tol=1e-5, maxit=50, restart=30, max_restarts=20)
+    x, it, _ = rot_ctx.solve(1, Q, opts)
+    assert abs(it - ito) <= 1 and U.relerr(x, xo) < 1e-7

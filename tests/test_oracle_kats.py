@@ -313,3 +313,39 @@ def test_as_shipped_switches_do_not_change_results():
         O.set_as_shipped(0, 0)
     assert U.relerr(S1, S0) < 1e-13
     assert U.relerr(K1, K0) < 1e-12
+
+
+def test_rotation_axial_factorisation():
+    """A(R) = U A(d z) U^-1 with U = diag(exp(i m phi)) d(theta) (Wigner small-d, Varshalovich 4.3.1), the axial blocks
+    diagonal in m with A(-mu) = A(mu), B(-mu) = -B(mu), and the reversed direction by parity: an independent pin of the
+    angular dependence of the oracle's translation coefficients, and the exact data layout / index formulas of the
+    device's rotated-axial operator (csrc/ob_rot.cu) through tests/rot_model.py."""
+    from tests import rot_model as R
+    k = 2 * np.pi / 800e-9 * (1.2 + 0.05j)
+    NM = 5
+    n = NM * (NM + 2)
+    # small-d recurrence against the explicit sum, incl. both poles
+    for beta in (0.0, 0.3, np.pi / 2, 2.9, np.pi):
+        for mp in range(-NM, NM + 1):
+            for m in range(-NM, NM + 1):
+                col = R.small_d_column(NM, mp, m, beta)
+                for j in range(max(abs(mp), abs(m), 1), NM + 1):
+                    assert abs(col[j] - R.wd(j, mp, m, beta)) < 1e-13
+    rng = np.random.RandomState(1)
+    for (d, the, phi) in ((260e-9, 1.1, 0.7), (190e-9, 2.7, -2.0), (400e-9, 0.0, 0.0), (210e-9, np.pi, 0.0),
+                          (330e-9, np.pi / 2, np.pi)):
+        A, B = O.coupling([d, the, phi], k, NM, True)
+        vec = -d * np.array([np.sin(the) * np.cos(phi), np.sin(the) * np.sin(phi), np.cos(the)])
+        Ar, Br = O.coupling([d, np.arccos(vec[2] / d), np.arctan2(vec[1], vec[0])], k, NM, True)
+        ph, dmat, Aax, Bax, Az, Bz = R.build_pair(NM, d, the, phi, k)
+        mask = np.array([[R.flat(1, 1) >= 0 and (p_m == q_m) for q_m in _ms(NM)] for p_m in _ms(NM)])
+        assert not np.abs(Az[~mask]).any() and not np.abs(Bz[~mask]).any()      # axial: equal m only
+        X = rng.standard_normal((2, n)) + 1j * rng.standard_normal((2, n))
+        W = R.apply_pair(NM, ph, dmat, Aax, Bax, X, 1.0, False)
+        assert U.relerr(W, np.stack([A.T @ X[0] + B.T @ X[1], B.T @ X[0] + A.T @ X[1]])) < 1e-13
+        Wr = R.apply_pair(NM, ph, dmat, Aax, Bax, X, -1.0, True)
+        assert U.relerr(Wr, np.stack([Ar.T @ X[0] + Br.T @ X[1], Br.T @ X[0] + Ar.T @ X[1]])) < 1e-13
+
+
+def _ms(NM):
+    return [m for nn in range(1, NM + 1) for m in range(nn, -nn - 1, -1)]
