@@ -1633,6 +1633,10 @@ int ob_set_option(ob_ctx *ctx, const char *name, double value) {
   } else if(n == "assemble_minb") { // tuning: resident CTAs per SM k_assemble_pairs is compiled for (0 auto, 2, 3)
     need(value == 0 || value == 2 || value == 3, "assemble_minb must be 0, 2 or 3");
     assemble_pairs_tuning((int)value);
+  } else if(n == "rot_assembly") { // 0 = validated vtac_block path, 1 = axial-only recursion (not yet validated on a GPU)
+    need(value == 0 || value == 1, "rot_assembly must be 0 or 1");
+    rot_tuning((int)value);
+    ctx->hs[0].assembled = ctx->hs[1].assembled = false;
   } else if(n == "eps_aca") {
     need(value > 0, "eps_aca must be positive");
     ctx->eps_aca = value;

@@ -110,6 +110,7 @@ struct RotLayout {
   size_t offA = 0, offB = 0, offD = 0, rec_bytes = 0; // byte offsets inside one pair record (phases at 0)
 };
 RotLayout rot_layout(int NM);
+void rot_tuning(int assembly); // 0 = vtac_block-based axial assembly (default), 1 = axial-only recursion
 void launch_assemble_rot(VtacTableSet const &ts, const double *xyz, cplx k, const int2 *pair_ij, long npairs,
                          unsigned char *recs, RotLayout const &L, cudaStream_t st);
 void launch_matvec_rot(PairPlan const &p, RotLayout const &L, const unsigned char *recs, const cplx *x, const cplx *Tdiag,

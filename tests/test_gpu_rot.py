@@ -79,3 +79,25 @@ def test_rot_operator_iteration_counts(rot_ctx, flavour):
         xo, ito, _ = O.solve_dense(So, Q, O.SOLVER_BELOS, tol=1e-5, maxit=50, restart=30, max_restarts=20)
     x, it, _ = rot_ctx.solve(1, Q, opts)
     assert abs(it - ito) <= 1 and U.relerr(x, xo) < 1e-7
+
+
+@pytest.mark.skipif(__import__("os").environ.get("OB_VALIDATE_PENDING") != "1",
+                    reason="k_assemble_axial_only was written after the round-1 GPU budget was spent: run with "
+                           "OB_VALIDATE_PENDING=1 to validate it, then make it the default (DESIGN.md section 8)")
+@pytest.mark.parametrize("name", ["random12_n6", "random3_n13", "random23_n8", "two_si_z_axis", "lossy_bg"])
+def test_rot_axial_only_assembly_pending(rot_ctx, name):
+    """The O(nMax^3) axial-only assembly ("rot_assembly" = 1) must produce the operator the validated path produces."""
+    spec = CLUSTERS[name]()
+    orc = U.oracle_case(spec)
+    U.configure_ctx(rot_ctx, spec, orc)
+    rng = np.random.RandomState(3)
+    for harmonic in (1, 2):
+        So = orc.matrix(harmonic)
+        x = rng.standard_normal(So.shape[1]) + 1j * rng.standard_normal(So.shape[1])
+        rot_ctx.set_option("rot_assembly", 1)
+        try:
+            rot_ctx.assemble(harmonic)
+            y1 = rot_ctx.matvec(harmonic, x)
+        finally:
+            rot_ctx.set_option("rot_assembly", 0)
+        assert U.relerr(y1, O.matvec(So, x)) < 1e-12

@@ -349,3 +349,18 @@ def test_rotation_axial_factorisation():
 
 def _ms(NM):
     return [m for nn in range(1, NM + 1) for m in range(nn, -nn - 1, -1)]
+
+
+@pytest.mark.parametrize("NM,k,d", [(6, 2 * np.pi / 800e-9 * (1.2 + 0.05j), 300e-9), (10, 2 * np.pi / 800e-9, 190e-9),
+                                    (13, 2 * np.pi / 400e-9, 160e-9)])
+def test_axial_only_recursion(NM, k, d):
+    """theta = 0: the TA recursion closes on the k = m entries (O(nMax^3) per pair).  tests/rot_axial_model.py is the
+    specification of the axial-only assembly kernel of the rotated-axial operator form; here against Coupling."""
+    from tests import rot_axial_model as M
+    Az, Bz = O.coupling([d, 0.0, 0.0], k, NM, True)
+    A, B = M.axial_AB(NM, k * d)
+    fl = lambda n, m: n * (n + 1) - m - 1
+    sa, sb = np.abs(Az).max(), np.abs(Bz).max()
+    for (mu, n, l), v in A.items():
+        assert abs(v - Az[fl(n, mu), fl(l, mu)]) < 1e-13 * sa
+        assert abs(B[(mu, n, l)] - Bz[fl(n, mu), fl(l, mu)]) < 1e-13 * sb
