@@ -5,13 +5,16 @@
 // __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
 // may load this library; the product (optimet_b200/) never links or calls it.
 //
-// Parity status: "parity unpinned" by the reference's own tests -- the
-// reference ships no tests, golden vectors or fixtures for this path (its
-// regression harness is orphaned and the test-data submodule is absent).  The
-// oracle is pinned instead by (i) the reference's own AMOS sources compiled
-// into oracle/_ref/libamos_ref.so (Bessel/Hankel values, incl. the -conj(k)
-// branch), (ii) independent known-answer tests (scipy / sympy / closed-form
-// Mie / translation-group identities), see tests/test_oracle_*.py.
+// Parity status.  The reference ships no tests, golden vectors or fixtures for this path (its regression harness is
+// orphaned and the test-data submodule is absent), so nothing of the reference's own test data pins it.  It is pinned
+// instead by (i) the REFERENCE'S OWN TRANSLATION UNITS compiled where they lie into oracle/_ref/libpath_ref.so
+// (TranslationAdditionCoefficients, Coupling, Scatterer, ElectroMagnetic, AuxCoefficients, Excitation, Symbol,
+// Geometry, AMOS; `make -C oracle ref_path`, stand-ins for the absent libraries in oracle/stub/): this restatement
+// reproduces them to 1e-13 or bit for bit (tests/test_reference_build.py); (ii) independent known-answer tests
+// (scipy / sympy / closed-form Mie / translation-group and rotation identities, plane wave, boundary continuity), see
+// tests/test_oracle_*.py.  "Parity unpinned" remains true for what lives in the TUs that cannot be built here
+// (PreconditionedMatrix.cpp, Solver.cpp, Result.cpp: block assembly wrapper, the GMRES flavours, ACA, the
+// extinction / scattering sums), which are covered by (ii) only.
 //
 // Every function cites the reference file:line it follows (paths relative to
 // /root/reference/srcAna/).  Third-party arithmetic that is NOT in the
