@@ -145,6 +145,26 @@ def cpu_reference_time(wl, threads, iters_ff, iters_sh, sample_rows=None, repeat
         orc.source()
         t_src += time.perf_counter() - t0
     t_asm, t_mv, t_src = t_asm / repeat, t_mv / repeat, t_src / repeat
+    # a sample of the same blocks on the reference's OWN compiled Coupling (oracle/_ref/libpath_ref.so, built from the
+    # reference sources; single thread: its f2c'd AMOS keeps static state and is not thread-safe)
+    ref_note = ""
+    try:
+        from oracle import reference_build as RB
+        if RB.have():
+            k = complex(orc.info()["waveK"])
+            xyz = np.asarray(a["xyz"], dtype=float)
+            jobs = [(0, j) for j in range(1, min(nobj, 65))]
+            t0 = time.perf_counter()
+            for i, j in jobs:
+                d = xyz[i] - xyz[j]
+                r = float(np.linalg.norm(d))
+                RB.coupling([r, float(np.arccos(d[2] / r)), float(np.arctan2(d[1], d[0]))], k, nMax, True)
+            per_block = (time.perf_counter() - t0) / max(1, len(jobs))
+            ref_note = ("; the reference's own compiled Coupling takes %.1f ms per block on one thread (%d blocks timed; "
+                        "the port: %.1f ms per block and thread)"
+                        % (per_block * 1e3, len(jobs), t_asm * min(threads, rows) / (rows * (nobj - 1)) * 1e3))
+    except Exception:
+        pass
     # SH source: per particle cost from the oracle on `rows` particles is not separable through the case API;
     # time the whole SH source once on a reduced cluster of `rows` particles
     orc2 = O.Case()
@@ -163,8 +183,8 @@ def cpu_reference_time(wl, threads, iters_ff, iters_sh, sample_rows=None, repeat
              + t_sh * scale)                         # SH source
     sample = ("oracle port, %d threads: FF assembly of %d of %d block-rows (%.2fs), %d matvecs on that %dx%d slab "
               "(%.3fs each), FF source (%.2fs), SH source on %d particles (%.2fs); scaled to the full workload with "
-              "the GPU run's GMRES iteration counts (%d FF + %d SH)"
-              % (threads, rows, nobj, t_asm, nmv, n2 * rows, N, t_mv, t_src, rows, t_sh, iters_ff, iters_sh))
+              "the GPU run's GMRES iteration counts (%d FF + %d SH)%s"
+              % (threads, rows, nobj, t_asm, nmv, n2 * rows, N, t_mv, t_src, rows, t_sh, iters_ff, iters_sh, ref_note))
     return total, sample
 
 
