@@ -90,6 +90,13 @@ def inc_local(wavelength_m, theta, phi, Eth, Eph, nMax, R_sph, background=(1.0, 
     return out
 
 
+def relative_position(xyz_i, xyz_j):
+    """vR_i - vR_j as the reference forms it (Tools::toSpherical of both, Spherical::operator-): (r, theta, phi)."""
+    out = (C.c_double * 3)()
+    lib().ref_relative_position((C.c_double * 3)(*xyz_i), (C.c_double * 3)(*xyz_j), out)
+    return [out[0], out[1], out[2]]
+
+
 def ynm(n, m, theta, phi):
     out = (C.c_double * 2)()
     lib().ref_ynm(int(n), int(m), C.c_double(theta), C.c_double(phi), out)

@@ -118,6 +118,17 @@ int ref_inc_local(double lambda, double theta, double phi, const double Eth[2], 
   auto e = make_excitation(lambda, theta, phi, Eth, Eph, bg_eps_r, bg_mu_r, nMax);
   return e->getIncLocal(Spherical<double>(R[0], R[1], R[2]), (cd *)out, nMax);
 }
+// Spherical<double>::operator- (Spherical.h:129-131) and Tools::toSpherical (Tools.cpp:250-258): relative position of
+// two scatterers exactly as PreconditionedMatrix.cpp:384 forms it
+int ref_relative_position(const double xyz_i[3], const double xyz_j[3], double out[3]) {
+  const Spherical<double> a = Tools::toSpherical(Cartesian<double>(xyz_i[0], xyz_i[1], xyz_i[2]));
+  const Spherical<double> b = Tools::toSpherical(Cartesian<double>(xyz_j[0], xyz_j[1], xyz_j[2]));
+  const Spherical<double> d = a - b;
+  out[0] = d.rrr;
+  out[1] = d.the;
+  out[2] = d.phi;
+  return 0;
+}
 // the Boost.Math stand-in itself, for its check against scipy
 int ref_ynm(int n, int m, double theta, double phi, double out[2]) {
   const cd y = boost::math::spherical_harmonic((unsigned)n, m, theta, phi);

@@ -138,6 +138,41 @@ def test_oracle_sh_path_equals_the_reference(backend, name):
     assert [ref.check_inner(list(p)) for p in pts] == list(inner)
 
 
+@pytest.mark.parametrize("name", sorted(SPECS))
+@pytest.mark.parametrize("harmonic", [1, 2])
+def test_oracle_matrix_and_source_from_reference_pieces(backend, name, harmonic):
+    """Rows a4, a5, a11: PreconditionedMatrix.cpp cannot be compiled here, but its assembly is three lines around pinned
+    pieces -- block (i, j) = -T_i [[A^T, B^T], [B^T, A^T]] with AB = Coupling(vR_i - vR_j, k, nMax) (:384-390, :592-598),
+    identity on the diagonal (:379), Q_j = T_j .* getIncLocal(vR_j) (:1339-1341).  Written out here from the
+    reference's compiled Coupling / Scatterer / Excitation and compared with the oracle's matrix and source."""
+    spec = SPECS[name]()
+    orc = U.oracle_case(spec)
+    bg = spec.background if spec.background is not None else (1.0, 1.0)
+    n, nobj = spec.nMax * (spec.nMax + 2), len(spec.xyz)
+    k = orc.info()["waveK"] * harmonic
+    S = orc.matrix(harmonic)
+    T = [RB.particle_factors(m, p, r, spec.nMax, spec.wavelength, harmonic - 1, bg) for r, (m, p) in zip(spec.radius, spec.material)]
+    for i in range(nobj):
+        for j in range(nobj):
+            blk = S[2 * n * i:2 * n * (i + 1), 2 * n * j:2 * n * (j + 1)]
+            if i == j:
+                assert np.array_equal(blk, np.eye(2 * n))
+                continue
+            A, B = RB.coupling(RB.relative_position(list(spec.xyz[i]), list(spec.xyz[j])), k, spec.nMax, True)
+            want = -T[i][:, None] * np.block([[A.T, B.T], [B.T, A.T]])
+            assert np.abs(blk - want).max() < 1e-12 * np.abs(want).max(), (i, j)
+    if harmonic == 1:
+        Q = orc.source()
+        for j in range(nobj):
+            p = spec.xyz[j]
+            r = np.linalg.norm(p)
+            if r == 0:
+                continue
+            loc = RB.inc_local(spec.wavelength, spec.theta, spec.phi, spec.Eth, spec.Eph, spec.nMax,
+                               [r, np.arccos(p[2] / r), np.arctan2(p[1], p[0])], bg)
+            assert U.relerr(Q[2 * n * j:2 * n * (j + 1)], T[j] * loc) < 1e-12
+
+
 # ---------------------------------------------------------------------------------------------- CUDA path vs reference
 @pytest.mark.gpu
 @pytest.mark.parametrize("R,k,nMax,flag", COUPLING_CASES)
