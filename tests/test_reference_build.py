@@ -123,6 +123,22 @@ def test_oracle_sh_path_equals_the_reference(backend, name):
         aux = ref.cabs_aux(j)
         cabs += (np.abs(xs[2 * n * j:2 * n * j + n]) ** 2 * aux[:n]).sum() + (np.abs(xs[2 * n * j + n:2 * n * (j + 1)]) ** 2 * aux[n:]).sum()
     assert abs(cabs / k.real ** 2 / cs["abs_direct"] - 1) < 1e-11
+    # extinction and scattering (Result.cpp:557-646): sums over getIncLocal and over the regular Coupling to the origin
+    cext = csca = 0.0
+    for j in range(nobj):
+        p = spec.xyz[j]
+        r = np.linalg.norm(p)
+        xj = xs[2 * n * j:2 * n * (j + 1)]
+        if r == 0:  # the oracle's restatement is used for a particle AT the origin only (Coupling -> identity, :82-84)
+            loc, TAB = orc.inc_local(j), np.eye(2 * n)
+        else:
+            R = [r, np.arccos(p[2] / r), np.arctan2(p[1], p[0])]
+            loc = RB.inc_local(spec.wavelength, spec.theta, spec.phi, spec.Eth, spec.Eph, spec.nMax, R, bg)
+            A, B = RB.coupling(R, k, spec.nMax, False)
+            TAB = np.block([[A.T, B.T], [B.T, A.T]])      # T_AB[p][q] = diagonal(q, p) ...
+        cext += (np.conj(loc) * xj).sum().real
+        csca += (np.abs(TAB) ** 2 * (np.abs(xj) ** 2)[None, :]).sum()
+    assert abs(-cext / k.real ** 2 / cs["ext"] - 1) < 1e-11 and abs(csca / k.real ** 2 / cs["sca"] - 1) < 1e-11
     eta = np.sqrt(bg[1] * U.MU0 / (bg[0] * U.EPS0))
     abs_sh = 0.0
     for j in range(nobj):
