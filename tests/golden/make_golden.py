@@ -11,6 +11,9 @@ AMOS-backed numbers.
 
     python tests/golden/make_golden.py        (run in the build container; needs oracle/_ref)
     python tests/golden/make_golden.py 8f     (only the fixtures of the SURVEY 8f rows: ACA operator, field maps)
+    python tests/golden/make_golden.py ref    (vtac_reference.npz: A/B blocks, Mie factors, incident coefficients, CG
+                                               tables straight from the reference's own compiled translation units,
+                                               oracle/_ref/libpath_ref.so -- no oracle arithmetic involved)
 """
 import os
 import sys
@@ -122,7 +125,32 @@ def main_8f():
         O.set_bessel_backend(0)
 
 
+def main_ref():
+    """Fixtures produced by the reference's own compiled code (oracle/reference_build.py), so that the GPU box and any
+    later container without /root/reference still hold the reference's numbers."""
+    from oracle import reference_build as RB
+    if not RB.have():
+        raise SystemExit("oracle/_ref/libpath_ref.so missing: run `make -C oracle` with /root/reference present")
+    out = {}
+    for i, (R, k, nMax, flag) in enumerate(VTAC_CASES):
+        out["A%d" % i], out["B%d" % i] = RB.coupling(R, k, nMax, flag)
+    for name, make in CASES.items():
+        spec = make()
+        bg = spec.background if spec.background is not None else (1.0, 1.0)
+        fac = np.array([np.concatenate([RB.particle_factors(m, p, r, spec.nMax, spec.wavelength, w, bg)
+                                        for r, (m, p) in zip(spec.radius, spec.material)]) for w in range(7)])
+        a, b, wk = RB.excitation(spec.wavelength, spec.theta, spec.phi, spec.Eth, spec.Eph, spec.nMax, bg)
+        out["factors_" + name], out["a_" + name], out["b_" + name], out["waveK_" + name] = fac, a, b, np.array(wk)
+    ref = RB.case_from_spec(CASES["three_au_nmax3"]())
+    out["cg_tables_nmax3"] = np.array([ref.cg_table(t) for t in range(9)])
+    np.savez_compressed(os.path.join(HERE, "reference_build.npz"), **out)
+    print("reference_build.npz:", sorted(out))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "ref":
+        main_ref()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "8f":
         main_8f()
         sys.exit(0)
