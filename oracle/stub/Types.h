@@ -1,17 +1,21 @@
-/* Stand-in for the reference's cmake-generated Types.h (srcAna/Types.in.h with every #cmakedefine off: serial build,
- * no Belos / MPI / ScaLAPACK), written for this repo so that a few of the reference's own translation units can be
- * compiled where they lie (oracle/Makefile, target ref_coupling).  Same typedefs and aliases as Types.in.h:33-52. */
+/* Stand-in for the header cmake generates from srcAna/Types.in.h in a real build of the reference (configure_file with
+ * every #cmakedefine off: serial, no Belos / MPI / ScaLAPACK).  Written for this repo so that some of the reference's
+ * translation units compile where they lie (oracle/Makefile, target ref_path); it only has to provide the scalar type
+ * names and the two container aliases those files use, here on top of the container-only <Eigen/Core> of this
+ * directory. */
 #ifndef OPTIMET_TYPES_H
 #define OPTIMET_TYPES_H
-#include <complex>
-#include <functional>
 #include <Eigen/Core>
+#include <complex>
+#include <cstddef>
+#include <functional>
 namespace optimet {
-typedef int t_int;
-typedef std::size_t t_uint;
-typedef double t_real;
-typedef std::complex<t_real> t_complex;
-template <class T = t_complex> using Vector = Eigen::Matrix<T, Eigen::Dynamic, 1, Eigen::ColMajor>;
-template <class T = t_complex> using Matrix = Eigen::Matrix<T, Eigen::Dynamic, Eigen::Dynamic, Eigen::ColMajor>;
-}
+using t_real = double;                  /* reals */
+using t_complex = std::complex<t_real>; /* complex numbers */
+using t_int = int;                      /* signed indices */
+using t_uint = std::size_t;             /* unsigned indices */
+/* column-major dynamic containers */
+template <class SCALAR = t_complex> using Matrix = Eigen::Matrix<SCALAR, Eigen::Dynamic, Eigen::Dynamic, Eigen::ColMajor>;
+template <class SCALAR = t_complex> using Vector = Eigen::Matrix<SCALAR, Eigen::Dynamic, 1, Eigen::ColMajor>;
+} // namespace optimet
 #endif
