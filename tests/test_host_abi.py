@@ -133,6 +133,12 @@ def test_reads_eleven_particles_belos_list():
     case = H.Case(path=os.path.join(EXAMPLES, "ElevenParticlesSi.xml"))
     i = case.info()
     assert (i["nobj"], i["nMax"], i["outputType"]) == (11, 12, 0)
+    # the file ships as a FIELD output (:87-93): 191 x 271 x 2 grid in nm -> Run::params in metres (Reader.cpp:850-858)
+    assert np.allclose(i["params"], [-450e-9, 4450e-9, 191, -450e-9, 4450e-9, 271, -0.1e-9, 0.1e-9, 2], rtol=1e-12)
+    pts = case.grid_points()                                   # OutputGrid::getPoint order, x fastest, +1e-12 m
+    assert pts.shape == (191 * 271 * 2, 3)
+    x0 = pts[0, 0] * np.sin(pts[0, 1]) * np.cos(pts[0, 2])
+    assert abs(x0 - (-450e-9 + 1e-12)) < 1e-20
     o = case.gmres_defaults()  # examples/ElevenParticlesSi.xml:4-12
     assert (o.flavour, o.tol, o.max_iters, o.restart, o.max_restarts) == (capi.OB_GMRES_BELOS, 1e-5, 50, 30, 20)
 
