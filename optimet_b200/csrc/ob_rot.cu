@@ -21,6 +21,7 @@
 // them in a fixed order and applies y = x - T .* acc, exactly as for the pair form.
 #include "ob_internal.h"
 #include "ob_vtac.cuh"
+#include "ob_rot_axial.cuh"
 #include <algorithm>
 #include <cuda_pipeline.h>
 
@@ -35,13 +36,6 @@ namespace ob {
 __host__ __device__ inline int rot_offD(int n) { // sum_{j<n} (2j+1)^2
   const int t = n - 1;
   return 4 * (t * (t + 1) * (2 * t + 1) / 6) + 4 * (t * (t + 1) / 2) + t;
-}
-__host__ __device__ inline int rot_n0(int mu) { return mu > 1 ? mu : 1; }
-__host__ __device__ inline int rot_offX(int NM, int mu) { // sum_{u<mu} (NM - max(u,1) + 1)^2
-  if(mu <= 0)
-    return 0;
-  const int a = NM, b = NM - mu + 1; // sum_{s=b+1}^{a} s^2
-  return NM * NM + (a * (a + 1) * (2 * a + 1) / 6 - b * (b + 1) * (2 * b + 1) / 6);
 }
 RotLayout rot_layout(int NM) {
   RotLayout L;
@@ -95,36 +89,21 @@ k_assemble_axial(VtacTables tb, const double *__restrict__ xyz, cplx k, const in
 // assembly 1b (opt-in, "rot_assembly" = 1): axial-only recursion, one warp per pair.  With theta = 0 the scalar
 // coefficients beta(n, m, l, k) vanish unless k = m and the reference's recursion
 // (TranslationAdditionCoefficients.cpp:102-124) closes on those entries: O(nMax^3) per pair instead of the O(nMax^4)
-// of the full block.  Transliterated from tests/rot_axial_model.py (pinned against the oracle's Coupling to 1e-16 by
-// tests/test_oracle_kats.py::test_axial_only_recursion).  NOT yet run on a GPU: the round-1 GPU budget was spent when
-// it was written, so it stays off by default until tests/test_gpu_rot.py has been run with the option set.
+// of the full block.  The per-pair body lives in ob_rot_axial.cuh and is ALSO compiled for the host: the very source the
+// warp runs is checked on the CPU against the oracle's Coupling (tests/test_rot_axial_host.py, lane 0 of 1).  NOT yet
+// run on a GPU: the round-1 GPU budget was spent when it was written, so it stays off by default until
+// tests/test_gpu_rot.py has been run with OB_VALIDATE_PENDING=1.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double ta_a_plus(int n, int m) {
-  return -sqrt((double)((n + m + 1) * (n - m + 1)) / (double)((2 * n + 1) * (2 * n + 3)));
-}
-__device__ __forceinline__ double ta_a_minus(int n, int m) {
-  return sqrt((double)((n + m) * (n - m)) / (double)((2 * n + 1) * (2 * n - 1)));
-}
-__device__ __forceinline__ double ta_b_plus(int n, int m) {
-  return sqrt((double)((n + m + 2) * (n + m + 1)) / (double)((2 * n + 1) * (2 * n + 3)));
-}
-__device__ __forceinline__ double ta_b_minus(int n, int m) {
-  return sqrt((double)((n - m) * (n - m - 1)) / (double)((2 * n + 1) * (2 * n - 1)));
-}
 #define ROT_AX_WARPS 4
-// per warp: three level buffers [3][NM + 2][L + 3] complex (level n % 3, chain m, degree l), entries with l < m are
-// never written and stay zero
-static size_t rot_axial_smem_bytes(int NM) {
-  return (size_t)ROT_AX_WARPS * 3 * (NM + 2) * (2 * NM + 3) * sizeof(cplx);
-}
+static size_t rot_axial_smem_bytes(int NM) { return (size_t)ROT_AX_WARPS * rot_axial_buf_entries(NM) * sizeof(cplx); }
 __global__ void __launch_bounds__(ROT_AX_WARPS * 32)
 k_assemble_axial_only(const double *__restrict__ xyz, cplx k, const int2 *__restrict__ pair_ij, long npairs,
                       unsigned char *__restrict__ recs, RotLayout L) {
   extern __shared__ __align__(16) unsigned char smem_ax[];
-  const int NM = L.NM, LL = 2 * NM, W = LL + 3, CH = NM + 2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  cplx *buf = (cplx *)smem_ax + (size_t)warp * 3 * CH * W;
-  for(int e = lane; e < 3 * CH * W; e += 32)
+  const int entries = rot_axial_buf_entries(L.NM);
+  cplx *buf = (cplx *)smem_ax + (size_t)warp * entries;
+  for(int e = lane; e < entries; e += 32)
     buf[e] = mk(0, 0);
   __syncwarp();
   for(long q = (long)blockIdx.x * ROT_AX_WARPS + warp; q < npairs; q += (long)gridDim.x * ROT_AX_WARPS) {
@@ -133,78 +112,7 @@ k_assemble_axial_only(const double *__restrict__ xyz, cplx k, const int2 *__rest
                  z = xyz[3 * ij.x + 2] - xyz[3 * ij.y + 2];
     const double r = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
     unsigned char *rec = recs + (size_t)q * L.rec_bytes;
-    cplx *Aout = (cplx *)(rec + L.offA), *Bout = (cplx *)(rec + L.offB);
-    // seeds (n = m = 0): sqrt(4 pi) (-1)^l Y_l0(0) h_l = (-1)^l sqrt(2l + 1) h_l(k d); every lane runs the short upward
-    // Hankel recurrence and keeps the orders it owns
-    {
-      cplx h[2 * OB_MAX_NMAX + 2];
-      sph_hankel1(cscale(k, r), LL + 1, h);
-      for(int l = lane; l <= LL; l += 32) {
-        const double f = ((l & 1) ? -1.0 : 1.0) * sqrt(2.0 * l + 1.0);
-        buf[(0 * CH + 0) * W + l] = cscale(h[l], f);
-      }
-    }
-    __syncwarp();
-    for(int n = 1; n <= NM; ++n) {
-      cplx *cur = buf + (size_t)(n % 3) * CH * W;
-      const cplx *p1 = buf + (size_t)((n - 1) % 3) * CH * W, *p2 = buf + (size_t)((n + 1) % 3) * CH * W; // n-1, n-2
-      const int span = LL - n + 1; // l in [m, LL - n]: index t = m * span + (l - m) over a (n + 1) x span rectangle
-      for(int t = lane; t < (n + 1) * span; t += 32) {
-        const int m = t / span, l = m + (t - m * span);
-        if(l > LL - n)
-          continue;
-        cplx v;
-        if(m == n) { // sectorial step (:113-117)
-          const cplx lo = l - 1 >= n - 1 ? p1[(n - 1) * W + (l - 1)] : mk(0, 0);
-          const cplx up = p1[(n - 1) * W + (l + 1)];
-          const double c0 = l - 1 >= n - 1 ? ta_b_plus(l - 1, n - 1) : 0.0, c1 = ta_b_minus(l + 1, n - 1);
-          const double inv = 1.0 / ta_b_plus(n - 1, n - 1);
-          v = mk((lo.x * c0 + up.x * c1) * inv, (lo.y * c0 + up.y * c1) * inv);
-        } else { // general step (:119-124)
-          const cplx lo = l - 1 >= m ? p1[m * W + (l - 1)] : mk(0, 0);
-          const cplx up = p1[m * W + (l + 1)];
-          const cplx o = n - 2 >= m ? p2[m * W + l] : mk(0, 0);
-          const double c0 = l - 1 >= m ? ta_a_plus(l - 1, m) : 0.0, c1 = ta_a_minus(l + 1, m);
-          const double c2 = n - 2 >= m ? ta_a_minus(n - 1, m) : 0.0, inv = 1.0 / ta_a_plus(n - 1, m);
-          v = mk((lo.x * c0 + up.x * c1 - o.x * c2) * inv, (lo.y * c0 + up.y * c1 - o.y * c2) * inv);
-        }
-        cur[m * W + l] = v;
-      }
-      __syncwarp();
-      // A, B of column degree n for every mu <= n and row degree l (Coupling.cpp:30-51 with k = m = mu)
-      for(int t = lane; t < (n + 1) * NM; t += 32) {
-        const int mu = t / NM, l = 1 + (t - mu * NM);
-        if(l < mu || (mu == 0 && n < 1))
-          continue;
-        const int n0 = rot_n0(mu);
-        if(n < n0 || l < n0)
-          continue;
-        // beta(n, m', l', m') at this level; m' = -1 by the phase-free symmetry beta(n,-m,l,-m) = beta(n,m,l,m)
-        auto ta = [&](int mp, int lp) -> cplx {
-          const int am = mp < 0 ? -mp : mp;
-          if(am > n || am > lp || lp < 0)
-            return mk(0, 0);
-          return cur[am * W + lp];
-        };
-        const double fa = 0.5 / sqrt((double)(l * (l + 1) * n * (n + 1)));
-        const double a0 = 2.0 * mu * mu;
-        const double a1 = sqrt((double)((n - mu) * (n + mu + 1) * (l - mu) * (l + mu + 1)));
-        const double a2 = sqrt((double)((n + mu) * (n - mu + 1) * (l + mu) * (l - mu + 1)));
-        const cplx t0 = ta(mu, l), tp = ta(mu + 1, l), tm = ta(mu - 1, l);
-        const cplx Av = mk(fa * (a0 * t0.x + a1 * tp.x + a2 * tm.x), fa * (a0 * t0.y + a1 * tp.y + a2 * tm.y));
-        const double fb = -0.5 * sqrt((2.0 * l + 1.0) / ((double)(2 * l - 1) * (double)(l * (l + 1)) * (double)(n * (n + 1))));
-        const double b0 = 2.0 * mu * sqrt((double)((l - mu) * (l + mu)));
-        const double b1 = sqrt((double)((n - mu) * (n + mu + 1) * (l - mu) * (l - mu - 1)));
-        const double b2 = sqrt((double)((n + mu) * (n - mu + 1) * (l + mu) * (l + mu - 1)));
-        const cplx u0 = ta(mu, l - 1), up = ta(mu + 1, l - 1), um = ta(mu - 1, l - 1);
-        const cplx sB = mk(b0 * u0.x + b1 * up.x - b2 * um.x, b0 * u0.y + b1 * up.y - b2 * um.y);
-        const cplx Bv = mk(-fb * sB.y, fb * sB.x); // times i fb (factor = (0, fb))
-        const int w = NM - n0 + 1, e = rot_offX(NM, mu) + (n - n0) * w + (l - n0);
-        Aout[e] = Av;
-        Bout[e] = Bv;
-      }
-      __syncwarp();
-    }
+    rot_axial_pair(L.NM, k, r, buf, (cplx *)(rec + L.offA), (cplx *)(rec + L.offB), lane, 32);
     __syncwarp();
   }
 }

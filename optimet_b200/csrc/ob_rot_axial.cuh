@@ -1,0 +1,119 @@
+// ob_rot_axial.cuh -- axial-only translation recursion for one pair, written once for the device (one warp per pair,
+// lanes stride the items of a level) and for the host (lane 0 of 1: the CPU check of this very source in
+// tests/test_rot_axial_host.py, which compiles tests/rot_axial_host.cpp around this header).
+//
+// With theta = 0 the scalar coefficients beta(n, m, l, k) vanish unless k = m and the reference's recursion
+// (srcAna/TranslationAdditionCoefficients.cpp:102-124) closes on those entries: O(nMax^3) per pair instead of the
+// O(nMax^4) of the full block.  Transliterated from tests/rot_axial_model.py.
+#pragma once
+#include "ob_common.cuh"
+#include "ob_special.cuh"
+
+#if defined(__CUDA_ARCH__)
+#define OB_SYNCWARP() __syncwarp()
+#else
+#define OB_SYNCWARP() ((void)0)
+#endif
+
+namespace ob {
+
+__host__ __device__ inline int rot_n0(int mu) { return mu > 1 ? mu : 1; }
+__host__ __device__ inline int rot_offX(int NM, int mu) { // sum_{u<mu} (NM - max(u,1) + 1)^2
+  if(mu <= 0)
+    return 0;
+  const int a = NM, b = NM - mu + 1; // sum_{s=b+1}^{a} s^2
+  return NM * NM + (a * (a + 1) * (2 * a + 1) / 6 - b * (b + 1) * (2 * b + 1) / 6);
+}
+__host__ __device__ inline double ta_a_plus(int n, int m) {
+  return -sqrt((double)((n + m + 1) * (n - m + 1)) / (double)((2 * n + 1) * (2 * n + 3)));
+}
+__host__ __device__ inline double ta_a_minus(int n, int m) {
+  return sqrt((double)((n + m) * (n - m)) / (double)((2 * n + 1) * (2 * n - 1)));
+}
+__host__ __device__ inline double ta_b_plus(int n, int m) {
+  return sqrt((double)((n + m + 2) * (n + m + 1)) / (double)((2 * n + 1) * (2 * n + 3)));
+}
+__host__ __device__ inline double ta_b_minus(int n, int m) {
+  return sqrt((double)((n - m) * (n - m - 1)) / (double)((2 * n + 1) * (2 * n - 1)));
+}
+// entries of one warp's level buffers: [3][NM + 2][2 NM + 3] complex (level n % 3, chain m, degree l); entries with
+// l < m are never written and must be zero on entry (and stay zero)
+__host__ __device__ inline int rot_axial_buf_entries(int NM) { return 3 * (NM + 2) * (2 * NM + 3); }
+
+// Axial A[(n,mu),(l,mu)], B[...] for translation r along z with wavenumber k into Aout / Bout (compact layout of
+// ob_rot.cu: rot_offX(mu) + (n - n0)(NM - n0 + 1) + (l - n0)).  `lane` of `nlanes` cooperating threads; buf as above.
+__host__ __device__ inline void rot_axial_pair(int NM, cplx k, double r, cplx *buf, cplx *Aout, cplx *Bout, int lane,
+                                               int nlanes) {
+  const int LL = 2 * NM, W = LL + 3, CH = NM + 2;
+  // seeds (n = m = 0): sqrt(4 pi) (-1)^l Y_l0(0) h_l = (-1)^l sqrt(2l + 1) h_l(k r); every lane runs the short upward
+  // Hankel recurrence and keeps the orders it owns
+  {
+    cplx h[2 * 13 + 2];
+    sph_hankel1(cscale(k, r), LL + 1, h);
+    for(int l = lane; l <= LL; l += nlanes) {
+      const double f = ((l & 1) ? -1.0 : 1.0) * sqrt(2.0 * l + 1.0);
+      buf[(0 * CH + 0) * W + l] = cscale(h[l], f);
+    }
+  }
+  OB_SYNCWARP();
+  for(int n = 1; n <= NM; ++n) {
+    cplx *cur = buf + (size_t)(n % 3) * CH * W;
+    const cplx *p1 = buf + (size_t)((n - 1) % 3) * CH * W, *p2 = buf + (size_t)((n + 1) % 3) * CH * W; // n-1, n-2
+    const int span = LL - n + 1; // l in [m, LL - n]: index t = m * span + (l - m) over a (n + 1) x span rectangle
+    for(int t = lane; t < (n + 1) * span; t += nlanes) {
+      const int m = t / span, l = m + (t - m * span);
+      if(l > LL - n)
+        continue;
+      cplx v;
+      if(m == n) { // sectorial step (:113-117)
+        const cplx lo = l - 1 >= n - 1 ? p1[(n - 1) * W + (l - 1)] : mk(0, 0);
+        const cplx up = p1[(n - 1) * W + (l + 1)];
+        const double c0 = l - 1 >= n - 1 ? ta_b_plus(l - 1, n - 1) : 0.0, c1 = ta_b_minus(l + 1, n - 1);
+        const double inv = 1.0 / ta_b_plus(n - 1, n - 1);
+        v = mk((lo.x * c0 + up.x * c1) * inv, (lo.y * c0 + up.y * c1) * inv);
+      } else { // general step (:119-124)
+        const cplx lo = l - 1 >= m ? p1[m * W + (l - 1)] : mk(0, 0);
+        const cplx up = p1[m * W + (l + 1)];
+        const cplx o = n - 2 >= m ? p2[m * W + l] : mk(0, 0);
+        const double c0 = l - 1 >= m ? ta_a_plus(l - 1, m) : 0.0, c1 = ta_a_minus(l + 1, m);
+        const double c2 = n - 2 >= m ? ta_a_minus(n - 1, m) : 0.0, inv = 1.0 / ta_a_plus(n - 1, m);
+        v = mk((lo.x * c0 + up.x * c1 - o.x * c2) * inv, (lo.y * c0 + up.y * c1 - o.y * c2) * inv);
+      }
+      cur[m * W + l] = v;
+    }
+    OB_SYNCWARP();
+    // A, B of column degree n for every mu <= n and row degree l (Coupling.cpp:30-51 with k = m = mu)
+    for(int t = lane; t < (n + 1) * NM; t += nlanes) {
+      const int mu = t / NM, l = 1 + (t - mu * NM);
+      const int n0 = rot_n0(mu);
+      if(n < n0 || l < n0)
+        continue;
+      const int mp1 = mu + 1, mm1 = mu > 0 ? mu - 1 : 1; // |mu - 1|: beta(n,-m,l,-m) = beta(n,m,l,m)
+      // beta(n, m', l', m') at this level; zero outside 0 <= m' <= min(n, l')
+      const cplx t0 = (mu <= n && mu <= l) ? cur[mu * W + l] : mk(0, 0);
+      const cplx tp = (mp1 <= n && mp1 <= l) ? cur[mp1 * W + l] : mk(0, 0);
+      const cplx tm = (mm1 <= n && mm1 <= l) ? cur[mm1 * W + l] : mk(0, 0);
+      const double fa = 0.5 / sqrt((double)(l * (l + 1) * n * (n + 1)));
+      const double a0 = 2.0 * mu * mu;
+      const double a1 = sqrt((double)((n - mu) * (n + mu + 1) * (l - mu) * (l + mu + 1)));
+      const double a2 = sqrt((double)((n + mu) * (n - mu + 1) * (l + mu) * (l - mu + 1)));
+      const cplx Av = mk(fa * (a0 * t0.x + a1 * tp.x + a2 * tm.x), fa * (a0 * t0.y + a1 * tp.y + a2 * tm.y));
+      const int lm = l - 1;
+      const cplx u0 = (lm >= 0 && mu <= n && mu <= lm) ? cur[mu * W + lm] : mk(0, 0);
+      const cplx up = (lm >= 0 && mp1 <= n && mp1 <= lm) ? cur[mp1 * W + lm] : mk(0, 0);
+      const cplx um = (lm >= 0 && mm1 <= n && mm1 <= lm) ? cur[mm1 * W + lm] : mk(0, 0);
+      const double fb = -0.5 * sqrt((2.0 * l + 1.0) / ((double)(2 * l - 1) * (double)(l * (l + 1)) * (double)(n * (n + 1))));
+      const double b0 = 2.0 * mu * sqrt((double)((l - mu) * (l + mu)));
+      const double b1 = sqrt((double)((n - mu) * (n + mu + 1) * (l - mu) * (l - mu - 1)));
+      const double b2 = sqrt((double)((n + mu) * (n - mu + 1) * (l + mu) * (l + mu - 1)));
+      const cplx sB = mk(b0 * u0.x + b1 * up.x - b2 * um.x, b0 * u0.y + b1 * up.y - b2 * um.y);
+      const cplx Bv = mk(-fb * sB.y, fb * sB.x); // times i fb (factor = (0, fb))
+      const int w = NM - n0 + 1, e = rot_offX(NM, mu) + (n - n0) * w + (l - n0);
+      Aout[e] = Av;
+      Bout[e] = Bv;
+    }
+    OB_SYNCWARP();
+  }
+}
+
+} // namespace ob

@@ -1,0 +1,17 @@
+// Host harness around optimet_b200/csrc/ob_rot_axial.cuh: runs the per-pair axial-only recursion the device warp
+// runs (same source, lane 0 of 1) on the CPU, for tests/test_rot_axial_host.py.  Test infrastructure.
+#include <cmath>
+using std::fabs;
+using std::fma;
+using std::hypot;
+using std::sqrt;
+#include "../optimet_b200/csrc/ob_rot_axial.cuh"
+#include <vector>
+
+extern "C" int rot_axial_host(int NM, const double k[2], double r, double *A, double *B) {
+  std::vector<ob::cplx> buf((size_t)ob::rot_axial_buf_entries(NM), ob::mk(0, 0));
+  // two pairs through the same buffers: the second run sees the stale level data a warp sees between pairs
+  ob::rot_axial_pair(NM, ob::mk(k[0] * 1.7, k[1] + 0.01 * k[0]), 0.6 * r, buf.data(), (ob::cplx *)A, (ob::cplx *)B, 0, 1);
+  ob::rot_axial_pair(NM, ob::mk(k[0], k[1]), r, buf.data(), (ob::cplx *)A, (ob::cplx *)B, 0, 1);
+  return ob::rot_offX(NM, NM + 1);
+}

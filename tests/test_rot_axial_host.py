@@ -1,0 +1,61 @@
+"""The axial-only assembly of the rotated-axial operator form, checked on the CPU from the very source the device warp
+runs: optimet_b200/csrc/ob_rot_axial.cuh is `__host__ __device__`; tests/rot_axial_host.cpp compiles it with g++ and
+runs one pair with lane 0 of 1 (a warp of one thread executes the items of every level in order, which is a valid
+schedule of the warp-parallel loops).  Compared with the oracle's Coupling at theta = 0 and, when present, with the
+reference's own compiled Coupling.  No GPU needed; the kernel wrapper itself (k_assemble_axial_only) is still pending
+its first GPU run (tests/test_gpu_rot.py, OB_VALIDATE_PENDING=1)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from oracle import reference_build as RB
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CUDA_INC = "/usr/local/cuda/include"
+
+pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")), reason="CUDA headers absent")
+
+
+@pytest.fixture(scope="module")
+def host_lib(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("rot_axial") / "librot_axial_host.so")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-I" + CUDA_INC,
+                           os.path.join(ROOT, "tests", "rot_axial_host.cpp"), "-o", out])
+    return C.CDLL(out)
+
+
+def _flat(n, m):
+    return n * (n + 1) - m - 1
+
+
+def _offX(NM, mu):
+    return sum((NM - max(u, 1) + 1) ** 2 for u in range(mu))
+
+
+@pytest.mark.parametrize("NM,k,d", [(1, 2 * np.pi / 800e-9, 200e-9), (6, 2 * np.pi / 800e-9 * (1.2 + 0.05j), 300e-9),
+                                    (8, 2 * np.pi / 800e-9, 190e-9), (10, 2 * np.pi / 400e-9, 160e-9),
+                                    (13, 2 * np.pi / 400e-9 * (1.0 + 0.02j), 700e-9)])
+def test_device_source_of_the_axial_recursion_on_the_host(host_lib, NM, k, d):
+    X = _offX(NM, NM + 1)
+    A = np.zeros(X, dtype=np.complex128)
+    B = np.zeros(X, dtype=np.complex128)
+    kk = (C.c_double * 2)(complex(k).real, complex(k).imag)
+    got = host_lib.rot_axial_host(int(NM), kk, C.c_double(d), A.ctypes.data_as(C.c_void_p), B.ctypes.data_as(C.c_void_p))
+    assert got == X
+    refs = [O.coupling([d, 0.0, 0.0], k, NM, True)]
+    if RB.have():
+        refs.append(RB.coupling([d, 0.0, 0.0], k, NM, True))  # the reference's own compiled Coupling
+    for Az, Bz in refs:
+        sa, sb = np.abs(Az).max(), np.abs(Bz).max()
+        for mu in range(NM + 1):
+            n0 = max(mu, 1)
+            w = NM - n0 + 1
+            for n in range(n0, NM + 1):
+                for l in range(n0, NM + 1):
+                    e = _offX(NM, mu) + (n - n0) * w + (l - n0)
+                    assert abs(A[e] - Az[_flat(n, mu), _flat(l, mu)]) < 1e-12 * sa, (mu, n, l)
+                    assert abs(B[e] - Bz[_flat(n, mu), _flat(l, mu)]) < 1e-12 * sb, (mu, n, l)
