@@ -139,6 +139,19 @@ def test_oracle_sh_path_equals_the_reference(backend, name):
         cext += (np.conj(loc) * xj).sum().real
         csca += (np.abs(TAB) ** 2 * (np.abs(xj) ** 2)[None, :]).sum()
     assert abs(-cext / k.real ** 2 / cs["ext"] - 1) < 1e-11 and abs(csca / k.real ** 2 / cs["sca"] - 1) < 1e-11
+    # SH scattering (Result.cpp:670-755): the same sum with Coupling(vR_j, 2 k, nMaxS, regular), / (4 eps_b,r mu_b,r)
+    csh = 0.0
+    for j in range(nobj):
+        p = spec.xyz[j]
+        r = np.linalg.norm(p)
+        xj = xsS[2 * n * j:2 * n * (j + 1)]
+        if r == 0:
+            TAB = np.eye(2 * n)
+        else:
+            A, B = RB.coupling([r, np.arccos(p[2] / r), np.arctan2(p[1], p[0])], 2.0 * k, spec.nMax, False)
+            TAB = np.block([[A.T, B.T], [B.T, A.T]])
+        csh += (np.abs(TAB) ** 2 * (np.abs(xj) ** 2)[None, :]).sum()
+    assert abs(csh / (4.0 * (bg[0] * bg[1]).real) / cs["sca_SH"] - 1) < 1e-11
     eta = np.sqrt(bg[1] * U.MU0 / (bg[0] * U.EPS0))
     abs_sh = 0.0
     for j in range(nobj):
