@@ -102,7 +102,7 @@ struct HarmonicState {
   // rotated-axial form (ob_rot.cu): one record per local pair i < j
   DevBuf<unsigned char> rot;
   RotLayout rl;
-  PairPlan rplan;
+  RotPlan rplan;
   int rplan_world = -1, rplan_rank = -1;
   DevBuf<cplx> AB;
   PairPlan pplan;
@@ -280,13 +280,13 @@ static void assemble(ob_ctx *c, int harmonic) {
     H.S.release();
     H.aca.release();
     if(H.rplan.nobj != c->nobj || H.rplan.n != H.n || H.rplan_world != c->world || H.rplan_rank != c->rank) {
-      pair_plan_build(H.rplan, c->nobj, H.n, c->world, c->rank, 4 * c->sm_count); // latency-bound: ~4 CTAs per SM
+      rot_plan_build(H.rplan, c->nobj, H.nMax, c->world, c->rank, c->sm_count);
       H.rplan_world = c->world;
       H.rplan_rank = c->rank;
     }
     H.rl = rot_layout(H.nMax);
     H.rot.alloc(std::max<size_t>(16, (size_t)H.rplan.npairs * H.rl.rec_bytes));
-    launch_assemble_rot(ts, c->xyz.p, H.k, H.rplan.pair_ij, H.rplan.npairs, H.rot.p, H.rl, c->st);
+    launch_assemble_rot(ts, c->xyz.p, H.k, H.rplan.pair_ij, H.rplan.npairs, H.rot.p, H.rl, c->sm_count, c->st);
     c->launches += 2;
     H.mode = 3;
     H.assembled = true;
@@ -950,7 +950,7 @@ void ob_destroy(ob_ctx *ctx) {
     ctx->tabs[i].release();
     matvec_plan_release(ctx->hs[i].plan);
     pair_plan_release(ctx->hs[i].pplan);
-    pair_plan_release(ctx->hs[i].rplan);
+    rot_plan_release(ctx->hs[i].rplan);
     ctx->hs[i].aca.release();
   }
   ctx->lu.release();
@@ -1633,10 +1633,20 @@ int ob_set_option(ob_ctx *ctx, const char *name, double value) {
   } else if(n == "assemble_minb") { // tuning: resident CTAs per SM k_assemble_pairs is compiled for (0 auto, 2, 3)
     need(value == 0 || value == 2 || value == 3, "assemble_minb must be 0, 2 or 3");
     assemble_pairs_tuning((int)value);
-  } else if(n == "rot_assembly") { // 0 = validated vtac_block path, 1 = axial-only recursion (not yet validated on a GPU)
+  } else if(n == "rot_assembly") { // 1 = axial-only recursion (default), 0 = vtac_block at theta = 0 (cross-check path)
     need(value == 0 || value == 1, "rot_assembly must be 0 or 1");
-    rot_tuning((int)value);
+    rot_tuning((int)value, -1, -1);
     ctx->hs[0].assembled = ctx->hs[1].assembled = false;
+  } else if(n == "rot_rows" || n == "rot_ctas_per_sm") { // tuning of the rotated-axial plan (0 = auto); forces a new plan
+    need(value >= 0 && value <= 64, "rot_rows / rot_ctas_per_sm out of range");
+    if(n == "rot_rows")
+      rot_tuning(-1, (int)value, -1);
+    else
+      rot_tuning(-1, -1, (int)value);
+    for(int h = 0; h < 2; ++h) {
+      ctx->hs[h].rplan_world = -1;
+      ctx->hs[h].assembled = false;
+    }
   } else if(n == "eps_aca") {
     need(value > 0, "eps_aca must be positive");
     ctx->eps_aca = value;

@@ -104,16 +104,30 @@ void assemble_pairs_tuning(int minb); // 0 auto, 2 or 3 resident CTAs per SM
 void launch_assemble_pairs(VtacTableSet const &ts, const double *xyz, cplx k, const int2 *pair_ij, long npairs,
                            cplx *AB, cudaStream_t st);
 
-// ---- ob_rot.cu (rotated-axial operator: per pair phases, axial A/B, Wigner small-d; see the file header) ----
+// ---- ob_rot.cu (rotated-axial operator: per pair phases, axial A+-B, flip-basis Wigner small-d; see the file header) ----
+#define OB_ROT_MAX_THREADS 224 // ceil32(nMax (nMax + 2)) at OB_MAX_NMAX
 struct RotLayout {
-  int NM = 0, n = 0, X = 0, Dn = 0;          // nMax, harmonics per polarisation, axial entries, small-d reals
-  size_t offA = 0, offB = 0, offD = 0, rec_bytes = 0; // byte offsets inside one pair record (phases at 0)
+  int NM = 0, n = 0, X = 0, nDs = 0, nDa = 0, LF = 0, nh = 0; // nMax, harmonics, axial entries, small-d reals, F / channel lengths
+  size_t offCp = 0, offCm = 0, offDs = 0, offDa = 0, rec_bytes = 0; // byte offsets inside one pair record (phases at 0)
+};
+struct RotPlan {
+  int nobj = 0, n = 0, I = 0, grid = 0, nseg = 0, nblocks = 0, threads = 0, ctas_per_sm = 0;
+  long npairs = 0, nstrips = 0, strip0 = 0; // local pairs / strips, global index of the first local strip
+  size_t smem = 0;
+  int2 *pair_ij = nullptr; // (i, j) of every local record (assembly)
+  int4 *pinfo = nullptr;   // (i, j, local strip, flags) of every local record (apply)
+  int *cta_pair = nullptr, *cta_seg = nullptr, *blk_seg = nullptr;
+  long *blk_strip = nullptr;
+  cplx *rowpart = nullptr, *colpart = nullptr, *acc = nullptr;
 };
 RotLayout rot_layout(int NM);
-void rot_tuning(int assembly); // 0 = vtac_block-based axial assembly (default), 1 = axial-only recursion
+void rot_plan_build(RotPlan &p, int nobj, int NM, int world, int rank, int sm_count);
+void rot_plan_release(RotPlan &p);
+// -1 keeps a setting; assembly: 1 = axial-only recursion (default), 0 = vtac_block-based; rows per block; CTAs per SM
+void rot_tuning(int assembly, int rows, int ctas_per_sm);
 void launch_assemble_rot(VtacTableSet const &ts, const double *xyz, cplx k, const int2 *pair_ij, long npairs,
-                         unsigned char *recs, RotLayout const &L, cudaStream_t st);
-void launch_matvec_rot(PairPlan const &p, RotLayout const &L, const unsigned char *recs, const cplx *x, const cplx *Tdiag,
+                         unsigned char *recs, RotLayout const &L, int sm_count, cudaStream_t st);
+void launch_matvec_rot(RotPlan const &p, RotLayout const &L, const unsigned char *recs, const cplx *x, const cplx *Tdiag,
                        cplx *acc_or_y, int finalize, cudaStream_t st, cudaEvent_t e0 = nullptr, cudaEvent_t e1 = nullptr);
 
 // ---- ob_aca.cu (ACA-compressed operator: U V^T-style low-rank far blocks, dense near blocks) ----

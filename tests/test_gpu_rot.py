@@ -24,6 +24,7 @@ CLUSTERS = {
     "random12_n6": lambda: U.random_cluster(12, 6, seed=18),
     "random3_n13": lambda: U.random_cluster(3, 13, seed=16),
     "random23_n8": lambda: U.random_cluster(23, 8, seed=31),
+    "random9_n10": lambda: U.random_cluster(9, 10, seed=77),          # the headline order (C5), several row blocks
     "pair_n1": lambda: U.random_cluster(2, 1, seed=3),
     "single_n4": lambda: U.random_cluster(1, 4, seed=5),
     "two_si_z_axis": lambda: U.two_si(nMax=6),                       # theta = 0 / pi
@@ -81,12 +82,10 @@ def test_rot_operator_iteration_counts(rot_ctx, flavour):
     assert abs(it - ito) <= 1 and U.relerr(x, xo) < 1e-7
 
 
-@pytest.mark.skipif(__import__("os").environ.get("OB_VALIDATE_PENDING") != "1",
-                    reason="k_assemble_axial_only was written after the round-1 GPU budget was spent: run with "
-                           "OB_VALIDATE_PENDING=1 to validate it, then make it the default (DESIGN.md section 8)")
 @pytest.mark.parametrize("name", ["random12_n6", "random3_n13", "random23_n8", "two_si_z_axis", "lossy_bg"])
-def test_rot_axial_only_assembly_pending(rot_ctx, name):
-    """The O(nMax^3) axial-only assembly ("rot_assembly" = 1) must produce the operator the validated path produces."""
+def test_rot_assembly_paths_agree(rot_ctx, name):
+    """The default O(nMax^3) axial-only assembly ("rot_assembly" = 1, k_assemble_axial_only) and the cross-check path
+    through the shared vtac_block code ("rot_assembly" = 0, k_assemble_axial) must both give the oracle's operator."""
     spec = CLUSTERS[name]()
     orc = U.oracle_case(spec)
     U.configure_ctx(rot_ctx, spec, orc)
@@ -94,10 +93,34 @@ def test_rot_axial_only_assembly_pending(rot_ctx, name):
     for harmonic in (1, 2):
         So = orc.matrix(harmonic)
         x = rng.standard_normal(So.shape[1]) + 1j * rng.standard_normal(So.shape[1])
-        rot_ctx.set_option("rot_assembly", 1)
-        try:
+        ys = []
+        for path in (0, 1):
+            rot_ctx.set_option("rot_assembly", path)
+            try:
+                rot_ctx.assemble(harmonic)
+                ys.append(rot_ctx.matvec(harmonic, x))
+            finally:
+                rot_ctx.set_option("rot_assembly", 1)
+        yo = O.matvec(So, x)
+        assert U.relerr(ys[0], yo) < 1e-12 and U.relerr(ys[1], yo) < 1e-12
+
+
+@pytest.mark.parametrize("rows,ctas", [(1, 0), (2, 1), (3, 0), (7, 2)])
+def test_rot_plan_geometry(rot_ctx, rows, ctas):
+    """Rows per block and CTAs per SM only change the order of the fixed-order sums: same operator for every plan
+    (blocks of 1, 2, 3 and 7 rows: ragged last blocks, strips shorter than a block, one CTA per SM)."""
+    spec = U.random_cluster(23, 5, seed=12)
+    orc = U.oracle_case(spec)
+    U.configure_ctx(rot_ctx, spec, orc)
+    rng = np.random.RandomState(5)
+    rot_ctx.set_option("rot_rows", rows)
+    rot_ctx.set_option("rot_ctas_per_sm", ctas)
+    try:
+        for harmonic in (1, 2):
+            So = orc.matrix(harmonic)
+            x = rng.standard_normal(So.shape[1]) + 1j * rng.standard_normal(So.shape[1])
             rot_ctx.assemble(harmonic)
-            y1 = rot_ctx.matvec(harmonic, x)
-        finally:
-            rot_ctx.set_option("rot_assembly", 0)
-        assert U.relerr(y1, O.matvec(So, x)) < 1e-12
+            assert U.relerr(rot_ctx.matvec(harmonic, x), O.matvec(So, x)) < 1e-12
+    finally:
+        rot_ctx.set_option("rot_rows", 0)
+        rot_ctx.set_option("rot_ctas_per_sm", 0)

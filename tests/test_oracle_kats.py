@@ -347,6 +347,27 @@ def test_rotation_axial_factorisation():
         assert U.relerr(Wr, np.stack([Ar.T @ X[0] + Br.T @ X[1], Br.T @ X[0] + Ar.T @ X[1]])) < 1e-13
 
 
+@pytest.mark.parametrize("NM", [1, 2, 5, 10])
+def test_rotation_axial_factorisation_flip_basis(NM):
+    """Record layout v2 of csrc/ob_rot.cu (tests/rot2_model.py): the flip-symmetric / antisymmetric split of the small-d
+    matrices and the (A + B), (A - B) channels reproduce [A^T B^T; B^T A^T](+-R) of the oracle's full blocks."""
+    from tests import rot2_model as R2
+    k = 2 * np.pi / 800e-9 * (1.2 + 0.05j)
+    n = NM * (NM + 2)
+    rng = np.random.RandomState(1)
+    for (d, the, phi) in ((260e-9, 1.1, 0.7), (190e-9, 2.7, -2.0), (400e-9, 0.0, 0.0), (210e-9, np.pi, 0.0),
+                          (330e-9, np.pi / 2, np.pi)):
+        A, B = O.coupling([d, the, phi], k, NM, True)
+        vec = -d * np.array([np.sin(the) * np.cos(phi), np.sin(the) * np.sin(phi), np.cos(the)])
+        Ar, Br = O.coupling([d, np.arccos(vec[2] / d), np.arctan2(vec[1], vec[0])], k, NM, True)
+        rec = R2.build_pair(NM, d, the, phi, k)
+        X = rng.standard_normal((2, n)) + 1j * rng.standard_normal((2, n))
+        W = R2.apply_pair(NM, rec, X, False)
+        assert U.relerr(W, np.stack([A.T @ X[0] + B.T @ X[1], B.T @ X[0] + A.T @ X[1]])) < 1e-13
+        Wr = R2.apply_pair(NM, rec, X, True)
+        assert U.relerr(Wr, np.stack([Ar.T @ X[0] + Br.T @ X[1], Br.T @ X[0] + Ar.T @ X[1]])) < 1e-13
+
+
 def _ms(NM):
     return [m for nn in range(1, NM + 1) for m in range(nn, -nn - 1, -1)]
 

@@ -2,8 +2,8 @@
 runs: optimet_b200/csrc/ob_rot_axial.cuh is `__host__ __device__`; tests/rot_axial_host.cpp compiles it with g++ and
 runs one pair with lane 0 of 1 (a warp of one thread executes the items of every level in order, which is a valid
 schedule of the warp-parallel loops).  Compared with the oracle's Coupling at theta = 0 and, when present, with the
-reference's own compiled Coupling.  No GPU needed; the kernel wrapper itself (k_assemble_axial_only) is still pending
-its first GPU run (tests/test_gpu_rot.py, OB_VALIDATE_PENDING=1)."""
+reference's own compiled Coupling.  No GPU needed; the kernel wrapper itself (k_assemble_axial_only) is checked on the
+GPU by tests/test_gpu_rot.py."""
 import ctypes as C
 import os
 import subprocess
@@ -59,3 +59,21 @@ def test_device_source_of_the_axial_recursion_on_the_host(host_lib, NM, k, d):
                     e = _offX(NM, mu) + (n - n0) * w + (l - n0)
                     assert abs(A[e] - Az[_flat(n, mu), _flat(l, mu)]) < 1e-12 * sa, (mu, n, l)
                     assert abs(B[e] - Bz[_flat(n, mu), _flat(l, mu)]) < 1e-12 * sb, (mu, n, l)
+
+
+@pytest.mark.parametrize("NM", [1, 4, 10])
+def test_combined_output_of_the_axial_recursion(host_lib, NM):
+    """combine = 1 (what k_assemble_axial_only passes): A + B for every mu, A - B for mu >= 1 behind the mu = 0 block."""
+    k, d = 2 * np.pi / 500e-9 * (1.1 + 0.03j), 230e-9
+    X = _offX(NM, NM + 1)
+    A = np.zeros(X, dtype=np.complex128)
+    B = np.zeros(X, dtype=np.complex128)
+    Cp = np.zeros(X, dtype=np.complex128)
+    Cm = np.zeros(X - NM * NM, dtype=np.complex128)
+    kk = (C.c_double * 2)(complex(k).real, complex(k).imag)
+    host_lib.rot_axial_host(int(NM), kk, C.c_double(d), A.ctypes.data_as(C.c_void_p), B.ctypes.data_as(C.c_void_p))
+    host_lib.rot_axial_host_combined(int(NM), kk, C.c_double(d), Cp.ctypes.data_as(C.c_void_p),
+                                     Cm.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(Cp, A + B)
+    assert np.array_equal(Cm, (A - B)[NM * NM:])
+    assert not np.abs(B[:NM * NM]).any()      # mu = 0: B = 0, so Cm = Cp there and is not stored
