@@ -48,7 +48,7 @@ def workload(name):
                     xml=xmlgen.cluster_xml(xyz, 50.0, 8, 800.0, belos=belos), nobj=200, nMax=8)
     if name == "c5":
         xyz = xmlgen.random_sites(1000, 2200.0, 150.0, 20261017)
-        return dict(name="C5: 1000 Si spheres r=50nm, random in (2200nm)^3 (seed 20261017), nMax=10, 800nm, FH+SH, dense",
+        return dict(name="C5: 1000 Si spheres r=50nm, random in (2200nm)^3 (std::mt19937_64 seed 20261017, min distance 150nm), nMax=10, 800nm, FH+SH, dense",
                     xml=xmlgen.cluster_xml(xyz, 50.0, 10, 800.0, belos=belos), nobj=1000, nMax=10)
     if name == "small":
         xyz = xmlgen.cube_sites(3, 27, 190.0)

@@ -15,31 +15,40 @@
 //     D[a',a] = (-1)^(a'-a) D[a,a'] (one stored array serves D^T and D);
 //   * in that basis A keeps the class (s/a) and B swaps it, so the channels (TE_s +- TM_a), (TM_s +- TE_a) diagonalise
 //     [A B; B A]: q+ = (A^T + B^T) p+, q- = (A^T - B^T) p-.
-// Record per unordered pair (i < j), 16-byte aligned sections:
+// Record per unordered pair (i < j):
 //   ph[m + NM] = exp(i m phi)                                                      (2 NM + 1 complex)
-//   Cp[offX(a) + (n - n0) w + (l - n0)] = A[(n,a),(l,a)] + B[(n,a),(l,a)],  a = 0..NM, n0 = max(a,1), w = NM - n0 + 1
-//   Cm[same - NM^2]                     = A - B,                             a = 1..NM   (a = 0: B = 0)
+//   Cp = A + B as two planes of doubles [Re | Im], entry offX(a) + (n - n0) w + (l - n0) holds (n,a),(l,a),
+//        a = 0..NM, n0 = max(a,1), w = NM - n0 + 1;   Cm = A - B likewise for a = 1..NM (a = 0: B = 0)
 //   Ds[offDs(n) + a' (n + 1) + a],  Da[offDa(n) + (a' - 1) n + (a - 1)]                 (reals)
 // 21.4 KB at nMax 10 (v1 30 KB, pair form 460.8 KB), 11.7 KB at nMax 8.
 //
 // Work decomposition: rows are grouped in blocks of I; a strip (b, j) holds the pairs (i, j), i in block b, i < j.
 // Records are stored strip by strip (block-major); ranks and CTAs own contiguous strip ranges of equal pair counts.
-// Inside a CTA the row-side sums of the I rows of the current block live in shared memory and the column-side sums
-// of the current strip in registers: one column partial per STRIP (not per pair) and one row partial per block
-// segment reach HBM, added in a fixed order by k_rot_reduce (deterministic, no atomics).
+// Inside a CTA the row-side sums of the I rows of the current block and the column-side sums of the current strip
+// live in shared memory: one column partial per STRIP (not per pair) and one row partial per block segment reach HBM,
+// added in a fixed order by k_rot_reduce (deterministic, no atomics).
 //
-// Apply, per pair and for both directions at once (four vectors: x_j TE/TM, parity-signed x_i TE/TM), CTA of
-// ceil32(n) threads, item = (degree, class, a) with the (s_a, a_a) items of one (n, a) in adjacent lanes:
-//   P0  t = exp(i m phi) x -> flip basis                 (x prefetched into registers during the previous pair)
-//   P1  u = D^T t (thread owns one output, reads its own column of D, broadcast reads of t), channel sums by shuffle
-//   P2  q = C p per (a, n) for the eight channels, back to the class vectors
-//   P3  w = D v (same array, same access pattern as P1);  P4  flip basis -> m (shuffle), conjugate phase, accumulate
+// Apply, per pair and for both directions at once: four complex vectors (x_j TE/TM, parity-signed x_i TE/TM) = EIGHT
+// REAL COLUMNS, which is exactly the N of the FP64 tensor-core instruction DMMA.8x8x4 (mma.sync m8n8k4 f64; measured
+// 37.1 TFLOP/s on B200, the DFMA pipe gives 34.0).  The first version of this kernel used one thread per output and
+// DFMA; ncu showed it bound by shared-memory wavefronts (4930 per pair, 89 % of the pipe: a 128-bit shared load costs
+// four wavefronts even when every lane reads the same address, so the 9 bytes per FMA of the thread-per-output
+// scheme could not be fed).  DMMA shares the operands across the warp in the tensor core: 2 bytes per FMA.
+//   P0  t = exp(i m phi) x -> flip basis (thread per (n, a); x prefetched into registers during the previous pair)
+//   P1  u = D^T t: per degree n and class, M = outputs a (tiles of 8), K = a' (steps of 4), N = 8 real columns;
+//       a warp runs the s and a class of one (n, tile): both results of (n, a) meet in one lane and the channel sums
+//       p+- = TE_s +- TM_a, r+- = TM_s +- TE_a need one shuffle
+//   P2  q = C p per order a: complex matrix as two real DMMAs (Re C, Im C) on the same B fragment, A + B and A - B
+//       channels in the same lanes -> class vectors v without any exchange
+//   P3  w = D v (same arrays and access pattern as P1);  P4  flip basis -> m, conjugate phase, parity signs,
+//       accumulate (owner lanes add into the shared-memory row / column sums and flush them at strip / segment ends)
 // The record of the next pair is fetched into the other shared-memory slot by one cp.async.bulk (TMA bulk copy,
-// mbarrier complete_tx) issued right after P0.
+// mbarrier complete_tx) issued right after P0.  Three barriers per pair, three CTAs per SM at nMax 10.
 #include "ob_internal.h"
 #include "ob_vtac.cuh"
 #include "ob_rot_axial.cuh"
 #include <algorithm>
+#include <cstring>
 
 namespace ob {
 
@@ -63,8 +72,8 @@ RotLayout rot_layout(int NM) {
   L.nDa = rot_offDa(NM + 1);
   L.LF = NM * (NM + 3);
   L.nh = L.LF / 2;
-  L.offCp = (size_t)(2 * NM + 1) * sizeof(cplx);
-  L.offCm = L.offCp + (size_t)L.X * sizeof(cplx);
+  L.offCp = (size_t)(2 * NM + 1) * sizeof(cplx);                       // Re plane, then Im plane (X doubles each)
+  L.offCm = L.offCp + (size_t)L.X * sizeof(cplx);                      // Re plane, then Im plane (X - NM^2 doubles each)
   L.offDs = L.offCm + (size_t)(L.X - NM * NM) * sizeof(cplx);
   L.offDa = (L.offDs + (size_t)L.nDs * sizeof(double) + 15) & ~(size_t)15;
   L.rec_bytes = (L.offDa + (size_t)L.nDa * sizeof(double) + 15) & ~(size_t)15;
@@ -75,8 +84,8 @@ RotLayout rot_layout(int NM) {
 // assembly 1 (cross-check path, "rot_assembly" = 0): axial A, B out of the shared VTAC block code at theta = phi = 0
 // ---------------------------------------------------------------------------------------------
 struct EmitAxial {
-  cplx *Cp, *Cm;
-  int NM;
+  double *Cp, *Cm; // [Re | Im] planes
+  int NM, X;
   // p = flat(n, mu) (first index of Coupling.diagonal), r = flat(l, k): keep mu == k >= 0
   __device__ __forceinline__ void item(int p, int r, cplx a, cplx b) {
     int n, mu, l, k;
@@ -86,9 +95,12 @@ struct EmitAxial {
       return;
     const int n0 = rot_n0(mu), w = NM - n0 + 1;
     const int e = rot_offX(NM, mu) + (n - n0) * w + (l - n0);
-    Cp[e] = cadd(a, b);
-    if(mu >= 1)
-      Cm[e - NM * NM] = csub(a, b);
+    Cp[e] = a.x + b.x;
+    Cp[X + e] = a.y + b.y;
+    if(mu >= 1) {
+      Cm[e - NM * NM] = a.x - b.x;
+      Cm[X - NM * NM + e - NM * NM] = a.y - b.y;
+    }
   }
 };
 __global__ void __launch_bounds__(OB_VTAC_THREADS, 2)
@@ -101,9 +113,10 @@ k_assemble_axial(VtacTables tb, const double *__restrict__ xyz, cplx k, const in
   const double r = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
   unsigned char *rec = recs + (size_t)blockIdx.x * L.rec_bytes;
   EmitAxial em;
-  em.Cp = (cplx *)(rec + L.offCp);
-  em.Cm = (cplx *)(rec + L.offCm);
+  em.Cp = (double *)(rec + L.offCp);
+  em.Cm = (double *)(rec + L.offCm);
   em.NM = L.NM;
+  em.X = L.X;
   vtac_block(tb, smem_raw, r, 0.0, 0.0, k, false, em);
 }
 
@@ -133,7 +146,7 @@ k_assemble_axial_only(const double *__restrict__ xyz, cplx k, const int2 *__rest
                  z = xyz[3 * ij.x + 2] - xyz[3 * ij.y + 2];
     const double r = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
     unsigned char *rec = recs + (size_t)q * L.rec_bytes;
-    rot_axial_pair(L.NM, k, r, buf, (cplx *)(rec + L.offCp), (cplx *)(rec + L.offCm), lane, 32, 1);
+    rot_axial_pair(L.NM, k, r, buf, (cplx *)(rec + L.offCp), (cplx *)(rec + L.offCm), lane, 32, 2);
     __syncwarp();
   }
 }
@@ -279,6 +292,15 @@ k_rot_tables(const double *__restrict__ xyz, const int2 *__restrict__ pair_ij, l
 // ---------------------------------------------------------------------------------------------
 // apply
 // ---------------------------------------------------------------------------------------------
+#define ROT_WARPS 4
+#define ROT_THREADS (32 * ROT_WARPS)
+#define ROT_MAX_UNITS 32
+// static work lists of the warps: d-phase units (degree n, first row m0 of an 8-row tile; the s and the a class together)
+// and P2 units (order a, first row of an 8-row tile; the A + B and the A - B channels together), balanced on the host
+struct RotUnits {
+  unsigned char dn[ROT_MAX_UNITS], dm[ROT_MAX_UNITS], ca[ROT_MAX_UNITS], cm[ROT_MAX_UNITS];
+  unsigned char dbeg[ROT_WARPS + 1], cbeg[ROT_WARPS + 1];
+};
 struct RotArgs {
   const unsigned char *recs;
   const cplx *x;
@@ -288,6 +310,7 @@ struct RotArgs {
   cplx *rowpart, *colpart;
   RotLayout L;
   int I;
+  RotUnits u;
 };
 
 __device__ __forceinline__ uint32_t r_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -314,44 +337,64 @@ __device__ __forceinline__ void r_bulk_g2s(void *dst, const void *src, uint32_t 
                ::"r"(r_smem_u32(dst)), "l"(src), "r"(bytes), "r"(r_smem_u32(bar)), "l"(pol)
                : "memory");
 }
-__device__ __forceinline__ cplx shfl_xor1(cplx v) {
-  return mk(__shfl_xor_sync(0xffffffffu, v.x, 1), __shfl_xor_sync(0xffffffffu, v.y, 1));
+// D (8x8) += A (8x4, row) B (4x8, col), FP64 tensor core.  Fragments: A[lane >> 2][lane & 3], B[lane & 3][lane >> 2],
+// D[lane >> 2][2 (lane & 3) + {0, 1}]
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
-// dynamic shared memory: record[2] | bufA[4 LF] | bufB[4 LF] | rowacc[I][2n] | mbarrier[2]
+// Shared-memory vector buffers (doubles).  Class vectors T / V: [direction][F index][TE re, TE im, TM re, TM im], the
+// two directions ("planes") PS doubles apart; channels P: [A+B | A-B][direction][(a, l)][p re, p im, r re, r im].  A B
+// fragment (row = lane & 3 consecutive F / channel indices, column = lane >> 2) reads 128 contiguous bytes per
+// half-warp: plane = lane >> 4, position inside the 32-byte row = (lane >> 2) & 3.  Rows past the valid K range are
+// read (their A entries are zero) and must stay finite: the planes carry eight spare rows and start zeroed.
+__host__ __device__ inline int rot_plane_doubles(int LF) { return 4 * (LF + 8); }
+// dynamic shared memory: record[2] | bufX[2 planes] | bufY[2 planes] | rowacc[I][2n] | colacc[2n] | mbarrier[2]
 static size_t rot_smem_bytes(RotLayout const &L, int I) {
-  return 2 * L.rec_bytes + (size_t)(8 * L.LF + I * 2 * L.n) * sizeof(cplx) + 2 * sizeof(uint64_t);
+  return 2 * L.rec_bytes + (size_t)4 * rot_plane_doubles(L.LF) * sizeof(double) + (size_t)(I + 1) * 2 * L.n * sizeof(cplx) +
+         2 * sizeof(uint64_t);
 }
-static int rot_block_threads(RotLayout const &L) { return (L.n + 31) & ~31; }
 
-// d-phase inner product (P1 and P3): acc[vv] = sum_t d[t stride] v[4 t + vv], vv = direction * 2 + polarisation
-__device__ __forceinline__ void rot_dphase(const double *__restrict__ dp, int stride, const cplx *__restrict__ vp, int cnt,
-                                           cplx acc[4]) {
-  acc[0] = acc[1] = acc[2] = acc[3] = mk(0, 0);
+// d-phase unit (P1 and P3): rows a = m0 .. m0 + 7 of degree n, both classes.
+//   accS[(a, col)] = sum_{a' = 0..n} Ds[a' (n + 1) + a] v_s[a'][col],  accA[(a, col)] = sum_{a' = 1..n} Da[(a' - 1) n + (a - 1)] v_a[a'][col]
+// vb = buffer + plane / in-row offset of this lane (see above)
+__device__ __forceinline__ void rot_dunit(const double *__restrict__ Ds, const double *__restrict__ Da,
+                                          const double *__restrict__ vb, int n, int m0, int lane, double (&accS)[2],
+                                          double (&accA)[2]) {
+  const int r = lane >> 2, c = lane & 3, a = m0 + r, n1 = n + 1;
+  accS[0] = accS[1] = accA[0] = accA[1] = 0.0;
+  const double *As = Ds + rot_offDs(n) + a;
+  const double *Bs = vb + 4 * (rot_offF(n) + c);
+  const bool rowS = a <= n;
 #pragma unroll 2
-  for(int t = 0; t < cnt; ++t) {
-    const double d = dp[t * stride];
-    const cplx v0 = vp[4 * t], v1 = vp[4 * t + 1], v2 = vp[4 * t + 2], v3 = vp[4 * t + 3];
-    acc[0].x = fma(d, v0.x, acc[0].x);
-    acc[0].y = fma(d, v0.y, acc[0].y);
-    acc[1].x = fma(d, v1.x, acc[1].x);
-    acc[1].y = fma(d, v1.y, acc[1].y);
-    acc[2].x = fma(d, v2.x, acc[2].x);
-    acc[2].y = fma(d, v2.y, acc[2].y);
-    acc[3].x = fma(d, v3.x, acc[3].x);
-    acc[3].y = fma(d, v3.y, acc[3].y);
+  for(int k0 = 0; k0 <= n; k0 += 4) {
+    const int ap = k0 + c;
+    const double av = (rowS && ap <= n) ? As[ap * n1] : 0.0;
+    dmma(accS, av, Bs[4 * k0]);
+  }
+  const double *Aa = Da + rot_offDa(n) + (a - 1);
+  const double *Ba = vb + 4 * (rot_offF(n) + n + 2 + c);
+  const bool rowA = a >= 1 && a <= n;
+#pragma unroll 2
+  for(int k0 = 0; k0 < n; k0 += 4) {
+    const int ap = 1 + k0 + c;
+    const double av = (rowA && ap <= n) ? Aa[(ap - 1) * n] : 0.0;
+    dmma(accA, av, Ba[4 * k0]);
   }
 }
 
-__global__ void __launch_bounds__(OB_ROT_MAX_THREADS) k_matvec_rot(RotArgs a) {
+__global__ void __launch_bounds__(ROT_THREADS) k_matvec_rot(const __grid_constant__ RotArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const RotLayout L = a.L;
-  const int NM = L.NM, nH = L.n, n2 = 2 * nH, I = a.I;
-  cplx *bufA = (cplx *)(smem + 2 * L.rec_bytes);
-  cplx *bufB = bufA + 4 * L.LF;
-  cplx *rowacc = bufB + 4 * L.LF;
-  uint64_t *full = (uint64_t *)(rowacc + (size_t)I * n2);
-  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int NM = L.NM, nH = L.n, n2 = 2 * nH, I = a.I, NM2 = NM * NM;
+  const int PS = rot_plane_doubles(L.LF); // plane stride of the class-vector buffers (doubles)
+  const int PP = PS / 2, SS = PS;         // channel buffers: plane stride, stride between the A+B and the A-B halves
+  double *bufX = (double *)(smem + 2 * L.rec_bytes);
+  double *bufY = bufX + 2 * PS;
+  cplx *rowacc = (cplx *)(bufY + 2 * PS);
+  cplx *colacc = rowacc + (size_t)I * n2;
+  uint64_t *full = (uint64_t *)(colacc + n2);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int qbeg = a.cta_pair[blockIdx.x], qend = a.cta_pair[blockIdx.x + 1];
   if(qbeg >= qend)
     return;
@@ -360,52 +403,31 @@ __global__ void __launch_bounds__(OB_ROT_MAX_THREADS) k_matvec_rot(RotArgs a) {
     r_mbar_init(&full[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // ---- the thread's item: paired lanes (2k, 2k+1) = (s_a, a_a) of (n, a >= 1); then the s_0 items; then idle lanes ----
-  const int npaired = NM * (NM + 1);
-  int dn = 1, da = 0, cls = 0, kind = 2; // kind 0: paired, 1: s_0, 2: idle
-  if(tid < npaired) {
-    const int k = tid >> 1;
-    dn = (int)((1.0 + sqrt(1.0 + 8.0 * k)) * 0.5);
-    while(dn * (dn - 1) / 2 > k)
-      --dn;
-    while(dn * (dn + 1) / 2 <= k)
-      ++dn;
-    da = k - dn * (dn - 1) / 2 + 1;
-    cls = tid & 1;
-    kind = 0;
-  } else if(tid < nH) {
-    dn = tid - npaired + 1;
-    kind = 1;
+  for(int e = tid; e < 4 * PS; e += ROT_THREADS)
+    bufX[e] = 0.0; // bufX and bufY
+  for(int e = tid; e < (I + 1) * n2; e += ROT_THREADS)
+    rowacc[e] = mk(0, 0); // rowacc and colacc
+  // ---- P0 item of this thread: (pn, pa), pa = 0..pn, sorted by degree ----
+  const bool p0live = tid < L.nh;
+  int pn = 1, pa = 0;
+  if(p0live) {
+    pn = (int)((-1.0 + sqrt(9.0 + 8.0 * tid)) * 0.5);
+    while((pn - 1) * (pn + 2) / 2 > tid)
+      --pn;
+    while(pn * (pn + 3) / 2 <= tid)
+      ++pn;
+    pa = tid - (pn - 1) * (pn + 2) / 2;
   }
-  const int offFn = rot_offF(dn);
-  const int cnt = kind == 2 ? 0 : (cls ? dn : dn + 1), stride = cls ? dn : dn + 1;
-  const size_t dofs = cls ? L.offDa + (size_t)(rot_offDa(dn) + (da - 1)) * sizeof(double)
-                          : L.offDs + (size_t)(rot_offDs(dn) + da) * sizeof(double);
-  const int vbase = cls ? offFn + dn + 2 : offFn; // first F index the d-loops read
-  const int fpos = flat_index(dn, da), fneg = flat_index(dn, -da);
-  const double sa = (da & 1) ? -1.0 : 1.0, sn = (dn & 1) ? -1.0 : 1.0;
-  const int pidx = rot_offP(NM, da) + (dn - rot_n0(da)); // channel index of (a, l = dn)
-  // ---- the thread's P2 item (a2, d2), sorted by a then n ----
-  int a2 = 0, d2 = 1;
-  const bool p2live = tid < L.nh;
-  if(p2live) {
-    int rem = tid;
-    for(a2 = 0; a2 <= NM; ++a2) {
-      const int w = NM - rot_n0(a2) + 1;
-      if(rem < w)
-        break;
-      rem -= w;
-    }
-    d2 = rot_n0(a2) + rem;
-  }
-  const int n02 = rot_n0(a2), w2 = NM - n02 + 1;
-  const int cofs = rot_offX(NM, a2) + (d2 - n02); // + (l - n0) w2 per step
-  const int pbase2 = rot_offP(NM, a2);
-  const double sa2 = (a2 & 1) ? -0.5 : 0.5;
-  const int fs2 = rot_offF(d2) + a2, fa2 = rot_offF(d2) + d2 + 1 + a2;
+  const int fpos = flat_index(pn, pa), fneg = flat_index(pn, -pa);
+  const double psa = (pa & 1) ? -1.0 : 1.0, psn = (pn & 1) ? -1.0 : 1.0;
+  const int pfs = rot_offF(pn) + pa, pfa = pfs + pn + 1;
+  // ---- fragment geometry of this lane ----
+  const int fr = lane >> 2, fc = lane & 3;
+  const int bofs = (lane >> 4) * PS + ((lane >> 2) & 3);  // B fragment: plane and position in the 32-byte row (class vectors)
+  const int bofsP = (lane >> 4) * PP + ((lane >> 2) & 3); // the same for the channel buffers
+  const int cdir = fc >> 1, cpol = fc & 1;                // D fragment column pair = complex vector fc = direction * 2 + pol
+  const int d0 = a.u.dbeg[warp], d1 = a.u.dbeg[warp + 1], c0 = a.u.cbeg[warp], c1 = a.u.cbeg[warp + 1];
 
-  for(int e = tid; e < I * n2; e += nthr)
-    rowacc[e] = mk(0, 0);
   uint64_t pol;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
   __syncthreads();
@@ -413,59 +435,50 @@ __global__ void __launch_bounds__(OB_ROT_MAX_THREADS) k_matvec_rot(RotArgs a) {
     r_mbar_expect_tx(&full[0], (uint32_t)L.rec_bytes);
     r_bulk_g2s(smem, a.recs + (size_t)qbeg * L.rec_bytes, (uint32_t)L.rec_bytes, &full[0], pol);
   }
-  // x of the pair about to be processed: paired s-lanes hold x_j (direction 0), a-lanes x_i (direction 1), at
-  // m = +a (xr[0..1] = TE, TM) and m = -a (xr[2..3]); s_0 lanes hold x_j(0) TE/TM and x_i(0) TE/TM
-  cplx xr[4];
-  xr[0] = xr[1] = xr[2] = xr[3] = mk(0, 0);
+  // x of the pair about to be processed, at m = +pa (TE, TM) and m = -pa (TE, TM): xj = x_j (direction 0), xi = x_i
+  cplx xj[4], xi[4];
   int4 pi = a.pinfo[qbeg];
-  auto load_x = [&](int4 const &p, bool reload_j) {
-    if(kind == 0) {
-      if(cls == 1 || reload_j) {
-        const cplx *xs = a.x + (size_t)(cls ? p.x : p.y) * n2;
-        xr[0] = xs[fpos];
-        xr[1] = xs[nH + fpos];
-        xr[2] = xs[fneg];
-        xr[3] = xs[nH + fneg];
-      }
-    } else if(kind == 1) {
-      const cplx *xj = a.x + (size_t)p.y * n2, *xi = a.x + (size_t)p.x * n2;
-      if(reload_j) {
-        xr[0] = xj[fpos];
-        xr[1] = xj[nH + fpos];
-      }
-      xr[2] = xi[fpos];
-      xr[3] = xi[nH + fpos];
-    }
+  auto load_x = [&](cplx (&xr)[4], int part) {
+    const cplx *xs = a.x + (size_t)part * n2;
+    xr[0] = xs[fpos];
+    xr[1] = xs[nH + fpos];
+    xr[2] = xs[fneg];
+    xr[3] = xs[nH + fneg];
   };
-  load_x(pi, true);
-  cplx colacc[4];
-  colacc[0] = colacc[1] = colacc[2] = colacc[3] = mk(0, 0);
+  if(p0live) {
+    load_x(xj, pi.y);
+    load_x(xi, pi.x);
+  }
   int sg = a.cta_seg[blockIdx.x];
+  double *bufA = bufX, *bufB = bufY; // class vectors T / V in bufA, channels in bufB; roles swap every pair
   for(int q = qbeg; q < qend; ++q) {
     const int cur = (q - qbeg) & 1;
     const unsigned char *rec = smem + (size_t)cur * L.rec_bytes;
     const cplx *s_ph = (const cplx *)rec;
-    const cplx *s_Cp = (const cplx *)(rec + L.offCp);
-    const cplx *s_Cm = (const cplx *)(rec + L.offCm) - NM * NM;
-    const double *dp = (const double *)(rec + dofs);
+    const double *s_Cp = (const double *)(rec + L.offCp), *s_Cm = (const double *)(rec + L.offCm);
+    const double *s_Ds = (const double *)(rec + L.offDs), *s_Da = (const double *)(rec + L.offDa);
     r_mbar_wait(&full[cur], (uint32_t)(((q - qbeg) >> 1) & 1));
     // ---- P0: phases, parity signs of the reversed direction, flip basis ----
-    if(kind == 0) {
-      const cplx pp = s_ph[NM + da], pm = s_ph[NM - da];
-      const cplx te_p = cmul(pp, xr[0]), tm_p = cmul(pp, xr[1]), te_m = cmul(pm, xr[2]), tm_m = cmul(pm, xr[3]);
-      // direction 1 (a-lanes): x_i with (-1)^deg, and -1 on TM
-      const double fe = (cls ? sn : 1.0) * ROT_SQH, fm = (cls ? -sn : 1.0) * ROT_SQH;
-      cplx *ts = bufA + 4 * (offFn + da) + 2 * cls, *ta = bufA + 4 * (offFn + dn + 1 + da) + 2 * cls;
-      ts[0] = mk(fe * (te_p.x + sa * te_m.x), fe * (te_p.y + sa * te_m.y));
-      ts[1] = mk(fm * (tm_p.x + sa * tm_m.x), fm * (tm_p.y + sa * tm_m.y));
-      ta[0] = mk(fe * (te_p.x - sa * te_m.x), fe * (te_p.y - sa * te_m.y));
-      ta[1] = mk(fm * (tm_p.x - sa * tm_m.x), fm * (tm_p.y - sa * tm_m.y));
-    } else if(kind == 1) {
-      cplx *ts = bufA + 4 * offFn; // exp(i 0 phi) = 1
-      ts[0] = xr[0];
-      ts[1] = xr[1];
-      ts[2] = cscale(xr[2], sn);
-      ts[3] = cscale(xr[3], -sn);
+    if(p0live) {
+      const cplx pp = s_ph[NM + pa], pm = s_ph[NM - pa];
+#pragma unroll
+      for(int dir = 0; dir < 2; ++dir) {
+        const cplx *xr = dir ? xi : xj;
+        const double ge = dir ? psn : 1.0, gm = dir ? -psn : 1.0; // direction 1: x_i with (-1)^deg, and -1 on TM
+        const cplx te_p = cmul(pp, xr[0]), tm_p = cmul(pp, xr[1]);
+        cplx *ts = (cplx *)(bufA + dir * PS + 4 * pfs), *ta = (cplx *)(bufA + dir * PS + 4 * pfa);
+        if(pa == 0) {
+          ts[0] = cscale(te_p, ge);
+          ts[1] = cscale(tm_p, gm);
+        } else {
+          const cplx te_m = cmul(pm, xr[2]), tm_m = cmul(pm, xr[3]);
+          const double fe = ge * ROT_SQH, fm = gm * ROT_SQH;
+          ts[0] = mk(fe * (te_p.x + psa * te_m.x), fe * (te_p.y + psa * te_m.y));
+          ts[1] = mk(fm * (tm_p.x + psa * tm_m.x), fm * (tm_p.y + psa * tm_m.y));
+          ta[0] = mk(fe * (te_p.x - psa * te_m.x), fe * (te_p.y - psa * te_m.y));
+          ta[1] = mk(fm * (tm_p.x - psa * tm_m.x), fm * (tm_p.y - psa * tm_m.y));
+        }
+      }
     }
     __syncthreads(); // B1: T complete; every thread is past P3/P4 of the previous pair -> the other record slot is free
     int4 pnext = pi;
@@ -476,125 +489,139 @@ __global__ void __launch_bounds__(OB_ROT_MAX_THREADS) k_matvec_rot(RotArgs a) {
                    &full[cur ^ 1], pol);
       }
       pnext = a.pinfo[q + 1];
+      if(p0live) { // next pair's x into registers (L2 hits), consumed by its P0
+        if(pnext.y != pi.y)
+          load_x(xj, pnext.y);
+        load_x(xi, pnext.x);
+      }
     }
     // ---- P1: u = D^T t, channel combinations ----
-    cplx acc[4];
-    rot_dphase(dp, stride, bufA + 4 * vbase, cnt, acc);
-    if(q + 1 < qend)
-      load_x(pnext, pnext.y != pi.y); // next pair's x into registers (L2 hits), consumed by its P0
-    {
-      // s-lane: p+- = TE_s +- TM_a; a-lane: r+- = TM_s +- TE_a (the partner's TM of both directions)
-      const cplx o1 = shfl_xor1(acc[1]), o3 = shfl_xor1(acc[3]);
-      if(kind == 0) {
-        cplx *P = bufB + 8 * pidx + 2 * cls;
-        if(cls == 0) {
-          P[0] = cadd(acc[0], o1);
-          P[1] = csub(acc[0], o1);
-          P[4] = cadd(acc[2], o3);
-          P[5] = csub(acc[2], o3);
-        } else {
-          P[0] = cadd(o1, acc[0]);
-          P[1] = csub(o1, acc[0]);
-          P[4] = cadd(o3, acc[2]);
-          P[5] = csub(o3, acc[2]);
-        }
-      } else if(kind == 1) {
-        cplx *P = bufB + 8 * pidx;
-        P[0] = acc[0];
-        P[1] = acc[0];
-        P[2] = acc[1];
-        P[3] = acc[1];
-        P[4] = acc[2];
-        P[5] = acc[2];
-        P[6] = acc[3];
-        P[7] = acc[3];
+    for(int u = d0; u < d1; ++u) {
+      const int n = a.u.dn[u], m0 = a.u.dm[u];
+      double accS[2], accA[2];
+      rot_dunit(s_Ds, s_Da, bufA + bofs, n, m0, lane, accS, accA);
+      // lane (row a, vector fc): TE lanes need the partner's u_a of TM and vice versa: ch+- = u_s +- u_a(partner)
+      const double ox = __shfl_xor_sync(0xffffffffu, accA[0], 1), oy = __shfl_xor_sync(0xffffffffu, accA[1], 1);
+      const int aa = m0 + fr;
+      if(aa <= n) { // a = 0: u_a = 0, both channels equal u_s
+        double *P = bufB + cdir * PP + 4 * (rot_offP(NM, aa) + (n - rot_n0(aa))) + 2 * cpol;
+        *(cplx *)P = mk(accS[0] + ox, accS[1] + oy);
+        *(cplx *)(P + SS) = mk(accS[0] - ox, accS[1] - oy);
       }
     }
     __syncthreads(); // B2
-    // ---- P2: q = C p for the eight channels of (a2, d2), back to the class vectors ----
-    if(p2live) {
-      cplx qv[8];
-#pragma unroll
-      for(int c = 0; c < 8; ++c)
-        qv[c] = mk(0, 0);
-      const cplx *cp = s_Cp + cofs, *cm = (a2 == 0 ? s_Cp : s_Cm) + cofs;
-      const cplx *pv = bufB + 8 * pbase2;
-      for(int l = 0; l < w2; ++l) {
-        const cplx vp = cp[l * w2], vm = cm[l * w2];
-#pragma unroll
-        for(int c = 0; c < 8; c += 2) {
-          cfma(qv[c], vp, pv[8 * l + c]);
-          cfma(qv[c + 1], vm, pv[8 * l + c + 1]);
+    // ---- P2: q = C p per order a (Re and Im of C as two real DMMAs on one B fragment), back to the class vectors ----
+    for(int u = c0; u < c1; ++u) {
+      const int ca = a.u.ca[u], m0 = a.u.cm[u];
+      const int n0 = rot_n0(ca), w = NM - n0 + 1;
+      const bool rowv = m0 + fr < w;
+      const int e0 = rot_offX(NM, ca) + m0 + fr;
+      const double *Bp = bufB + bofsP + 4 * (rot_offP(NM, ca) + fc);
+      double apr[2] = {0, 0}, api[2] = {0, 0}, amr[2] = {0, 0}, ami[2] = {0, 0};
+      if(ca == 0) {
+#pragma unroll 2
+        for(int k0 = 0; k0 < w; k0 += 4) {
+          const int lc = k0 + fc;
+          const bool v = rowv && lc < w;
+          const int e = e0 + lc * w;
+          const double vr = v ? s_Cp[e] : 0.0, vi = v ? s_Cp[L.X + e] : 0.0, bp = Bp[4 * k0];
+          dmma(apr, vr, bp);
+          dmma(api, vi, bp);
+        }
+      } else {
+        const int XM = L.X - NM2;
+#pragma unroll 2
+        for(int k0 = 0; k0 < w; k0 += 4) {
+          const int lc = k0 + fc;
+          const bool v = rowv && lc < w;
+          const int e = e0 + lc * w;
+          const double vr = v ? s_Cp[e] : 0.0, vi = v ? s_Cp[L.X + e] : 0.0, bp = Bp[4 * k0];
+          const double wr = v ? s_Cm[e - NM2] : 0.0, wi = v ? s_Cm[XM + e - NM2] : 0.0, bm = Bp[SS + 4 * k0];
+          dmma(apr, vr, bp);
+          dmma(api, vi, bp);
+          dmma(amr, wr, bm);
+          dmma(ami, wi, bm);
         }
       }
-#pragma unroll
-      for(int d = 0; d < 2; ++d) {
-        const cplx qp = qv[4 * d], qm = qv[4 * d + 1], rp = qv[4 * d + 2], rm = qv[4 * d + 3];
-        bufA[4 * fs2 + 2 * d] = mk(sa2 * (qp.x + qm.x), sa2 * (qp.y + qm.y));     // TE_s
-        bufA[4 * fs2 + 2 * d + 1] = mk(sa2 * (rp.x + rm.x), sa2 * (rp.y + rm.y)); // TM_s
-        if(a2 >= 1) {
-          bufA[4 * fa2 + 2 * d] = mk(sa2 * (rp.x - rm.x), sa2 * (rp.y - rm.y));     // TE_a
-          bufA[4 * fa2 + 2 * d + 1] = mk(sa2 * (qp.x - qm.x), sa2 * (qp.y - qm.y)); // TM_a
+      if(rowv) {
+        // complex products: (Re C p_re - Im C p_im, Re C p_im + Im C p_re); lane = (row n, channel fc = direction * 2 + family)
+        const double qpx = apr[0] - api[1], qpy = apr[1] + api[0];
+        const int n = n0 + m0 + fr, fs = rot_offF(n) + ca, fam = cpol;
+        double *V = bufA + cdir * PS;
+        if(ca == 0) { // p- = p+: v_s = q+ (TE_s from the p family, TM_s from the r family), no a class
+          *(cplx *)(V + 4 * fs + 2 * fam) = mk(qpx, qpy);
+        } else {
+          const double qmx = amr[0] - ami[1], qmy = amr[1] + ami[0];
+          const double h = (ca & 1) ? -0.5 : 0.5; // (-1)^a of the transposed small-d read, and the 1/2 of the channel split
+          *(cplx *)(V + 4 * fs + 2 * fam) = mk(h * (qpx + qmx), h * (qpy + qmy));                   // v_s: TE (p) / TM (r)
+          *(cplx *)(V + 4 * (fs + n + 1) + 2 * (1 - fam)) = mk(h * (qpx - qmx), h * (qpy - qmy)); // v_a: TM (p) / TE (r)
         }
       }
     }
     __syncthreads(); // B3
-    // ---- P3: w = D v;  P4: flip basis -> m, conjugate phase, parity signs, accumulate ----
-    rot_dphase(dp, stride, bufA + 4 * vbase, cnt, acc);
+    // ---- P3: w = D v;  P4: flip basis -> m, conjugate phase, parity signs, accumulate (owner lanes) ----
     {
-      // the s-lane finishes direction 0 (needs the partner's w_a of direction 0), the a-lane direction 1
-      const cplx r0 = shfl_xor1(cls ? acc[0] : acc[2]), r1 = shfl_xor1(cls ? acc[1] : acc[3]);
-      cplx *ra = rowacc + (size_t)(pi.x % I) * n2;
-      if(kind == 0) {
-        const cplx cpp = cconj(s_ph[NM + da]), cpm = cconj(s_ph[NM - da]);
-        if(cls == 0) { // w_s = acc[0..1], w_a = r0, r1; the (-1)^a' of the transposed read: sa on the +a' output
-          const double f = sa * ROT_SQH;
-          const cplx ep = cmul(cpp, mk(f * (acc[0].x + r0.x), f * (acc[0].y + r0.y)));
-          const cplx mp_ = cmul(cpp, mk(f * (acc[1].x + r1.x), f * (acc[1].y + r1.y)));
-          const cplx em = cmul(cpm, mk(ROT_SQH * (acc[0].x - r0.x), ROT_SQH * (acc[0].y - r0.y)));
-          const cplx mm = cmul(cpm, mk(ROT_SQH * (acc[1].x - r1.x), ROT_SQH * (acc[1].y - r1.y)));
-          ra[fpos] = cadd(ra[fpos], ep);
-          ra[nH + fpos] = cadd(ra[nH + fpos], mp_);
-          ra[fneg] = cadd(ra[fneg], em);
-          ra[nH + fneg] = cadd(ra[nH + fneg], mm);
-        } else { // w_a = acc[2..3], w_s = r0, r1; direction 1: (-1)^deg, and -1 on TM
-          const double fe = sa * sn * ROT_SQH, fm = -fe, ge = sn * ROT_SQH, gm = -ge;
-          cfma(colacc[0], cpp, mk(fe * (r0.x + acc[2].x), fe * (r0.y + acc[2].y)));
-          cfma(colacc[1], cpp, mk(fm * (r1.x + acc[3].x), fm * (r1.y + acc[3].y)));
-          cfma(colacc[2], cpm, mk(ge * (r0.x - acc[2].x), ge * (r0.y - acc[2].y)));
-          cfma(colacc[3], cpm, mk(gm * (r1.x - acc[3].x), gm * (r1.y - acc[3].y)));
+      const bool endc = (pi.w & 1) != 0, endr = (pi.w & 2) != 0;
+      const int islot = pi.x % I;
+      for(int u = d0; u < d1; ++u) {
+        const int n = a.u.dn[u], m0 = a.u.dm[u];
+        double accS[2], accA[2];
+        rot_dunit(s_Ds, s_Da, bufA + bofs, n, m0, lane, accS, accA);
+        const int ap = m0 + fr;
+        if(ap > n)
+          continue;
+        const double sn = (n & 1) ? -1.0 : 1.0, sap = (ap & 1) ? -1.0 : 1.0;
+        const double g = cdir ? (cpol ? -sn : sn) : 1.0; // direction 1: (-1)^deg, and -1 on TM
+        const int ip = cpol * nH + flat_index(n, ap), im = cpol * nH + flat_index(n, -ap);
+        cplx op, om;
+        if(ap == 0) {
+          op = mk(g * accS[0], g * accS[1]);
+          om = op;
+        } else {
+          const double fp = g * sap * ROT_SQH, fm = g * ROT_SQH;
+          op = cmul(cconj(s_ph[NM + ap]), mk(fp * (accS[0] + accA[0]), fp * (accS[1] + accA[1])));
+          om = cmul(cconj(s_ph[NM - ap]), mk(fm * (accS[0] - accA[0]), fm * (accS[1] - accA[1])));
         }
-      } else if(kind == 1) {
-        ra[fpos] = cadd(ra[fpos], acc[0]);
-        ra[nH + fpos] = cadd(ra[nH + fpos], acc[1]);
-        colacc[0] = cadd(colacc[0], cscale(acc[2], sn));
-        colacc[1] = cadd(colacc[1], cscale(acc[3], -sn));
+        if(cdir) { // column side: sums of particle j over the strip
+          op = cadd(colacc[ip], op);
+          if(ap)
+            om = cadd(colacc[im], om);
+          if(endc) {
+            cplx *cpart = a.colpart + (size_t)pi.z * n2;
+            cpart[ip] = op;
+            colacc[ip] = mk(0, 0);
+            if(ap) {
+              cpart[im] = om;
+              colacc[im] = mk(0, 0);
+            }
+          } else {
+            colacc[ip] = op;
+            if(ap)
+              colacc[im] = om;
+          }
+        } else { // row side: sums of the block's rows over the segment
+          cplx *ra = rowacc + (size_t)islot * n2;
+          ra[ip] = cadd(ra[ip], op);
+          if(ap)
+            ra[im] = cadd(ra[im], om);
+          if(endr) {
+            cplx *rp = a.rowpart + (size_t)sg * I * n2;
+            for(int s = 0; s < I; ++s) {
+              rp[(size_t)s * n2 + ip] = rowacc[(size_t)s * n2 + ip];
+              rowacc[(size_t)s * n2 + ip] = mk(0, 0);
+              if(ap) {
+                rp[(size_t)s * n2 + im] = rowacc[(size_t)s * n2 + im];
+                rowacc[(size_t)s * n2 + im] = mk(0, 0);
+              }
+            }
+          }
+        }
       }
-    }
-    if(pi.w & 1) { // last pair of the strip: the column-side sums of particle j
-      cplx *cpart = a.colpart + (size_t)pi.z * n2;
-      if(kind == 0 && cls == 1) {
-        cpart[fpos] = colacc[0];
-        cpart[nH + fpos] = colacc[1];
-        cpart[fneg] = colacc[2];
-        cpart[nH + fneg] = colacc[3];
-      } else if(kind == 1) {
-        cpart[fpos] = colacc[0];
-        cpart[nH + fpos] = colacc[1];
-      }
-      colacc[0] = colacc[1] = colacc[2] = colacc[3] = mk(0, 0);
-    }
-    if(pi.w & 2) { // last pair of the segment: flush the row-side sums of the block's I rows
-      __syncthreads();
-      cplx *rp = a.rowpart + (size_t)sg * I * n2;
-      for(int e = tid; e < I * n2; e += nthr) {
-        rp[e] = rowacc[e];
-        rowacc[e] = mk(0, 0);
-      }
-      ++sg;
+      if(endr)
+        ++sg;
     }
     pi = pnext;
-    cplx *tb = bufA;
+    double *tb = bufA;
     bufA = bufB;
     bufB = tb;
   }
@@ -671,8 +698,8 @@ void rot_plan_build(RotPlan &p, int nobj, int NM, int world, int rank, int sm_co
   const RotLayout L = rot_layout(NM);
   p.nobj = nobj;
   p.n = L.n;
-  p.threads = rot_block_threads(L);
-  if(p.threads > OB_ROT_MAX_THREADS)
+  p.threads = ROT_THREADS;
+  if(L.nh > ROT_THREADS)
     throw Error("rotated-axial operator: nMax exceeds the kernel's thread bound");
   // rows per block: as many (<= 4) as keep three CTAs per SM resident (the row sums of a block live in shared memory)
   int I = g_rot_rows > 0 ? g_rot_rows : 4;
@@ -816,6 +843,57 @@ void launch_assemble_rot(VtacTableSet const &ts, const double *xyz, cplx k, cons
   OB_CUDA(cudaGetLastError());
 }
 
+// longest-processing-time assignment of the DMMA work units to the warps
+static RotUnits const &rot_units(int NM) {
+  static RotUnits cache[OB_MAX_NMAX + 1];
+  static bool have[OB_MAX_NMAX + 1] = {false};
+  RotUnits &U = cache[NM];
+  if(have[NM])
+    return U;
+  memset(&U, 0, sizeof(U));
+  struct Unit {
+    int x, m0, cost;
+  };
+  auto assign = [&](std::vector<Unit> units, unsigned char *ux, unsigned char *um, unsigned char *beg) {
+    if(units.size() > ROT_MAX_UNITS)
+      throw Error("rotated-axial operator: too many work units");
+    std::stable_sort(units.begin(), units.end(), [](Unit const &p, Unit const &q) { return p.cost > q.cost; });
+    std::vector<std::vector<Unit>> per(ROT_WARPS);
+    int load[ROT_WARPS] = {0};
+    for(Unit const &u : units) {
+      int wmin = 0;
+      for(int w = 1; w < ROT_WARPS; ++w)
+        if(load[w] < load[wmin])
+          wmin = w;
+      per[wmin].push_back(u);
+      load[wmin] += u.cost;
+    }
+    int k = 0;
+    for(int w = 0; w < ROT_WARPS; ++w) {
+      beg[w] = (unsigned char)k;
+      for(Unit const &u : per[w]) {
+        ux[k] = (unsigned char)u.x;
+        um[k] = (unsigned char)u.m0;
+        ++k;
+      }
+    }
+    beg[ROT_WARPS] = (unsigned char)k;
+  };
+  std::vector<Unit> du, cu;
+  for(int n = 1; n <= NM; ++n)
+    for(int m0 = 0; m0 <= n; m0 += 8)
+      du.push_back({n, m0, (n + 1 + 3) / 4 + (n + 3) / 4});
+  for(int a = 0; a <= NM; ++a) {
+    const int w = NM - rot_n0(a) + 1;
+    for(int m0 = 0; m0 < w; m0 += 8)
+      cu.push_back({a, m0, ((w + 3) / 4) * (a == 0 ? 2 : 4)});
+  }
+  assign(du, U.dn, U.dm, U.dbeg);
+  assign(cu, U.ca, U.cm, U.cbeg);
+  have[NM] = true;
+  return U;
+}
+
 void launch_matvec_rot(RotPlan const &p, RotLayout const &L, const unsigned char *recs, const cplx *x, const cplx *Tdiag,
                        cplx *acc_or_y, int finalize, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1) {
   if(e0)
@@ -834,6 +912,7 @@ void launch_matvec_rot(RotPlan const &p, RotLayout const &L, const unsigned char
     a.colpart = p.colpart;
     a.L = L;
     a.I = p.I;
+    a.u = rot_units(L.NM);
     k_matvec_rot<<<p.grid, p.threads, p.smem, st>>>(a);
     OB_CUDA(cudaGetLastError());
   }

@@ -42,7 +42,9 @@ __host__ __device__ inline int rot_axial_buf_entries(int NM) { return 3 * (NM + 
 
 // Axial A[(n,mu),(l,mu)], B[...] for translation r along z with wavenumber k into Aout / Bout (compact layout of
 // ob_rot.cu: rot_offX(mu) + (n - n0)(NM - n0 + 1) + (l - n0)).  `lane` of `nlanes` cooperating threads; buf as above.
-// combine != 0: Aout[e] = A + B for every mu and Bout[e - NM^2] = A - B for mu >= 1 (record layout v2 of ob_rot.cu).
+// combine = 1: Aout[e] = A + B for every mu and Bout[e - NM^2] = A - B for mu >= 1 (interleaved complex).
+// combine = 2 (record layout of ob_rot.cu): the same values as planes of doubles, Aout -> [Re(A+B)[X] | Im(A+B)[X]],
+// Bout -> [Re(A-B)[X - NM^2] | Im(A-B)[X - NM^2]], X = rot_offX(NM, NM + 1).
 __host__ __device__ inline void rot_axial_pair(int NM, cplx k, double r, cplx *buf, cplx *Aout, cplx *Bout, int lane,
                                                int nlanes, int combine = 0) {
   const int LL = 2 * NM, W = LL + 3, CH = NM + 2;
@@ -110,7 +112,16 @@ __host__ __device__ inline void rot_axial_pair(int NM, cplx k, double r, cplx *b
       const cplx sB = mk(b0 * u0.x + b1 * up.x - b2 * um.x, b0 * u0.y + b1 * up.y - b2 * um.y);
       const cplx Bv = mk(-fb * sB.y, fb * sB.x); // times i fb (factor = (0, fb))
       const int w = NM - n0 + 1, e = rot_offX(NM, mu) + (n - n0) * w + (l - n0);
-      if(combine) {
+      if(combine == 2) {
+        const int X = rot_offX(NM, NM + 1), XM = X - NM * NM;
+        double *P = (double *)Aout, *M = (double *)Bout;
+        P[e] = Av.x + Bv.x;
+        P[X + e] = Av.y + Bv.y;
+        if(mu >= 1) {
+          M[e - NM * NM] = Av.x - Bv.x;
+          M[XM + e - NM * NM] = Av.y - Bv.y;
+        }
+      } else if(combine) {
         Aout[e] = cadd(Av, Bv);
         if(mu >= 1)
           Bout[e - NM * NM] = csub(Av, Bv);

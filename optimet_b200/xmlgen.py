@@ -70,13 +70,51 @@ def cube_sites(points, count=None, d_nm=190.0):
     return np.array(pts[:count] if count is not None else pts)
 
 
+class MT19937_64:
+    """std::mt19937_64 (Matsumoto & Nishimura 2004, the C++11 parameter set); the 10000th output for the default seed
+    5489 is 9981545732273789042 ([rand.predef] of the C++ standard; checked in tests/test_host_abi.py)."""
+    NN, MM = 312, 156
+    MATRIX_A, UM, LM, MASK = 0xB5026F5AA96619E9, 0xFFFFFFFF80000000, 0x7FFFFFFF, (1 << 64) - 1
+
+    def __init__(self, seed=5489):
+        self.mt = [0] * self.NN
+        self.mt[0] = seed & self.MASK
+        for i in range(1, self.NN):
+            self.mt[i] = (6364136223846793005 * (self.mt[i - 1] ^ (self.mt[i - 1] >> 62)) + i) & self.MASK
+        self.mti = self.NN
+
+    def next(self):
+        mt, NN, MM = self.mt, self.NN, self.MM
+        if self.mti >= NN:
+            for i in range(NN):
+                x = (mt[i] & self.UM) | (mt[(i + 1) % NN] & self.LM)
+                mt[i] = mt[(i + MM) % NN] ^ (x >> 1) ^ (self.MATRIX_A if x & 1 else 0)
+            self.mti = 0
+        x = mt[self.mti]
+        self.mti += 1
+        x ^= (x >> 29) & 0x5555555555555555
+        x ^= (x << 17) & 0x71D67FFFEDA60000
+        x ^= (x << 37) & 0xFFF7EEE000000000
+        x ^= x >> 43
+        return x & self.MASK
+
+    def uniform(self, lo, hi):
+        """std::uniform_real_distribution<double>(lo, hi) as libstdc++ evaluates it for a 64-bit engine: one draw,
+        generate_canonical<double, 53> = draw / 2^64 rounded to nearest (values that round to 1 step down)."""
+        u = float(self.next()) * (2.0 ** -64)
+        if u >= 1.0:
+            u = 1.0 - 2.0 ** -53
+        return u * (hi - lo) + lo
+
+
 def random_sites(nobj, side_nm, min_dist_nm, seed):
-    """Sequential rejection sampling in a cube (seed 20261017, side 2200 nm, min distance 150 nm)."""
-    rng = np.random.RandomState(seed % (2 ** 32))
+    """Sequential rejection sampling in a cube (SURVEY.md section 8d, C5: std::mt19937_64 seed 20261017, side 2200 nm,
+    minimum centre distance 150 nm); x, y, z of a candidate are drawn in that order with uniform_real_distribution."""
+    rng = MT19937_64(seed)
     pts = np.zeros((nobj, 3))
     n = 0
     while n < nobj:
-        p = rng.uniform(0.0, side_nm, 3)
+        p = np.array([rng.uniform(0.0, side_nm), rng.uniform(0.0, side_nm), rng.uniform(0.0, side_nm)])
         if n == 0 or np.min(np.linalg.norm(pts[:n] - p, axis=1)) >= min_dist_nm:
             pts[n] = p
             n += 1

@@ -17,8 +17,8 @@ extern "C" int rot_axial_host(int NM, const double k[2], double r, double *A, do
 }
 
 // record layout v2: Cp = A + B (all mu), Cm = A - B (mu >= 1, stored from offX(1) = NM^2 on)
-extern "C" int rot_axial_host_combined(int NM, const double k[2], double r, double *Cp, double *Cm) {
+extern "C" int rot_axial_host_combined(int NM, const double k[2], double r, double *Cp, double *Cm, int mode) {
   std::vector<ob::cplx> buf((size_t)ob::rot_axial_buf_entries(NM), ob::mk(0, 0));
-  ob::rot_axial_pair(NM, ob::mk(k[0], k[1]), r, buf.data(), (ob::cplx *)Cp, (ob::cplx *)Cm, 0, 1, 1);
+  ob::rot_axial_pair(NM, ob::mk(k[0], k[1]), r, buf.data(), (ob::cplx *)Cp, (ob::cplx *)Cm, 0, 1, mode);
   return ob::rot_offX(NM, NM + 1);
 }

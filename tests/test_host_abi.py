@@ -198,3 +198,21 @@ def test_solver_selection_follows_the_reference_factory():
     assert opts(aca=True, belos=belos("eigen")) == (capi.OB_GMRES_ZCOMP, 1e-6, 240, 2)
     assert opts(aca=True, belos=belos("GMRES")) == (capi.OB_GMRES_ZCOMP, 1e-6, 340, 1)
     assert opts(aca=True, belos=belos("scalapack")) == (capi.OB_GMRES_ZCOMP, 1e-7, 250, 3)
+
+
+def test_c5_generator_is_the_contract_rng():
+    """SURVEY section 8(d), C5: 1000 centres by sequential rejection from std::mt19937_64 seed 20261017.  The engine is
+    pinned by the standard's known answer (10000th output of the default-seeded engine, [rand.predef])."""
+    from optimet_b200 import xmlgen
+    eng = xmlgen.MT19937_64()
+    for _ in range(9999):
+        eng.next()
+    assert eng.next() == 9981545732273789042
+    pts = xmlgen.random_sites(1000, 2200.0, 150.0, 20261017)
+    assert pts.shape == (1000, 3) and pts.min() >= 0.0 and pts.max() < 2200.0
+    d = np.linalg.norm(pts[:, None, :] - pts[None, :, :], axis=2) + 1e9 * np.eye(1000)
+    assert d.min() >= 150.0
+    # first centre = first three draws of the seeded engine times the side
+    eng = xmlgen.MT19937_64(20261017)
+    first = [float(eng.next()) * 2.0 ** -64 * 2200.0 for _ in range(3)]
+    assert np.array_equal(pts[0], np.array(first))

@@ -63,7 +63,7 @@ def test_device_source_of_the_axial_recursion_on_the_host(host_lib, NM, k, d):
 
 @pytest.mark.parametrize("NM", [1, 4, 10])
 def test_combined_output_of_the_axial_recursion(host_lib, NM):
-    """combine = 1 (what k_assemble_axial_only passes): A + B for every mu, A - B for mu >= 1 behind the mu = 0 block."""
+    """combine = 1 / 2 (2 is what k_assemble_axial_only passes): A + B for every mu, A - B for mu >= 1 behind the mu = 0 block."""
     k, d = 2 * np.pi / 500e-9 * (1.1 + 0.03j), 230e-9
     X = _offX(NM, NM + 1)
     A = np.zeros(X, dtype=np.complex128)
@@ -73,7 +73,13 @@ def test_combined_output_of_the_axial_recursion(host_lib, NM):
     kk = (C.c_double * 2)(complex(k).real, complex(k).imag)
     host_lib.rot_axial_host(int(NM), kk, C.c_double(d), A.ctypes.data_as(C.c_void_p), B.ctypes.data_as(C.c_void_p))
     host_lib.rot_axial_host_combined(int(NM), kk, C.c_double(d), Cp.ctypes.data_as(C.c_void_p),
-                                     Cm.ctypes.data_as(C.c_void_p))
+                                     Cm.ctypes.data_as(C.c_void_p), 1)
     assert np.array_equal(Cp, A + B)
     assert np.array_equal(Cm, (A - B)[NM * NM:])
+    # combine = 2 (the record layout of ob_rot.cu): the same values as [Re | Im] planes of doubles
+    Pp = np.zeros(2 * X)
+    Pm = np.zeros(2 * (X - NM * NM))
+    host_lib.rot_axial_host_combined(int(NM), kk, C.c_double(d), Pp.ctypes.data_as(C.c_void_p),
+                                     Pm.ctypes.data_as(C.c_void_p), 2)
+    assert np.array_equal(Pp[:X] + 1j * Pp[X:], Cp) and np.array_equal(Pm[:X - NM * NM] + 1j * Pm[X - NM * NM:], Cm)
     assert not np.abs(B[:NM * NM]).any()      # mu = 0: B = 0, so Cm = Cp there and is not stored
