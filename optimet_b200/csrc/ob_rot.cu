@@ -49,6 +49,7 @@
 #include "ob_rot_axial.cuh"
 #include <algorithm>
 #include <cstring>
+#include <utility>
 
 namespace ob {
 
@@ -57,10 +58,10 @@ namespace ob {
 // ---------------------------------------------------------------------------------------------
 // layout helpers (host + device), mirrored by tests/rot2_model.py
 // ---------------------------------------------------------------------------------------------
-__host__ __device__ inline int rot_offDs(int n) { return n * (n + 1) * (2 * n + 1) / 6 - 1; } // sum_{j<n} (j+1)^2
-__host__ __device__ inline int rot_offDa(int n) { return (n - 1) * n * (2 * n - 1) / 6; }     // sum_{j<n} j^2
-__host__ __device__ inline int rot_offF(int n) { return (n - 1) * (n + 2); }
-__host__ __device__ inline int rot_offP(int NM, int a) { // channel index of (a, l = n0): sum_{u<a} (NM - max(u,1) + 1)
+__host__ __device__ constexpr inline int rot_offDs(int n) { return n * (n + 1) * (2 * n + 1) / 6 - 1; } // sum_{j<n} (j+1)^2
+__host__ __device__ constexpr inline int rot_offDa(int n) { return (n - 1) * n * (2 * n - 1) / 6; }     // sum_{j<n} j^2
+__host__ __device__ constexpr inline int rot_offF(int n) { return (n - 1) * (n + 2); }
+__host__ __device__ constexpr inline int rot_offP(int NM, int a) { // channel index of (a, l = n0): sum_{u<a} (NM - max(u,1) + 1)
   return a <= 0 ? 0 : NM + (a - 1) * (NM + 1) - (a - 1) * a / 2;
 }
 RotLayout rot_layout(int NM) {
@@ -295,12 +296,57 @@ k_rot_tables(const double *__restrict__ xyz, const int2 *__restrict__ pair_ij, l
 #define ROT_WARPS 4
 #define ROT_THREADS (32 * ROT_WARPS)
 #define ROT_MAX_UNITS 32
-// static work lists of the warps: d-phase units (degree n, first row m0 of an 8-row tile; the s and the a class together)
-// and P2 units (order a, first row of an 8-row tile; the A + B and the A - B channels together), balanced on the host
-struct RotUnits {
-  unsigned char dn[ROT_MAX_UNITS], dm[ROT_MAX_UNITS], ca[ROT_MAX_UNITS], cm[ROT_MAX_UNITS];
-  unsigned char dbeg[ROT_WARPS + 1], cbeg[ROT_WARPS + 1];
+// Static work lists, evaluated at COMPILE TIME per nMax (the kernel is a template on nMax: every offset, stride, K-step
+// count and tail condition below is an immediate; the first DMMA version took them from run-time tables and spent
+// 33 instructions per DMMA on index arithmetic).  d-phase units: degree n, first row m0 of an 8-row tile, the s and the
+// a class together.  P2 units: order a, first row of an 8-row tile, the A + B and the A - B channels together.  Units
+// go to the warps by longest-processing-time (cost = DMMAs).
+struct RotCT {
+  int nd, nc;
+  int dn[ROT_MAX_UNITS], dm[ROT_MAX_UNITS], dw[ROT_MAX_UNITS], dc[ROT_MAX_UNITS];
+  int ca[ROT_MAX_UNITS], cm[ROT_MAX_UNITS], cw[ROT_MAX_UNITS], cc[ROT_MAX_UNITS];
 };
+__host__ __device__ constexpr inline void rot_ct_assign(int count, const int *cost, int *owner) {
+  bool done[ROT_MAX_UNITS] = {};
+  int load[ROT_WARPS] = {};
+  for(int it = 0; it < count; ++it) {
+    int best = -1;
+    for(int u = 0; u < count; ++u)
+      if(!done[u] && (best < 0 || cost[u] > cost[best]))
+        best = u;
+    int w = 0;
+    for(int i = 1; i < ROT_WARPS; ++i)
+      if(load[i] < load[w])
+        w = i;
+    owner[best] = w;
+    load[w] += cost[best];
+    done[best] = true;
+  }
+}
+__host__ __device__ constexpr inline RotCT rot_ct(int NM) {
+  RotCT T{};
+  for(int n = 1; n <= NM; ++n)
+    for(int m0 = 0; m0 <= n; m0 += 8) {
+      T.dn[T.nd] = n;
+      T.dm[T.nd] = m0;
+      T.dc[T.nd] = (n + 1 + 3) / 4 + (n + 3) / 4;
+      ++T.nd;
+    }
+  for(int a = 0; a <= NM; ++a) {
+    const int w = NM - rot_n0(a) + 1;
+    for(int m0 = 0; m0 < w; m0 += 8) {
+      T.ca[T.nc] = a;
+      T.cm[T.nc] = m0;
+      T.cc[T.nc] = ((w + 3) / 4) * (a == 0 ? 2 : 4);
+      ++T.nc;
+    }
+  }
+  rot_ct_assign(T.nd, T.dc, T.dw);
+  rot_ct_assign(T.nc, T.cc, T.cw);
+  return T;
+}
+static_assert(rot_ct(OB_MAX_NMAX).nd <= ROT_MAX_UNITS && rot_ct(OB_MAX_NMAX).nc <= ROT_MAX_UNITS, "unit tables too small");
+
 struct RotArgs {
   const unsigned char *recs;
   const cplx *x;
@@ -310,7 +356,6 @@ struct RotArgs {
   cplx *rowpart, *colpart;
   RotLayout L;
   int I;
-  RotUnits u;
 };
 
 __device__ __forceinline__ uint32_t r_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -347,54 +392,185 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
 // two directions ("planes") PS doubles apart; channels P: [A+B | A-B][direction][(a, l)][p re, p im, r re, r im].  A B
 // fragment (row = lane & 3 consecutive F / channel indices, column = lane >> 2) reads 128 contiguous bytes per
 // half-warp: plane = lane >> 4, position inside the 32-byte row = (lane >> 2) & 3.  Rows past the valid K range are
-// read (their A entries are zero) and must stay finite: the planes carry eight spare rows and start zeroed.
-__host__ __device__ inline int rot_plane_doubles(int LF) { return 4 * (LF + 8); }
-// dynamic shared memory: record[2] | bufX[2 planes] | bufY[2 planes] | rowacc[I][2n] | colacc[2n] | mbarrier[2]
+// read (their A entries are forced to zero) and must stay finite: the planes carry eight spare rows and start zeroed.
+// A-fragment rows past the valid outputs of a tile are read from wherever they fall inside the CTA's shared memory:
+// rows of a matrix product are independent and those results are never stored.
+__host__ __device__ constexpr inline int rot_plane_doubles(int LF) { return 4 * (LF + 8); }
+// dynamic shared memory: record[2] | bufX[2 planes] | bufY[2 planes] | acc[I + 1][2n] (rows of the block, then the
+// column sums of the strip) | mbarrier[2]
 static size_t rot_smem_bytes(RotLayout const &L, int I) {
   return 2 * L.rec_bytes + (size_t)4 * rot_plane_doubles(L.LF) * sizeof(double) + (size_t)(I + 1) * 2 * L.n * sizeof(cplx) +
          2 * sizeof(uint64_t);
 }
 
-// d-phase unit (P1 and P3): rows a = m0 .. m0 + 7 of degree n, both classes.
-//   accS[(a, col)] = sum_{a' = 0..n} Ds[a' (n + 1) + a] v_s[a'][col],  accA[(a, col)] = sum_{a' = 1..n} Da[(a' - 1) n + (a - 1)] v_a[a'][col]
-// vb = buffer + plane / in-row offset of this lane (see above)
-__device__ __forceinline__ void rot_dunit(const double *__restrict__ Ds, const double *__restrict__ Da,
-                                          const double *__restrict__ vb, int n, int m0, int lane, double (&accS)[2],
-                                          double (&accA)[2]) {
-  const int r = lane >> 2, c = lane & 3, a = m0 + r, n1 = n + 1;
-  accS[0] = accS[1] = accA[0] = accA[1] = 0.0;
-  const double *As = Ds + rot_offDs(n) + a;
-  const double *Bs = vb + 4 * (rot_offF(n) + c);
-  const bool rowS = a <= n;
-#pragma unroll 2
-  for(int k0 = 0; k0 <= n; k0 += 4) {
-    const int ap = k0 + c;
-    const double av = (rowS && ap <= n) ? As[ap * n1] : 0.0;
-    dmma(accS, av, Bs[4 * k0]);
+// per-lane state of the pair being processed (everything else is an immediate)
+struct RotLane {
+  int warp, fr, fc, cpol;
+  const double *Ds, *Da, *Cp, *Cm; // sections of the current record, already offset by this lane's fragment row (+ fr)
+  const double *vb;                // class-vector buffer + plane / in-row offset of the B fragment
+  const double *pb;                // channel buffer + plane / in-row offset of the B fragment
+  double *pst;                     // channel buffer + direction plane + 2 * pol (P1 stores)
+  double *vst;                     // class-vector buffer + direction plane + 2 * pol (P2 stores)
+  const cplx *ph;                  // phases of the current record + NM
+  cplx *dst;                       // accumulator row of this lane's direction + pol * nH (P4)
+  double gl;                       // sign of this lane's vector in direction 1 (without (-1)^deg)
+  bool dir1;
+};
+
+// accumulation chain of KS K-steps over K columns: straight-line loads, then DMMAs; A advances stepA doubles per step,
+// B 16 doubles; only the last step can run past the K range (compile-time known), where the lane's A entry is zeroed
+template <int KS, int K>
+__device__ __forceinline__ void rot_chain(double (&acc)[2], const double *__restrict__ pa, int stepA,
+                                          const double *__restrict__ pb, int fc) {
+  double av[KS], bv[KS];
+#pragma unroll
+  for(int s = 0; s < KS; ++s) {
+    av[s] = pa[s * stepA];
+    bv[s] = pb[16 * s];
   }
-  const double *Aa = Da + rot_offDa(n) + (a - 1);
-  const double *Ba = vb + 4 * (rot_offF(n) + n + 2 + c);
-  const bool rowA = a >= 1 && a <= n;
-#pragma unroll 2
-  for(int k0 = 0; k0 < n; k0 += 4) {
-    const int ap = 1 + k0 + c;
-    const double av = (rowA && ap <= n) ? Aa[(ap - 1) * n] : 0.0;
-    dmma(accA, av, Ba[4 * k0]);
+  if(4 * KS > K)
+    av[KS - 1] = 4 * (KS - 1) + fc < K ? av[KS - 1] : 0.0;
+#pragma unroll
+  for(int s = 0; s < KS; ++s)
+    dmma(acc, av[s], bv[s]);
+}
+// two chains on the same B fragments: real and imaginary plane of one complex matrix (planes dI doubles apart)
+template <int KS, int K>
+__device__ __forceinline__ void rot_chain2(double (&accR)[2], double (&accI)[2], const double *__restrict__ pa, int dI,
+                                           int stepA, const double *__restrict__ pb, int fc) {
+  double ar[KS], ai[KS], bv[KS];
+#pragma unroll
+  for(int s = 0; s < KS; ++s) {
+    ar[s] = pa[s * stepA];
+    ai[s] = pa[s * stepA + dI];
+    bv[s] = pb[16 * s];
+  }
+  if(4 * KS > K) {
+    const bool in = 4 * (KS - 1) + fc < K;
+    ar[KS - 1] = in ? ar[KS - 1] : 0.0;
+    ai[KS - 1] = in ? ai[KS - 1] : 0.0;
+  }
+#pragma unroll
+  for(int s = 0; s < KS; ++s) {
+    dmma(accR, ar[s], bv[s]);
+    dmma(accI, ai[s], bv[s]);
   }
 }
 
-__global__ void __launch_bounds__(ROT_THREADS) k_matvec_rot(const __grid_constant__ RotArgs a) {
+// d-phase unit U of nMax NM (P1 and P3): rows a = m0 .. m0 + 7 of degree n, both classes.
+//   accS[(a, col)] = sum_{a' = 0..n} Ds[a' (n + 1) + a] v_s[a'][col],  accA[(a, col)] = sum_{a' = 1..n} Da[(a' - 1) n + (a - 1)] v_a[a'][col]
+template <int NM, int U>
+__device__ __forceinline__ void rot_dchains(RotLane const &c, double (&accS)[2], double (&accA)[2]) {
+  constexpr RotCT T = rot_ct(NM);
+  constexpr int n = T.dn[U], m0 = T.dm[U], n1 = n + 1;
+  accS[0] = accS[1] = accA[0] = accA[1] = 0.0;
+  rot_chain<(n1 + 3) / 4, n1>(accS, c.Ds + rot_offDs(n) + m0 + c.fc * n1, 4 * n1, c.vb + 4 * rot_offF(n) + 4 * c.fc, c.fc);
+  rot_chain<(n + 3) / 4, n>(accA, c.Da + rot_offDa(n) + m0 - 1 + c.fc * n, 4 * n, c.vb + 4 * (rot_offF(n) + n + 2) + 4 * c.fc, c.fc);
+}
+
+// P1 unit: u = D^T t, channel sums p+- = TE_s +- TM_a (TE lanes), r+- = TM_s +- TE_a (TM lanes)
+template <int NM, int U> __device__ __forceinline__ void rot_p1_unit(RotLane const &c) {
+  constexpr RotCT T = rot_ct(NM);
+  constexpr int n = T.dn[U], m0 = T.dm[U], SS = rot_plane_doubles(NM * (NM + 3));
+  if(c.warp != T.dw[U])
+    return;
+  double aS[2], aA[2];
+  rot_dchains<NM, U>(c, aS, aA);
+  const int aa = m0 + c.fr;
+  if(m0 == 0 && c.fr == 0) // the a class has no a = 0 row (its fragment row was read from outside the block)
+    aA[0] = aA[1] = 0.0;
+  // lane (row a, vector fc): TE lanes need the partner's u_a of TM and vice versa: ch+- = u_s +- u_a(partner)
+  const double ox = __shfl_xor_sync(0xffffffffu, aA[0], 1), oy = __shfl_xor_sync(0xffffffffu, aA[1], 1);
+  if(m0 + 7 <= n || aa <= n) { // a = 0: both channels equal u_s
+    // channel index of (a, l = n): offP(a) + n - max(a, 1)
+    const int idx = (aa == 0 ? 0 : NM + (aa - 1) * (NM + 1) - (aa - 1) * aa / 2) + n - (aa > 1 ? aa : 1);
+    double *P = c.pst + 4 * idx;
+    *(cplx *)P = mk(aS[0] + ox, aS[1] + oy);
+    *(cplx *)(P + SS) = mk(aS[0] - ox, aS[1] - oy);
+  }
+}
+
+// P2 unit: q = C p for order a, rows n = n0 + m0 .. + 7 (Re and Im of C as two real DMMAs on one B fragment), back to
+// the class vectors: v_s = (-1)^a (q+ + q-) / 2, v_a = (-1)^a (q+ - q-) / 2
+template <int NM, int U> __device__ __forceinline__ void rot_p2_unit(RotLane const &c) {
+  constexpr RotCT T = rot_ct(NM);
+  constexpr int a = T.ca[U], m0 = T.cm[U], n0 = rot_n0(a), w = NM - n0 + 1, ks = (w + 3) / 4;
+  constexpr int XC = rot_offX(NM, NM + 1), XM = XC - NM * NM, SS = rot_plane_doubles(NM * (NM + 3));
+  if(c.warp != T.cw[U])
+    return;
+  double apr[2] = {0, 0}, api[2] = {0, 0};
+  const double *pb = c.pb + 4 * rot_offP(NM, a) + 4 * c.fc;
+  rot_chain2<ks, w>(apr, api, c.Cp + rot_offX(NM, a) + m0 + c.fc * w, XC, 4 * w, pb, c.fc);
+  // complex products: (Re C p_re - Im C p_im, Re C p_im + Im C p_re); lane = (row n, channel fc = direction * 2 + family)
+  const double qpx = apr[0] - api[1], qpy = apr[1] + api[0];
+  const int row = m0 + c.fr, n = n0 + row;
+  double *V = c.vst + 4 * ((n - 1) * (n + 2) + a);
+  if(a == 0) { // p- = p+: v_s = q+ (TE_s from the p family, TM_s from the r family), no a class
+    if(m0 + 7 < w || row < w)
+      *(cplx *)V = mk(qpx, qpy);
+  } else {
+    double amr[2] = {0, 0}, ami[2] = {0, 0};
+    rot_chain2<ks, w>(amr, ami, c.Cm + rot_offX(NM, a) + m0 + c.fc * w, XM, 4 * w, pb + SS, c.fc);
+    const double qmx = amr[0] - ami[1], qmy = amr[1] + ami[0];
+    constexpr double h = (a & 1) ? -0.5 : 0.5; // (-1)^a of the transposed small-d read, and the 1/2 of the channel split
+    if(m0 + 7 < w || row < w) {
+      *(cplx *)V = mk(h * (qpx + qmx), h * (qpy + qmy));                                   // v_s: TE (p) / TM (r)
+      *(cplx *)(V + 4 * (n + 1) + 2 - 4 * c.cpol) = mk(h * (qpx - qmx), h * (qpy - qmy)); // v_a: TM (p) / TE (r)
+    }
+  }
+}
+
+// P3 + P4 unit: w = D v, flip basis -> m, conjugate phase, parity signs of direction 1, accumulate (owner lanes)
+template <int NM, int U> __device__ __forceinline__ void rot_p3_unit(RotLane const &c) {
+  constexpr RotCT T = rot_ct(NM);
+  constexpr int n = T.dn[U], m0 = T.dm[U];
+  if(c.warp != T.dw[U])
+    return;
+  double aS[2], aA[2];
+  rot_dchains<NM, U>(c, aS, aA);
+  const int ap = m0 + c.fr;
+  if(m0 + 7 > n && ap > n)
+    return;
+  const double g = (c.dir1 && (n & 1)) ? -c.gl : c.gl; // direction 1: (-1)^deg
+  cplx *d = c.dst + (n * (n + 1) - 1) - ap;
+  if(m0 == 0 && ap == 0) { // a' = 0: the s class alone, exp(i 0 phi) = 1
+    d[0] = cadd(d[0], mk(g * aS[0], g * aS[1]));
+    return;
+  }
+  const double fp = (ap & 1) ? -g * ROT_SQH : g * ROT_SQH, fm = g * ROT_SQH;
+  const cplx php = c.ph[ap], phm = c.ph[-ap];
+  const double sx = fp * (aS[0] + aA[0]), sy = fp * (aS[1] + aA[1]);
+  const double dx = fm * (aS[0] - aA[0]), dy = fm * (aS[1] - aA[1]);
+  // conj(phase) * value
+  const cplx o1 = d[0], o2 = d[2 * ap];
+  d[0] = mk(o1.x + (php.x * sx + php.y * sy), o1.y + (php.x * sy - php.y * sx));
+  d[2 * ap] = mk(o2.x + (phm.x * dx + phm.y * dy), o2.y + (phm.x * dy - phm.y * dx));
+}
+
+template <int NM, int... U> __device__ __forceinline__ void rot_p1_all(RotLane const &c, std::integer_sequence<int, U...>) {
+  (rot_p1_unit<NM, U>(c), ...);
+}
+template <int NM, int... U> __device__ __forceinline__ void rot_p2_all(RotLane const &c, std::integer_sequence<int, U...>) {
+  (rot_p2_unit<NM, U>(c), ...);
+}
+template <int NM, int... U> __device__ __forceinline__ void rot_p3_all(RotLane const &c, std::integer_sequence<int, U...>) {
+  (rot_p3_unit<NM, U>(c), ...);
+}
+
+template <int NM>
+__global__ void __launch_bounds__(ROT_THREADS, 3) k_matvec_rot(const __grid_constant__ RotArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
+  constexpr RotCT T = rot_ct(NM);
+  constexpr int nH = NM * (NM + 2), n2 = 2 * nH, LF = NM * (NM + 3), NH = LF / 2;
+  constexpr int PS = rot_plane_doubles(LF); // plane stride of the class-vector buffers (doubles)
+  constexpr int PP = PS / 2;                // channel buffers: plane stride (the A+B and A-B halves are PS apart)
   const RotLayout L = a.L;
-  const int NM = L.NM, nH = L.n, n2 = 2 * nH, I = a.I, NM2 = NM * NM;
-  const int PS = rot_plane_doubles(L.LF); // plane stride of the class-vector buffers (doubles)
-  const int PP = PS / 2, SS = PS;         // channel buffers: plane stride, stride between the A+B and the A-B halves
+  const int I = a.I;
   double *bufX = (double *)(smem + 2 * L.rec_bytes);
   double *bufY = bufX + 2 * PS;
-  cplx *rowacc = (cplx *)(bufY + 2 * PS);
-  cplx *colacc = rowacc + (size_t)I * n2;
-  uint64_t *full = (uint64_t *)(colacc + n2);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  cplx *acc = (cplx *)(bufY + 2 * PS); // [I rows of the block | column sums of the strip][2n]
+  uint64_t *full = (uint64_t *)(acc + (size_t)(I + 1) * n2);
+  const int tid = threadIdx.x, lane = tid & 31;
   const int qbeg = a.cta_pair[blockIdx.x], qend = a.cta_pair[blockIdx.x + 1];
   if(qbeg >= qend)
     return;
@@ -403,12 +579,15 @@ __global__ void __launch_bounds__(ROT_THREADS) k_matvec_rot(const __grid_constan
     r_mbar_init(&full[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for(int e = tid; e < 4 * PS; e += ROT_THREADS)
-    bufX[e] = 0.0; // bufX and bufY
-  for(int e = tid; e < (I + 1) * n2; e += ROT_THREADS)
-    rowacc[e] = mk(0, 0); // rowacc and colacc
+  { // everything the fragment loads may touch starts finite
+    double *z = (double *)smem;
+    const int nz = (int)((2 * L.rec_bytes) / sizeof(double)) + 4 * PS + 2 * (I + 1) * n2;
+    for(int e = tid; e < nz; e += ROT_THREADS)
+      z[e] = 0.0;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy writes before the bulk copies into the slots
+  }
   // ---- P0 item of this thread: (pn, pa), pa = 0..pn, sorted by degree ----
-  const bool p0live = tid < L.nh;
+  const bool p0live = tid < NH;
   int pn = 1, pa = 0;
   if(p0live) {
     pn = (int)((-1.0 + sqrt(9.0 + 8.0 * tid)) * 0.5);
@@ -422,11 +601,16 @@ __global__ void __launch_bounds__(ROT_THREADS) k_matvec_rot(const __grid_constan
   const double psa = (pa & 1) ? -1.0 : 1.0, psn = (pn & 1) ? -1.0 : 1.0;
   const int pfs = rot_offF(pn) + pa, pfa = pfs + pn + 1;
   // ---- fragment geometry of this lane ----
-  const int fr = lane >> 2, fc = lane & 3;
+  RotLane c;
+  c.warp = tid >> 5;
+  c.fr = lane >> 2;
+  c.fc = lane & 3;
+  c.cpol = c.fc & 1;
+  c.dir1 = (c.fc >> 1) != 0;
+  c.gl = (c.dir1 && c.cpol) ? -1.0 : 1.0; // direction 1 carries -1 on TM (and (-1)^deg, applied per unit)
   const int bofs = (lane >> 4) * PS + ((lane >> 2) & 3);  // B fragment: plane and position in the 32-byte row (class vectors)
   const int bofsP = (lane >> 4) * PP + ((lane >> 2) & 3); // the same for the channel buffers
-  const int cdir = fc >> 1, cpol = fc & 1;                // D fragment column pair = complex vector fc = direction * 2 + pol
-  const int d0 = a.u.dbeg[warp], d1 = a.u.dbeg[warp + 1], c0 = a.u.cbeg[warp], c1 = a.u.cbeg[warp + 1];
+  const int sofs = (c.fc >> 1) * PS + 2 * c.cpol, sofsP = (c.fc >> 1) * PP + 2 * c.cpol; // D fragment column pair -> store offsets
 
   uint64_t pol;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
@@ -455,8 +639,16 @@ __global__ void __launch_bounds__(ROT_THREADS) k_matvec_rot(const __grid_constan
     const int cur = (q - qbeg) & 1;
     const unsigned char *rec = smem + (size_t)cur * L.rec_bytes;
     const cplx *s_ph = (const cplx *)rec;
-    const double *s_Cp = (const double *)(rec + L.offCp), *s_Cm = (const double *)(rec + L.offCm);
-    const double *s_Ds = (const double *)(rec + L.offDs), *s_Da = (const double *)(rec + L.offDa);
+    c.ph = s_ph + NM;
+    c.Cp = (const double *)(rec + L.offCp) + c.fr;
+    c.Cm = (const double *)(rec + L.offCm) - NM * NM + c.fr;
+    c.Ds = (const double *)(rec + L.offDs) + c.fr;
+    c.Da = (const double *)(rec + L.offDa) + c.fr;
+    c.vb = bufA + bofs;
+    c.pb = bufB + bofsP;
+    c.pst = bufB + sofsP;
+    c.vst = bufA + sofs;
+    c.dst = acc + (size_t)(c.dir1 ? I : pi.x % I) * n2 + c.cpol * nH; // direction 1: column sums of particle j
     r_mbar_wait(&full[cur], (uint32_t)(((q - qbeg) >> 1) & 1));
     // ---- P0: phases, parity signs of the reversed direction, flip basis ----
     if(p0live) {
@@ -495,130 +687,28 @@ __global__ void __launch_bounds__(ROT_THREADS) k_matvec_rot(const __grid_constan
         load_x(xi, pnext.x);
       }
     }
-    // ---- P1: u = D^T t, channel combinations ----
-    for(int u = d0; u < d1; ++u) {
-      const int n = a.u.dn[u], m0 = a.u.dm[u];
-      double accS[2], accA[2];
-      rot_dunit(s_Ds, s_Da, bufA + bofs, n, m0, lane, accS, accA);
-      // lane (row a, vector fc): TE lanes need the partner's u_a of TM and vice versa: ch+- = u_s +- u_a(partner)
-      const double ox = __shfl_xor_sync(0xffffffffu, accA[0], 1), oy = __shfl_xor_sync(0xffffffffu, accA[1], 1);
-      const int aa = m0 + fr;
-      if(aa <= n) { // a = 0: u_a = 0, both channels equal u_s
-        double *P = bufB + cdir * PP + 4 * (rot_offP(NM, aa) + (n - rot_n0(aa))) + 2 * cpol;
-        *(cplx *)P = mk(accS[0] + ox, accS[1] + oy);
-        *(cplx *)(P + SS) = mk(accS[0] - ox, accS[1] - oy);
-      }
-    }
-    __syncthreads(); // B2
-    // ---- P2: q = C p per order a (Re and Im of C as two real DMMAs on one B fragment), back to the class vectors ----
-    for(int u = c0; u < c1; ++u) {
-      const int ca = a.u.ca[u], m0 = a.u.cm[u];
-      const int n0 = rot_n0(ca), w = NM - n0 + 1;
-      const bool rowv = m0 + fr < w;
-      const int e0 = rot_offX(NM, ca) + m0 + fr;
-      const double *Bp = bufB + bofsP + 4 * (rot_offP(NM, ca) + fc);
-      double apr[2] = {0, 0}, api[2] = {0, 0}, amr[2] = {0, 0}, ami[2] = {0, 0};
-      if(ca == 0) {
-#pragma unroll 2
-        for(int k0 = 0; k0 < w; k0 += 4) {
-          const int lc = k0 + fc;
-          const bool v = rowv && lc < w;
-          const int e = e0 + lc * w;
-          const double vr = v ? s_Cp[e] : 0.0, vi = v ? s_Cp[L.X + e] : 0.0, bp = Bp[4 * k0];
-          dmma(apr, vr, bp);
-          dmma(api, vi, bp);
-        }
-      } else {
-        const int XM = L.X - NM2;
-#pragma unroll 2
-        for(int k0 = 0; k0 < w; k0 += 4) {
-          const int lc = k0 + fc;
-          const bool v = rowv && lc < w;
-          const int e = e0 + lc * w;
-          const double vr = v ? s_Cp[e] : 0.0, vi = v ? s_Cp[L.X + e] : 0.0, bp = Bp[4 * k0];
-          const double wr = v ? s_Cm[e - NM2] : 0.0, wi = v ? s_Cm[XM + e - NM2] : 0.0, bm = Bp[SS + 4 * k0];
-          dmma(apr, vr, bp);
-          dmma(api, vi, bp);
-          dmma(amr, wr, bm);
-          dmma(ami, wi, bm);
+    rot_p1_all<NM>(c, std::make_integer_sequence<int, T.nd>{}); // P1: u = D^T t, channel combinations
+    __syncthreads();                                            // B2
+    rot_p2_all<NM>(c, std::make_integer_sequence<int, T.nc>{}); // P2: q = C p, back to the class vectors
+    __syncthreads();                                            // B3
+    rot_p3_all<NM>(c, std::make_integer_sequence<int, T.nd>{}); // P3: w = D v; P4: accumulate
+    if(pi.w & 3) { // last pair of the strip / of the segment: the finished sums go to HBM
+      __syncthreads();
+      if(pi.w & 1) {
+        cplx *cs = acc + (size_t)I * n2, *cpart = a.colpart + (size_t)pi.z * n2;
+        for(int e = tid; e < n2; e += ROT_THREADS) {
+          cpart[e] = cs[e];
+          cs[e] = mk(0, 0);
         }
       }
-      if(rowv) {
-        // complex products: (Re C p_re - Im C p_im, Re C p_im + Im C p_re); lane = (row n, channel fc = direction * 2 + family)
-        const double qpx = apr[0] - api[1], qpy = apr[1] + api[0];
-        const int n = n0 + m0 + fr, fs = rot_offF(n) + ca, fam = cpol;
-        double *V = bufA + cdir * PS;
-        if(ca == 0) { // p- = p+: v_s = q+ (TE_s from the p family, TM_s from the r family), no a class
-          *(cplx *)(V + 4 * fs + 2 * fam) = mk(qpx, qpy);
-        } else {
-          const double qmx = amr[0] - ami[1], qmy = amr[1] + ami[0];
-          const double h = (ca & 1) ? -0.5 : 0.5; // (-1)^a of the transposed small-d read, and the 1/2 of the channel split
-          *(cplx *)(V + 4 * fs + 2 * fam) = mk(h * (qpx + qmx), h * (qpy + qmy));                   // v_s: TE (p) / TM (r)
-          *(cplx *)(V + 4 * (fs + n + 1) + 2 * (1 - fam)) = mk(h * (qpx - qmx), h * (qpy - qmy)); // v_a: TM (p) / TE (r)
+      if(pi.w & 2) {
+        cplx *rp = a.rowpart + (size_t)sg * I * n2;
+        for(int e = tid; e < I * n2; e += ROT_THREADS) {
+          rp[e] = acc[e];
+          acc[e] = mk(0, 0);
         }
-      }
-    }
-    __syncthreads(); // B3
-    // ---- P3: w = D v;  P4: flip basis -> m, conjugate phase, parity signs, accumulate (owner lanes) ----
-    {
-      const bool endc = (pi.w & 1) != 0, endr = (pi.w & 2) != 0;
-      const int islot = pi.x % I;
-      for(int u = d0; u < d1; ++u) {
-        const int n = a.u.dn[u], m0 = a.u.dm[u];
-        double accS[2], accA[2];
-        rot_dunit(s_Ds, s_Da, bufA + bofs, n, m0, lane, accS, accA);
-        const int ap = m0 + fr;
-        if(ap > n)
-          continue;
-        const double sn = (n & 1) ? -1.0 : 1.0, sap = (ap & 1) ? -1.0 : 1.0;
-        const double g = cdir ? (cpol ? -sn : sn) : 1.0; // direction 1: (-1)^deg, and -1 on TM
-        const int ip = cpol * nH + flat_index(n, ap), im = cpol * nH + flat_index(n, -ap);
-        cplx op, om;
-        if(ap == 0) {
-          op = mk(g * accS[0], g * accS[1]);
-          om = op;
-        } else {
-          const double fp = g * sap * ROT_SQH, fm = g * ROT_SQH;
-          op = cmul(cconj(s_ph[NM + ap]), mk(fp * (accS[0] + accA[0]), fp * (accS[1] + accA[1])));
-          om = cmul(cconj(s_ph[NM - ap]), mk(fm * (accS[0] - accA[0]), fm * (accS[1] - accA[1])));
-        }
-        if(cdir) { // column side: sums of particle j over the strip
-          op = cadd(colacc[ip], op);
-          if(ap)
-            om = cadd(colacc[im], om);
-          if(endc) {
-            cplx *cpart = a.colpart + (size_t)pi.z * n2;
-            cpart[ip] = op;
-            colacc[ip] = mk(0, 0);
-            if(ap) {
-              cpart[im] = om;
-              colacc[im] = mk(0, 0);
-            }
-          } else {
-            colacc[ip] = op;
-            if(ap)
-              colacc[im] = om;
-          }
-        } else { // row side: sums of the block's rows over the segment
-          cplx *ra = rowacc + (size_t)islot * n2;
-          ra[ip] = cadd(ra[ip], op);
-          if(ap)
-            ra[im] = cadd(ra[im], om);
-          if(endr) {
-            cplx *rp = a.rowpart + (size_t)sg * I * n2;
-            for(int s = 0; s < I; ++s) {
-              rp[(size_t)s * n2 + ip] = rowacc[(size_t)s * n2 + ip];
-              rowacc[(size_t)s * n2 + ip] = mk(0, 0);
-              if(ap) {
-                rp[(size_t)s * n2 + im] = rowacc[(size_t)s * n2 + im];
-                rowacc[(size_t)s * n2 + im] = mk(0, 0);
-              }
-            }
-          }
-        }
-      }
-      if(endr)
         ++sg;
+      }
     }
     pi = pnext;
     double *tb = bufA;
@@ -843,55 +933,14 @@ void launch_assemble_rot(VtacTableSet const &ts, const double *xyz, cplx k, cons
   OB_CUDA(cudaGetLastError());
 }
 
-// longest-processing-time assignment of the DMMA work units to the warps
-static RotUnits const &rot_units(int NM) {
-  static RotUnits cache[OB_MAX_NMAX + 1];
-  static bool have[OB_MAX_NMAX + 1] = {false};
-  RotUnits &U = cache[NM];
-  if(have[NM])
-    return U;
-  memset(&U, 0, sizeof(U));
-  struct Unit {
-    int x, m0, cost;
-  };
-  auto assign = [&](std::vector<Unit> units, unsigned char *ux, unsigned char *um, unsigned char *beg) {
-    if(units.size() > ROT_MAX_UNITS)
-      throw Error("rotated-axial operator: too many work units");
-    std::stable_sort(units.begin(), units.end(), [](Unit const &p, Unit const &q) { return p.cost > q.cost; });
-    std::vector<std::vector<Unit>> per(ROT_WARPS);
-    int load[ROT_WARPS] = {0};
-    for(Unit const &u : units) {
-      int wmin = 0;
-      for(int w = 1; w < ROT_WARPS; ++w)
-        if(load[w] < load[wmin])
-          wmin = w;
-      per[wmin].push_back(u);
-      load[wmin] += u.cost;
-    }
-    int k = 0;
-    for(int w = 0; w < ROT_WARPS; ++w) {
-      beg[w] = (unsigned char)k;
-      for(Unit const &u : per[w]) {
-        ux[k] = (unsigned char)u.x;
-        um[k] = (unsigned char)u.m0;
-        ++k;
-      }
-    }
-    beg[ROT_WARPS] = (unsigned char)k;
-  };
-  std::vector<Unit> du, cu;
-  for(int n = 1; n <= NM; ++n)
-    for(int m0 = 0; m0 <= n; m0 += 8)
-      du.push_back({n, m0, (n + 1 + 3) / 4 + (n + 3) / 4});
-  for(int a = 0; a <= NM; ++a) {
-    const int w = NM - rot_n0(a) + 1;
-    for(int m0 = 0; m0 < w; m0 += 8)
-      cu.push_back({a, m0, ((w + 3) / 4) * (a == 0 ? 2 : 4)});
-  }
-  assign(du, U.dn, U.dm, U.dbeg);
-  assign(cu, U.ca, U.cm, U.cbeg);
-  have[NM] = true;
-  return U;
+typedef void (*RotKernel)(const RotArgs);
+template <int NM> static RotKernel rot_kernel_for(int nMax) {
+  if(nMax == NM)
+    return k_matvec_rot<NM>;
+  if constexpr(NM > 1)
+    return rot_kernel_for<NM - 1>(nMax);
+  else
+    throw Error("rotated-axial operator: nMax out of range");
 }
 
 void launch_matvec_rot(RotPlan const &p, RotLayout const &L, const unsigned char *recs, const cplx *x, const cplx *Tdiag,
@@ -899,8 +948,9 @@ void launch_matvec_rot(RotPlan const &p, RotLayout const &L, const unsigned char
   if(e0)
     cudaEventRecord(e0, st);
   if(p.npairs > 0) {
-    OB_CUDA(cudaFuncSetAttribute((const void *)k_matvec_rot, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-    OB_CUDA(cudaFuncSetAttribute((const void *)k_matvec_rot, cudaFuncAttributePreferredSharedMemoryCarveout,
+    RotKernel kern = rot_kernel_for<OB_MAX_NMAX>(L.NM); // one instantiation per nMax: every index is an immediate
+    OB_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    OB_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared));
     RotArgs a;
     a.recs = recs;
@@ -912,8 +962,7 @@ void launch_matvec_rot(RotPlan const &p, RotLayout const &L, const unsigned char
     a.colpart = p.colpart;
     a.L = L;
     a.I = p.I;
-    a.u = rot_units(L.NM);
-    k_matvec_rot<<<p.grid, p.threads, p.smem, st>>>(a);
+    kern<<<p.grid, p.threads, p.smem, st>>>(a);
     OB_CUDA(cudaGetLastError());
   }
   if(e1)

@@ -17,12 +17,11 @@
 
 namespace ob {
 
-__host__ __device__ inline int rot_n0(int mu) { return mu > 1 ? mu : 1; }
-__host__ __device__ inline int rot_offX(int NM, int mu) { // sum_{u<mu} (NM - max(u,1) + 1)^2
-  if(mu <= 0)
-    return 0;
-  const int a = NM, b = NM - mu + 1; // sum_{s=b+1}^{a} s^2
-  return NM * NM + (a * (a + 1) * (2 * a + 1) / 6 - b * (b + 1) * (2 * b + 1) / 6);
+__host__ __device__ constexpr inline int rot_n0(int mu) { return mu > 1 ? mu : 1; }
+__host__ __device__ constexpr inline int rot_offX(int NM, int mu) { // sum_{u<mu} (NM - max(u,1) + 1)^2
+  // mu >= 1: NM^2 + sum_{s = NM - mu + 2}^{NM} s^2
+  return mu <= 0 ? 0
+                 : NM * NM + (NM * (NM + 1) * (2 * NM + 1) / 6 - (NM - mu + 1) * (NM - mu + 2) * (2 * (NM - mu + 1) + 1) / 6);
 }
 __host__ __device__ inline double ta_a_plus(int n, int m) {
   return -sqrt((double)((n + m + 1) * (n - m + 1)) / (double)((2 * n + 1) * (2 * n + 3)));
