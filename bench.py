@@ -9,17 +9,19 @@ A "step" is one pass of the hot path over one synthetic cluster at one wavelengt
 SH GMRES) + the Result cross sections -- what Simulation::scan_wavelengths does per wavelength
 (srcAna/Simulation.cpp:643-667).
 
-Workload (BASELINE.json configs[3], the largest single-GPU configuration; C5 needs 8 GPUs for its dense
-921.6 GB matrix): 200 Si spheres r = 50 nm on the first 200 sites of the 190 nm cubic lattice of
-examples/ManyParticles.xml, nMax = 8, lambda = 800 nm, theta = 45, phi = 90, E_theta = 1, FH + SH, dense
-operator, Belos-style GMRES tol 1e-5 / restart 30 / <= 20 restarts.  The same total work is used at every
-N (strong scaling); rows of particles are sharded across ranks.  `--workload c5` runs the 1000-sphere
-nMax = 10 cluster (8 GPUs).
+Workload (default, BASELINE.json configs[4] = the north-star target): C5, 1000 Si spheres r = 50 nm, centres uniform
+random in a (2200 nm)^3 cube by sequential rejection (minimum distance 150 nm, std::mt19937_64 seed 20261017),
+nMax = nMaxS = 10, lambda = 800 nm, theta = 45, phi = 90, E_theta = 1, FH + SH, Belos-style GMRES tol 1e-5 /
+restart 30 / <= 20 restarts.  The same total work is used at every N (strong scaling); the pair list is sharded
+across ranks.  `--workload c4` runs configs[3] (200 spheres on the 190 nm lattice, nMax 8).
 
-Operator form: `--operator pairs` (default) streams the compact pair form (unscaled A^T, B^T of the pairs
-i < j: 4.08 GB per harmonic on C4), `--operator dense` the reference's full slab (16.4 GB).  Either is far
-larger than the 126 MB L2, so consecutive matvecs / steps cannot hit in L2 (config.l2: "inputs larger than
-L2").  The roofline numerator is the bytes of the form actually streamed.
+Operator form: `--operator rot` (default) is the rotated-axial form (csrc/ob_rot.cu): exact, 21.4 KB per unordered
+pair at nMax 10 (10.7 GB per harmonic on C5: fits ONE GPU and every N), applied on the FP64 tensor core.
+`--operator pairs` streams the compact pair form with TMA (unscaled A^T, B^T of the pairs i < j, 460.8 KB per pair:
+230 GB per harmonic on C5, needs >= 2 GPUs), `--operator dense` the reference's full slab.  Every form is far larger
+than the 126 MB L2, so consecutive matvecs / steps cannot hit in L2 (config.l2: "inputs larger than L2").  The roofline
+numerator is the bytes of the form actually streamed; the TMA-streamed pair-form kernel the north
+star names is measured beside it on a C5 sub-cluster that fits (`roofline_pairs`).
 """
 import argparse
 import ctypes as C
@@ -44,16 +46,16 @@ def workload(name):
              ("Maximum Restarts", "int", "20")]
     if name == "c4":
         xyz = xmlgen.cube_sites(7, 200, 190.0)
-        return dict(name="C4: 200 Si spheres r=50nm, 190nm cubic lattice (first 200 sites), nMax=8, 800nm, FH+SH, dense",
-                    xml=xmlgen.cluster_xml(xyz, 50.0, 8, 800.0, belos=belos), nobj=200, nMax=8)
+        return dict(name="C4: 200 Si spheres r=50nm, 190nm cubic lattice (first 200 sites), nMax=8, 800nm, FH+SH",
+                    xml=xmlgen.cluster_xml(xyz, 50.0, 8, 800.0, belos=belos), nobj=200, nMax=8, xyz_nm=xyz, belos=belos)
     if name == "c5":
         xyz = xmlgen.random_sites(1000, 2200.0, 150.0, 20261017)
-        return dict(name="C5: 1000 Si spheres r=50nm, random in (2200nm)^3 (std::mt19937_64 seed 20261017, min distance 150nm), nMax=10, 800nm, FH+SH, dense",
-                    xml=xmlgen.cluster_xml(xyz, 50.0, 10, 800.0, belos=belos), nobj=1000, nMax=10)
+        return dict(name="C5: 1000 Si spheres r=50nm, random in (2200nm)^3 (std::mt19937_64 seed 20261017, min distance 150nm), nMax=10, 800nm, FH+SH",
+                    xml=xmlgen.cluster_xml(xyz, 50.0, 10, 800.0, belos=belos), nobj=1000, nMax=10, xyz_nm=xyz, belos=belos)
     if name == "small":
         xyz = xmlgen.cube_sites(3, 27, 190.0)
         return dict(name="small: 27 Si spheres, nMax=6 (smoke-sized)", xml=xmlgen.cluster_xml(xyz, 50.0, 6, 800.0, belos=belos),
-                    nobj=27, nMax=6)
+                    nobj=27, nMax=6, xyz_nm=xyz, belos=belos)
     raise SystemExit("unknown workload " + name)
 
 
@@ -113,79 +115,165 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_reference_time(wl, threads, iters_ff, iters_sh, sample_rows=None, repeat=1):
-    """The reference's CPU path (oracle port, all host threads) on a bounded sample of the workload,
-    scaled to the full workload: assembly per block-row, matvec per byte, SH source per particle."""
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def _oracle_case(wl, nobj=None):
+    """The workload as an oracle case, built from the generator's own arrays (no product library is loaded)."""
     from oracle import oracle as O
-    from optimet_b200 import host as H
-    O.set_threads(threads)
-    case = H.Case(xml=wl["xml"])
-    a = case.arrays()
-    info = case.info()
-    nobj, nMax = info["nobj"], info["nMax"]
+    orc = O.Case()
+    xyz = np.asarray(wl["xyz_nm"], dtype=float)[: (nobj or wl["nobj"])]
+    for p in xyz:
+        orc.add_sphere([float(v) * 1e-9 for v in p], 50e-9, wl["nMax"], O.MODEL_SILICON, [1.0, 0.0])
+    orc.set_source(800e-9, np.deg2rad(45.0), np.deg2rad(90.0), 1.0, 0.0, True)
+    return orc
+
+
+def cpu_reference(wl, threads, iters_ff, iters_sh, full=False, light=False):
+    """The reference's CPU path on the box's host cores, per phase with a steady clock.
+
+    The reference itself cannot be built here as a program (Eigen / Boost / GSL / HDF5 / Trilinos absent, DESIGN.md
+    section 2): the arm is the oracle port (checked against 16 compiled translation units of the reference) with the
+    per-block assembly rate of the reference's OWN compiled Coupling (oracle/_ref/libpath_ref.so) reported beside it.
+    full: one complete unsampled step (C4-sized workloads only: the dense matrices must fit host memory).
+    Otherwise a bounded sample: FF assembly of `threads` block-rows, three products with that slab, the whole FF
+    source, the SH source on `threads` particles; scaled to the workload with the GPU run's iteration counts and
+    labelled extrapolated.  Variants: serial vs all threads; as-shipped (dense T multiply, Bessel calls inside the
+    SH-source loops, as the reference has them) vs optimised (both removed)."""
+    from oracle import oracle as O
+    nobj, nMax = wl["nobj"], wl["nMax"]
     n2 = 2 * nMax * (nMax + 2)
     N = n2 * nobj
-    orc = O.Case()
-    for j in range(nobj):
-        orc.add_sphere(list(a["xyz"][j]), float(a["radius"][j]), nMax, O.MODEL_SILICON, [1.0, 0.0])
-    orc.set_source(info["wavelength"], np.deg2rad(45.0), np.deg2rad(90.0), 1.0, 0.0, True)
-    rows = sample_rows if sample_rows is not None else max(1, min(threads, nobj))
-    t_asm = t_mv = t_src = t_sh = 0.0
+    clock = time.perf_counter
+    phases, variants = {}, {}
+    O.set_threads(threads)
+    O.set_as_shipped(0, 0)
+    if full:
+        orc = _oracle_case(wl)
+        t0 = clock()
+        orc.solve(O.SOLVER_BELOS, tol=1e-5, maxit=600, restart=30, max_restarts=20)
+        cs = orc.cross_sections()
+        total = clock() - t0
+        it = orc.iters()
+        sample = ("one complete unsampled step of the oracle port on %d threads (update + FF solve + SH source + SH solve + "
+                  "cross sections, Belos-style GMRES %s iterations, C_ext %.12e)" % (threads, list(it), cs["ext"]))
+        return dict(value=total, cores=threads, kind="port", sample=sample, extrapolated=False, cpu_model=cpu_model(),
+                    phases_s={"step": total}, variants={})
+    rows = max(1, min(threads, nobj))
+    nsub = min(nobj, 120 if light else 400)  # the sample's cluster: the first nsub spheres (per-block and per-byte rates
+    wls = dict(wl, nobj=nsub)                # do not depend on the cluster size)
+    orc = _oracle_case(wls)
+    Ns = n2 * nsub
+    t0 = clock()
+    S = orc.matrix(1, 0, rows)  # rows block-rows x all columns of the sample cluster, threads over block-rows
+    phases["assembly_ff_sample"] = clock() - t0
+    x = np.ones(Ns, dtype=np.complex128)
     nmv = 3
-    for _ in range(repeat):
-        t0 = time.perf_counter()
-        S = orc.matrix(1, 0, rows)  # rows block-rows x all columns, threads over block-rows
-        t_asm += time.perf_counter() - t0
-        x = np.ones(N, dtype=np.complex128)
-        t0 = time.perf_counter()
-        for _ in range(nmv):
-            O.matvec(S, x)
-        t_mv += (time.perf_counter() - t0) / nmv
-        t0 = time.perf_counter()
-        orc.source()
-        t_src += time.perf_counter() - t0
-    t_asm, t_mv, t_src = t_asm / repeat, t_mv / repeat, t_src / repeat
-    # a sample of the same blocks on the reference's OWN compiled Coupling (oracle/_ref/libpath_ref.so, built from the
-    # reference sources; single thread: its f2c'd AMOS keeps static state and is not thread-safe)
-    ref_note = ""
+    t0 = clock()
+    for _ in range(nmv):
+        O.matvec(S, x)
+    phases["matvec_sample"] = (clock() - t0) / nmv
+    slab_rows = S.shape[0]
+    del S
+    t0 = clock()
+    orc.source()
+    phases["source_ff_sample"] = clock() - t0
+    orc2 = _oracle_case(wl, rows)
+    xi = np.ones(n2 * rows, dtype=np.complex128) * 1e-3
+    t0 = clock()
+    orc2.sh_source(xi)  # first call builds the CG tables (once per run in the reference, not part of a step)
+    t_first = clock() - t0
+    t0 = clock()
+    orc2.sh_source(xi)
+    phases["source_sh_sample"] = clock() - t0
+    phases["cg_tables_once"] = max(0.0, t_first - phases["source_sh_sample"])
+    blocks_sample, blocks_all = rows * (nsub - 1), nobj * (nobj - 1)
+    asm = phases["assembly_ff_sample"] * blocks_all / blocks_sample
+    mv = phases["matvec_sample"] * (float(N) * N) / (float(slab_rows) * Ns)
+    src = phases["source_ff_sample"] * nobj / nsub
+    scale = nobj / float(rows)
+    total = 2 * asm + (iters_ff + iters_sh + 2) * mv + src + phases["source_sh_sample"] * scale
+    phases.update({"assembly_per_harmonic_scaled": asm, "matvec_per_apply_scaled": mv, "source_ff_scaled": src,
+                   "source_sh_scaled": phases["source_sh_sample"] * scale})
+    phases["source_ff"] = src
+    per_block_port = phases["assembly_ff_sample"] * min(threads, rows) / blocks_sample
+    # per-block rates: the reference's own compiled Coupling and the port, one thread, same blocks
+    xyz = np.asarray(wl["xyz_nm"], dtype=float) * 1e-9
+    k = complex(orc.info()["waveK"])
+    jobs = [(0, j) for j in range(1, min(nobj, 17 if light else 65))]
+
+    def per_block(fn):
+        t0 = clock()
+        for i, j in jobs:
+            d = xyz[i] - xyz[j]
+            r = float(np.linalg.norm(d))
+            fn([r, float(np.arccos(d[2] / r)), float(np.arctan2(d[1], d[0]))], k, nMax, True)
+        return (clock() - t0) / len(jobs)
+    variants["port_coupling_ms_per_block_1thread"] = per_block(O.coupling) * 1e3
+    kind = "port"
     try:
         from oracle import reference_build as RB
         if RB.have():
-            k = complex(orc.info()["waveK"])
-            xyz = np.asarray(a["xyz"], dtype=float)
-            jobs = [(0, j) for j in range(1, min(nobj, 65))]
-            t0 = time.perf_counter()
-            for i, j in jobs:
-                d = xyz[i] - xyz[j]
-                r = float(np.linalg.norm(d))
-                RB.coupling([r, float(np.arccos(d[2] / r)), float(np.arctan2(d[1], d[0]))], k, nMax, True)
-            per_block = (time.perf_counter() - t0) / max(1, len(jobs))
-            ref_note = ("; the reference's own compiled Coupling takes %.1f ms per block on one thread (%d blocks timed; "
-                        "the port: %.1f ms per block and thread)"
-                        % (per_block * 1e3, len(jobs), t_asm * min(threads, rows) / (rows * (nobj - 1)) * 1e3))
+            variants["reference_build_coupling_ms_per_block_1thread"] = per_block(RB.coupling) * 1e3
+            kind = "reference-build+port"
     except Exception:
         pass
-    # SH source: per particle cost from the oracle on `rows` particles is not separable through the case API;
-    # time the whole SH source once on a reduced cluster of `rows` particles
-    orc2 = O.Case()
-    for j in range(rows):
-        orc2.add_sphere(list(a["xyz"][j]), float(a["radius"][j]), nMax, O.MODEL_SILICON, [1.0, 0.0])
-    orc2.set_source(info["wavelength"], np.deg2rad(45.0), np.deg2rad(90.0), 1.0, 0.0, True)
-    xi = np.ones(n2 * rows, dtype=np.complex128) * 1e-3
-    orc2.sh_source(xi)  # builds the CG tables (once per run in the reference, not counted per step)
-    t0 = time.perf_counter()
-    orc2.sh_source(xi)
-    t_sh = time.perf_counter() - t0
-    scale = nobj / float(rows)
-    total = (2 * t_asm * scale                      # FF + SH assembly
-             + (iters_ff + iters_sh + 2) * t_mv * scale  # matvecs (+1 initial residual each)
-             + t_src                                 # FF source (all particles)
-             + t_sh * scale)                         # SH source
-    sample = ("oracle port, %d threads: FF assembly of %d of %d block-rows (%.2fs), %d matvecs on that %dx%d slab "
-              "(%.3fs each), FF source (%.2fs), SH source on %d particles (%.2fs); scaled to the full workload with "
-              "the GPU run's GMRES iteration counts (%d FF + %d SH)%s"
-              % (threads, rows, nobj, t_asm, nmv, n2 * rows, N, t_mv, t_src, rows, t_sh, iters_ff, iters_sh, ref_note))
-    return total, sample
+    # serial (the reference's dompi=OFF build, Solver.cpp:32-34): the same sample on one thread, smaller
+    O.set_threads(1)
+    t0 = clock()
+    S1 = orc.matrix(1, 0, 1)
+    t_row = clock() - t0
+    t0 = clock()
+    O.matvec(S1, x)
+    t_mv1 = clock() - t0
+    variants["serial_step_s_scaled"] = (2 * t_row * blocks_all / (nsub - 1) + (iters_ff + iters_sh + 2) * t_mv1 * (float(N) * N) / (float(S1.shape[0]) * Ns)
+                                        + (src + phases["source_sh_scaled"]) * min(threads, rows))
+    del S1
+    # as-shipped: dense T multiply in the assembly, Bessel calls inside the SH-source loops
+    O.set_threads(threads)
+    O.set_as_shipped(1, 1)
+    try:
+        t0 = clock()
+        orc.matrix(1, 0, rows)
+        variants["as_shipped_assembly_per_harmonic_s_scaled"] = (clock() - t0) * blocks_all / blocks_sample
+        orc3 = _oracle_case(wl, 1)
+        x1 = np.ones(n2, dtype=np.complex128) * 1e-3
+        if nMax <= 8:
+            orc3.sh_source(x1)
+            t0 = clock()
+            orc3.sh_source(x1)
+            variants["as_shipped_source_sh_s_scaled"] = (clock() - t0) * nobj / float(threads)
+    finally:
+        O.set_as_shipped(0, 0)
+    sample = ("oracle port (optimised variant), %d threads over particle block-rows, on the first %d of the %d spheres: FF "
+              "assembly of %d block-rows = %d blocks (%.2f s), %d products with that %d x %d slab (%.3f s each), the FF source "
+              "(%.2f s), the SH source on %d particles (%.2f s); scaled per block (x %d / %d), per matrix byte and per particle "
+              "to the workload, with the GPU run's GMRES iteration counts (%d FF + %d SH, +1 product each for the initial "
+              "residual).  The workload's dense matrix (%.1f GB per harmonic) cannot be assembled on the host in bounded "
+              "time: the value is an EXTRAPOLATION from these measured rates (`--full-cpu` runs one complete unsampled step "
+              "of a C4-sized workload instead).  Per block and thread the port costs %.1f ms in this sample; the serial and "
+              "as-shipped variants and the reference's own compiled Coupling per block are under cpu_baseline.variants; the "
+              "iteration counts are the GPU run's (Belos semantics restated from its documentation, parity-unpinned)"
+              % (threads, nsub, nobj, rows, blocks_sample, phases["assembly_ff_sample"], nmv, slab_rows, Ns,
+                 phases["matvec_sample"], phases["source_ff_sample"], rows, phases["source_sh_sample"], blocks_all, blocks_sample,
+                 iters_ff, iters_sh, 16.0 * N * N / 1e9, per_block_port * 1e3))
+    return dict(value=total, cores=threads, kind=kind, sample=sample, extrapolated=True, cpu_model=cpu_model(),
+                phases_s=phases, variants=variants)
+
+
+def bench_config(wl, operator):
+    """The keys both arms print under `config` (the driver compares them)."""
+    nobj, nMax = wl["nobj"], wl["nMax"]
+    return {"workload": wl["name"], "N": 2 * nMax * (nMax + 2) * nobj, "gmres": "belos tol=1e-5 restart=30",
+            "l2": "inputs larger than L2", "operator": operator}
 
 
 def main():
@@ -194,14 +282,17 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c4")
+    ap.add_argument("--workload", default="c5")
     ap.add_argument("--matvec-variant", type=int, default=None)
-    ap.add_argument("--operator", default="pairs", choices=["pairs", "dense", "aca", "rot"],
-                    help="pairs: compact A^T/B^T-of-i<j form (default); dense: the reference's full slab; "
-                         "aca: the reference's ACA-compressed operator (eps 1e-3; results differ at that level); "
-                         "rot: rotated-axial form (exact; phases + axial A/B + Wigner small-d per pair, csrc/ob_rot.cu)")
+    ap.add_argument("--operator", default="rot", choices=["pairs", "dense", "aca", "rot"],
+                    help="rot: rotated-axial form (default; exact; phases + axial A+-B + flip-basis Wigner small-d per pair, "
+                         "csrc/ob_rot.cu, fits every N); pairs: compact A^T/B^T-of-i<j form, TMA-streamed (C5 needs >= 2 GPUs); "
+                         "dense: the reference's full slab; aca: the reference's ACA-compressed operator (eps 1e-3; results "
+                         "differ at that level)")
+    ap.add_argument("--full-cpu", action="store_true",
+                    help="--impl reference: one complete unsampled CPU step (C4-sized workloads; needs ~40 GB of host memory)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-alt", action="store_true", help="skip the extra end-to-end steps in the rotated-axial form")
+    ap.add_argument("--no-alt", action="store_true", help="skip the side measurement of the TMA-streamed pair-form matvec")
     ap.add_argument("--opt", action="append", default=[], help="library tuning option name=value (ob_set_option)")
     args = ap.parse_args()
 
@@ -214,28 +305,27 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        # the reference's own CPU implementation of the path (oracle port; the reference itself cannot be built
-        # here: Eigen/Boost/GSL/HDF5 absent), all host threads, bounded sample per step
+        # the reference's own CPU implementation of the path on the host cores (see cpu_reference); no product library
+        # is imported or loaded by this arm
         iters = (30, 30)
         p = os.path.join(ROOT, "profiles", "last_iters_%s.json" % args.workload)
         if os.path.exists(p):
             with open(p) as f:
                 d = json.load(f)
                 iters = (d["iters_ff"], d["iters_sh"])
-        for _ in range(max(0, min(args.warmup, 1))):
-            cpu_reference_time(wl, threads, *iters, sample_rows=1)
-        vals = []
-        sample = ""
-        for _ in range(max(1, min(args.steps, 3))):
-            v, sample = cpu_reference_time(wl, threads, *iters)
-            vals.append(v)
-        v = float(np.mean(vals))
+        if args.warmup > 0 and not args.full_cpu:
+            cpu_reference(wl, threads, *iters, light=True)
+        r = cpu_reference(wl, threads, *iters, full=args.full_cpu)
+        v = r["value"]
         print(json.dumps({
             "impl": "reference", "metric": "time_to_solution_s", "value": v, "unit": "s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": v * 1e3, "higher_is_better": False,
             "scaling": "strong", "vs_baseline": None, "dtype": "c128 (complex FP64)", "data": "synthetic",
-            "config": {"workload": wl["name"], "l2": "inputs larger than L2"},
-            "cpu_baseline": {"value": v, "unit": "s", "cores": threads, "kind": "port", "sample": sample},
+            "config": bench_config(wl, args.operator),
+            "extrapolated": r["extrapolated"],
+            "cpu_baseline": {"value": v, "unit": "s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+                             "extrapolated": r["extrapolated"], "cpu_model": r["cpu_model"], "phases_s": r["phases_s"],
+                             "variants": r["variants"]},
             "e2e": {"value": v, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return 0
 
@@ -324,32 +414,33 @@ def main():
     e2e_per_step = float(e2e_ms.item()) / args.steps
     clocks = sampler.stop() if sampler else None
 
-    # ---------------- extra (not the headline): the same end-to-end steps in the rotated-axial operator form ----------------
-    # (csrc/ob_rot.cu: exact, 12-15x fewer operator bytes than the pair form; bound by shared-memory wavefronts rather
-    # than HBM, so it is reported beside the TMA-streamed pair form the north star specifies, not instead of it)
-    alt = None
-    if args.operator == "pairs" and not args.no_alt:
-        solver.set_option("operator", 3)
-        for _ in range(max(1, args.warmup)):
-            r2 = solver.step(fetch=True)
-        barrier()
-        lib.ob_timer(ctx, 0, None)
-        for _ in range(args.steps):
-            r2 = solver.step(fetch=True)
-        lib.ob_timer(ctx, 1, C.byref(ms))
-        barrier()
-        a_ms = torch.tensor([ms.value], dtype=torch.float64, device="cuda")
-        cs2 = torch.tensor([r2[k] for k in ("ext", "sca", "abs", "sca_SH", "abs_SH")], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(a_ms, op=dist.ReduceOp.MAX)
-            dist.all_reduce(cs2, op=dist.ReduceOp.SUM)
-        tm2 = solver.ctx_timings()
-        alt = {"operator": "rot (phases + axial A/B + Wigner small-d per pair, k_matvec_rot)",
-               "e2e_ms_per_step": float(a_ms.item()) / args.steps,
-               "matvec_ms_per_apply": tm2["matvec_ms"] / max(1.0, tm2["matvec_count"]),
-               "operator_bytes_per_apply": tm2["operator_bytes"], "iters_ff": r2["iters_ff"], "iters_sh": r2["iters_sh"],
-               "cross_sections": [float(v) for v in cs2.tolist()]}
-        solver.set_option("operator", 1)
+    # ---------------- side measurement (not in the timed step): the TMA-streamed pair-form matvec of the north star -------
+    # k_matvec_pairs on the first `sub` spheres of the same cluster (the pair form of all of C5 is 230 GB per harmonic and
+    # does not fit one GPU; 300 spheres = 44 850 pairs = 20.7 GB), assembled by k_assemble_pairs, 12 products, CUDA events
+    # around the streaming kernel on the library's stream
+    pairs_side = None
+    if world == 1 and args.operator == "rot" and not args.no_alt:
+        mainctx = solver.ctx()
+        mainctx.release_matrix(1)
+        mainctx.release_matrix(2)
+        sub = min(nobj, 300)
+        case2 = H.Case(xml=xmlgen.cluster_xml(wl["xyz_nm"][:sub], 50.0, nMax, 800.0, belos=wl["belos"]))
+        s2 = H.Solver(case2, device=local_rank)
+        s2.set_option("operator", 1)
+        c2 = s2.ctx()
+        s2.step(fetch=False)  # configures the context and assembles both harmonics in the pair form
+        xx = np.ones(n2 * sub, dtype=np.complex128)
+        c2.matvec(1, xx)
+        c2.set_option("reset_timings", 1)
+        for _ in range(12):
+            c2.matvec(1, xx)
+        tm2 = s2.ctx_timings()
+        ms2 = tm2["matvec_ms"] / max(1.0, tm2["matvec_count"])
+        pairs_side = {"kernel": "k_matvec_pairs (TMA-streamed complex-FP64 pair-form block matvec, the north-star operator kernel)",
+                      "workload": "first %d spheres of the same cluster, nMax %d, FF operator" % (sub, nMax),
+                      "algorithmic_bytes_per_launch": tm2["operator_bytes"], "avg_launch_ms": ms2, "launches_timed": tm2["matvec_count"],
+                      "achieved": tm2["operator_bytes"] / (ms2 * 1e-3) / 1e9, "unit": "GB/s"}
+        s2.close()
 
     # cross sections are per-rank partial sums over the rank's own particles (linear): add them up
     cs_t = torch.tensor([res[k] for k in ("ext", "sca", "abs", "sca_SH", "abs_SH")], dtype=torch.float64, device="cuda")
@@ -361,11 +452,9 @@ def main():
         dist.all_reduce(mv_t, op=dist.ReduceOp.MAX)
 
     if rank == 0:
-        if alt is not None:
-            ref_cs = [float(v) for v in cs_t.tolist()]
-            alt["max_rel_diff_of_cross_sections_vs_headline_form"] = max(
-                abs(a_ / b_ - 1.0) for a_, b_ in zip(alt["cross_sections"], ref_cs) if b_ != 0.0)
         peak, peak_src = measured_peaks()
+        if pairs_side is not None:
+            pairs_side.update({"bound": "hbm", "peak": peak, "frac": pairs_side["achieved"] / peak, "peak_source": peak_src})
         m_loc = n2 * count
         # dense 16 M_loc N + 32 N per apply; pair form 32 n^2 per local pair + 32 N
         # (= 4 N^2 (1 - 1/N_obj) + 32 N on one GPU), reported by the library for the form actually streamed
@@ -379,35 +468,62 @@ def main():
             pass
         h2d = (3 + 1) * 8 * nobj + 7 * 16 * nobj + 2 * 16 * (n2 // 2)
         d2h = 4 * 16 * N + 5 * 8
+        fp64 = C.c_double()
+        lib.ob_measure_fp64_peak(ctx, C.byref(fp64))
+        cfg = bench_config(wl, args.operator)
+        kernel_names = {"pairs": "k_matvec_pairs (TMA-streamed complex-FP64 pair-form block matvec)",
+                        "dense": "k_matvec (TMA-streamed complex-FP64 dense block matvec)",
+                        "aca": "k_matvec_aca (complex-FP64 U(Vx) low-rank + dense near blocks)",
+                        "rot": "k_matvec_rot<nMax> (rotated-axial form: records streamed by TMA bulk copies, applied with "
+                               "DMMA.8x8x4 on the FP64 tensor core)"}
+        roof = {"bound": "hbm", "kernel": kernel_names[args.operator], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "peak_source": peak_src, "traffic": None, "algorithmic_bytes_per_launch": mv_bytes,
+                "avg_launch_ms": float(mv_t.item())}
+        if args.operator == "rot":
+            # algorithmic FP64 work of one pair: two small-d phases (8 real columns per stored real)
+            # and the axial phase (complex x complex = 4 real FMA; 8 channels, 4 for a = 0)
+            NMv = nMax
+            nDs = sum((j + 1) ** 2 for j in range(1, NMv + 1))
+            nDa = sum(j * j for j in range(1, NMv + 1))
+            w = lambda a_: NMv - max(a_, 1) + 1
+            fma = 16 * (nDs + nDa) + 16 * w(0) ** 2 + 32 * sum(w(a_) ** 2 for a_ in range(1, NMv + 1))
+            tf = 2.0 * fma * (nobj * (nobj - 1) // 2 / world) / (float(mv_t.item()) * 1e-3) / 1e12
+            roof["fp64"] = {"algorithmic_fma_per_pair": fma, "achieved_tflops": tf, "peak_tflops_dfma_measured": fp64.value,
+                            "frac_of_fp64_peak": tf / fp64.value if fp64.value else None,
+                            "note": "HBM is the higher floor (record bytes / peak bandwidth > algorithmic flops / FP64 peak), so it "
+                                    "is the stated bound; the measured limiter is the shared-memory pipe (profiles/)"}
         out = {
             "metric": "time_to_solution_s", "value": ms_per_step / 1e3, "unit": "s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": False,
             "scaling": "strong", "vs_baseline": None, "dtype": "c128 (complex FP64)", "data": "synthetic",
-            "config": {"workload": wl["name"], "N": N, "rows_per_gpu": m_loc, "gmres": "belos tol=1e-5 restart=30",
-                       "iters_ff": st[0], "iters_sh": st[1], "l2": "inputs larger than L2",
-                       "operator": args.operator,
-                       "phases_ms_per_step": {k: acc[k] / args.steps for k in acc
-                                              if k not in ("matvec_count", "launches", "operator_bytes")
-                                              and not (k.startswith("trace_") and acc[k] == 0)},
-                       "matvecs_per_step": acc["matvec_count"] / args.steps,
-                       "cross_sections": dict(zip(["ext", "sca", "abs", "sca_SH", "abs_SH"], [float(x) for x in cs_t.tolist()])),
-                       "wall_s_resident_arm": wall},
+            "config": cfg,
+            "run": {"rows_per_gpu": m_loc, "iters_ff": st[0], "iters_sh": st[1],
+                    "gmres_parity": "iteration counts +-1 against the oracle's restatement of Belos GMRES (Trilinos absent: "
+                                    "DGKS / implicit-residual defaults from its documentation, parity-unpinned)",
+                    "phases_ms_per_step": {k: acc[k] / args.steps for k in acc
+                                           if k not in ("matvec_count", "launches", "operator_bytes")
+                                           and not (k.startswith("trace_") and acc[k] == 0)},
+                    "matvecs_per_step": acc["matvec_count"] / args.steps,
+                    "nvlink_bytes_per_matvec_per_rank": (16.0 * N if world > 1 else 0.0),
+                    "cross_sections": dict(zip(["ext", "sca", "abs", "sca_SH", "abs_SH"], [float(x) for x in cs_t.tolist()])),
+                    "wall_s_resident_arm": wall},
             "clocks": clocks,
             "e2e": {"value": e2e_per_step / 1e3, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(acc["launches"]),
-            "alt_operator": alt,
-            "roofline": {"bound": "hbm", "kernel": {"pairs": "k_matvec_pairs (TMA-streamed complex-FP64 pair-form block matvec)",
-                                                    "dense": "k_matvec (TMA-streamed complex-FP64 dense block matvec)",
-                                                    "aca": "k_matvec_aca (complex-FP64 U(Vx) low-rank + dense near blocks)",
-                                                    "rot": "k_matvec_rot (rotation - axial translation - rotation per pair; FP64 latency bound, not HBM)"}[args.operator],
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": peak_src, "traffic": None,
-                         "algorithmic_bytes_per_launch": mv_bytes, "avg_launch_ms": float(mv_t.item())},
+            "roofline": roof,
+            "roofline_pairs": pairs_side,
         }
         # assembly (north_star: "achieved FP64 FLOP/s against B200 FP64 peak" + store bandwidth).  Algorithmic flops per
         # VTAC block from SURVEY.md section 8(d) (replay count of the reference recursion); one block per unit
         # processed: a pair in the pair form, an off-diagonal block in the dense form.
         F = {3: 15.8e3, 6: 154.5e3, 8: 427.3e3, 10: 960.5e3, 12: 1883.6e3}.get(nMax)
+        if args.operator == "rot":
+            # the axial-only recursion (csrc/ob_rot_axial.cuh) does O(nMax^3) work per pair, not the reference's O(nMax^4):
+            # same per-item counts as SURVEY.md section 8(d) (12 flops per recursion step, 20 per seed, 12 per A or B entry)
+            # over the entries it actually computes, plus 6 flops per small-d entry
+            rec_items = sum((n_ + 1) * (2 * nMax - n_ + 1) for n_ in range(1, nMax + 1))
+            F = 12.0 * rec_items + 20.0 * (2 * nMax + 1) + 24.0 * nMax * sum(n_ + 1 for n_ in range(1, nMax + 1)) + \
+                6.0 * 2 * sum((nMax - max(a_, b_) + 1) for a_ in range(nMax + 1) for b_ in range(nMax + 1))
         asm_ms = 0.5 * (acc["assemble_ff"] + acc["assemble_sh"]) / args.steps
         if args.operator == "pairs":
             units = nobj * (nobj - 1) // 2 // world
@@ -422,9 +538,7 @@ def main():
         else:
             units = count * (nobj - 1)
             asm_bytes = 16.0 * n2 * n2 * count * nobj
-        fp64 = C.c_double()
-        lib.ob_measure_fp64_peak(ctx, C.byref(fp64))
-        out["assembly"] = {"kernel": {"pairs": "k_assemble_pairs", "dense": "k_assemble", "rot": "k_assemble_axial + k_rot_tables",
+        out["assembly"] = {"kernel": {"pairs": "k_assemble_pairs", "dense": "k_assemble", "rot": "k_assemble_axial_only + k_rot_tables",
                                       "aca": "k_assemble + k_aca_compress + pack"}[args.operator],
                            "ms_per_harmonic": asm_ms, "units_per_launch": units, "stored_bytes_per_launch": asm_bytes,
                            "store_GBps": asm_bytes / (asm_ms * 1e-3) / 1e9,
@@ -433,8 +547,10 @@ def main():
                            "fp64_peak_tflops_measured": fp64.value,
                            "frac_of_fp64_peak": (units * F / (asm_ms * 1e-3) / 1e12 / fp64.value) if F else None}
         if world == 1 and not args.no_cpu_baseline:
-            v, sample = cpu_reference_time(wl, threads, st[0], st[1])
-            out["cpu_baseline"] = {"value": v, "unit": "s", "cores": threads, "kind": "port", "sample": sample}
+            r = cpu_reference(wl, threads, st[0], st[1], light=True)
+            out["cpu_baseline"] = {"value": r["value"], "unit": "s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+                                   "extrapolated": r["extrapolated"], "cpu_model": r["cpu_model"], "phases_s": r["phases_s"],
+                                   "variants": r["variants"]}
         tr = os.path.join(ROOT, "profiles", "traffic_matvec.json")
         if os.path.exists(tr) and world == 1:
             try:

@@ -396,10 +396,17 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
 // A-fragment rows past the valid outputs of a tile are read from wherever they fall inside the CTA's shared memory:
 // rows of a matrix product are independent and those results are never stored.
 __host__ __device__ constexpr inline int rot_plane_doubles(int LF) { return 4 * (LF + 8); }
+// Accumulator rows (complex units): TE at 0, TM at nHp = nH rounded up to 2 mod 8, row stride a multiple of 8; the
+// column-sum row sits first and the block's rows start 4 units later.  A quarter-warp of the P4 read-modify-write
+// (two consecutive outputs x four vectors = (direction, polarisation)) then touches eight distinct 16-byte bank groups
+// (the plain [I + 1][2 nH] layout put the four vectors on the same banks: 16 wavefronts per access instead of 4).
+__host__ __device__ constexpr inline int rot_acc_tm(int nH) { return nH + ((2 - nH % 8) + 8) % 8; }
+__host__ __device__ constexpr inline int rot_acc_row(int nH) { return (rot_acc_tm(nH) + nH + 7) / 8 * 8; }
+__host__ __device__ constexpr inline int rot_acc_units(int nH, int I) { return (I + 1) * rot_acc_row(nH) + 4; }
 // dynamic shared memory: record[2] | bufX[2 planes] | bufY[2 planes] | acc[I + 1][2n] (rows of the block, then the
 // column sums of the strip) | mbarrier[2]
 static size_t rot_smem_bytes(RotLayout const &L, int I) {
-  return 2 * L.rec_bytes + (size_t)4 * rot_plane_doubles(L.LF) * sizeof(double) + (size_t)(I + 1) * 2 * L.n * sizeof(cplx) +
+  return 2 * L.rec_bytes + (size_t)4 * rot_plane_doubles(L.LF) * sizeof(double) + (size_t)rot_acc_units(L.n, I) * sizeof(cplx) +
          2 * sizeof(uint64_t);
 }
 
@@ -568,8 +575,9 @@ __global__ void __launch_bounds__(ROT_THREADS, 3) k_matvec_rot(const __grid_cons
   const int I = a.I;
   double *bufX = (double *)(smem + 2 * L.rec_bytes);
   double *bufY = bufX + 2 * PS;
-  cplx *acc = (cplx *)(bufY + 2 * PS); // [I rows of the block | column sums of the strip][2n]
-  uint64_t *full = (uint64_t *)(acc + (size_t)(I + 1) * n2);
+  constexpr int NHP = rot_acc_tm(nH), RS = rot_acc_row(nH);
+  cplx *acc = (cplx *)(bufY + 2 * PS); // column sums of the strip, then (4 units later) the I rows of the block
+  uint64_t *full = (uint64_t *)(acc + rot_acc_units(nH, I));
   const int tid = threadIdx.x, lane = tid & 31;
   const int qbeg = a.cta_pair[blockIdx.x], qend = a.cta_pair[blockIdx.x + 1];
   if(qbeg >= qend)
@@ -581,7 +589,7 @@ __global__ void __launch_bounds__(ROT_THREADS, 3) k_matvec_rot(const __grid_cons
   }
   { // everything the fragment loads may touch starts finite
     double *z = (double *)smem;
-    const int nz = (int)((2 * L.rec_bytes) / sizeof(double)) + 4 * PS + 2 * (I + 1) * n2;
+    const int nz = (int)((2 * L.rec_bytes) / sizeof(double)) + 4 * PS + 2 * rot_acc_units(nH, I);
     for(int e = tid; e < nz; e += ROT_THREADS)
       z[e] = 0.0;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy writes before the bulk copies into the slots
@@ -648,7 +656,7 @@ __global__ void __launch_bounds__(ROT_THREADS, 3) k_matvec_rot(const __grid_cons
     c.pb = bufB + bofsP;
     c.pst = bufB + sofsP;
     c.vst = bufA + sofs;
-    c.dst = acc + (size_t)(c.dir1 ? I : pi.x % I) * n2 + c.cpol * nH; // direction 1: column sums of particle j
+    c.dst = acc + (c.dir1 ? 0 : RS + 4 + (pi.x % I) * RS) + c.cpol * NHP; // direction 1: column sums of particle j
     r_mbar_wait(&full[cur], (uint32_t)(((q - qbeg) >> 1) & 1));
     // ---- P0: phases, parity signs of the reversed direction, flip basis ----
     if(p0live) {
@@ -659,16 +667,24 @@ __global__ void __launch_bounds__(ROT_THREADS, 3) k_matvec_rot(const __grid_cons
         const double ge = dir ? psn : 1.0, gm = dir ? -psn : 1.0; // direction 1: x_i with (-1)^deg, and -1 on TM
         const cplx te_p = cmul(pp, xr[0]), tm_p = cmul(pp, xr[1]);
         cplx *ts = (cplx *)(bufA + dir * PS + 4 * pfs), *ta = (cplx *)(bufA + dir * PS + 4 * pfa);
+        // consecutive lanes write consecutive 32-byte rows, 16 bytes per store: lanes 4..7 of every eight take the TM half
+        // first so that one store instruction covers eight distinct 16-byte bank groups
+        const int h0 = (tid >> 2) & 1, h1 = h0 ^ 1;
         if(pa == 0) {
-          ts[0] = cscale(te_p, ge);
-          ts[1] = cscale(tm_p, gm);
+          const cplx v[2] = {cscale(te_p, ge), cscale(tm_p, gm)};
+          ts[h0] = h0 ? v[1] : v[0];
+          ts[h1] = h1 ? v[1] : v[0];
         } else {
           const cplx te_m = cmul(pm, xr[2]), tm_m = cmul(pm, xr[3]);
           const double fe = ge * ROT_SQH, fm = gm * ROT_SQH;
-          ts[0] = mk(fe * (te_p.x + psa * te_m.x), fe * (te_p.y + psa * te_m.y));
-          ts[1] = mk(fm * (tm_p.x + psa * tm_m.x), fm * (tm_p.y + psa * tm_m.y));
-          ta[0] = mk(fe * (te_p.x - psa * te_m.x), fe * (te_p.y - psa * te_m.y));
-          ta[1] = mk(fm * (tm_p.x - psa * tm_m.x), fm * (tm_p.y - psa * tm_m.y));
+          const cplx se = mk(fe * (te_p.x + psa * te_m.x), fe * (te_p.y + psa * te_m.y));
+          const cplx sm = mk(fm * (tm_p.x + psa * tm_m.x), fm * (tm_p.y + psa * tm_m.y));
+          const cplx ae = mk(fe * (te_p.x - psa * te_m.x), fe * (te_p.y - psa * te_m.y));
+          const cplx am = mk(fm * (tm_p.x - psa * tm_m.x), fm * (tm_p.y - psa * tm_m.y));
+          ts[h0] = h0 ? sm : se;
+          ta[h0] = h0 ? am : ae;
+          ts[h1] = h1 ? sm : se;
+          ta[h1] = h1 ? am : ae;
         }
       }
     }
@@ -695,17 +711,20 @@ __global__ void __launch_bounds__(ROT_THREADS, 3) k_matvec_rot(const __grid_cons
     if(pi.w & 3) { // last pair of the strip / of the segment: the finished sums go to HBM
       __syncthreads();
       if(pi.w & 1) {
-        cplx *cs = acc + (size_t)I * n2, *cpart = a.colpart + (size_t)pi.z * n2;
+        cplx *cpart = a.colpart + (size_t)pi.z * n2;
         for(int e = tid; e < n2; e += ROT_THREADS) {
-          cpart[e] = cs[e];
-          cs[e] = mk(0, 0);
+          cplx *src = acc + (e < nH ? e : e - nH + NHP);
+          cpart[e] = *src;
+          *src = mk(0, 0);
         }
       }
       if(pi.w & 2) {
         cplx *rp = a.rowpart + (size_t)sg * I * n2;
         for(int e = tid; e < I * n2; e += ROT_THREADS) {
-          rp[e] = acc[e];
-          acc[e] = mk(0, 0);
+          const int r = e / n2, k = e - r * n2;
+          cplx *src = acc + RS + 4 + r * RS + (k < nH ? k : k - nH + NHP);
+          rp[e] = *src;
+          *src = mk(0, 0);
         }
         ++sg;
       }

@@ -112,5 +112,23 @@ def test_reference_arm_under_torchrun_prints_one_line(tmp_path):
     lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 1
     d = json.loads(lines[0])
-    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] in ("port", "reference")
+    assert d["impl"] == "reference" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] in ("port", "reference", "reference-build+port")
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["higher_is_better"] is False
+    # a sampled arm says so, names the CPU, and carries the section 8(d) variants
+    assert d["extrapolated"] is True and d["cpu_baseline"]["cpu_model"]
+    assert "serial_step_s_scaled" in d["cpu_baseline"]["variants"]
+    assert set(d["config"]) == {"workload", "N", "gmres", "l2", "operator"}
+
+
+def test_reference_arm_does_not_load_the_product_libraries():
+    """The CPU arm builds its case from the generator's arrays: neither liboptimet_b200.so nor the host layer may be
+    mapped into its process (only oracle/ libraries)."""
+    import subprocess
+    code = ("import sys, json; sys.argv = ['bench.py', '--impl', 'reference', '--workload', 'small', '--steps', '1', "
+            "'--warmup', '0']; import bench; bench.main(); "
+            "maps = open('/proc/self/maps').read(); "
+            "print('MAPPED', [l.split()[-1] for l in maps.splitlines() if 'liboptimet_b200' in l])")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "MAPPED []" in out.stdout
