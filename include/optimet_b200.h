@@ -57,6 +57,32 @@ int ob_device_info(ob_ctx *ctx, int *sm_count, size_t *free_bytes, size_t *total
 int ob_partition(int nobj, int world, int rank, int *first, int *count);
 int ob_comm_unique_id(char out[128]);                                  /* rank 0, then broadcast by the host */
 int ob_comm_init(ob_ctx *ctx, const char uid[128], int rank, int world); /* NCCL communicator over NVLink */
+/* plan and assemble as `rank` of `world` WITHOUT a communicator: ob_matvec_partial then returns this shard's partial sums
+ * acc_p (pair and rotated-axial forms: the local pairs applied to x, before the cross-rank sum);
+ * y = x - T .* sum_ranks acc.  Lets one device execute every shard in turn (tests/test_gpu_shards.py checks the
+ * sharding on a one-GPU box); the sharded solvers themselves need ob_comm_init or ob_create_multi. */
+int ob_set_shard(ob_ctx *ctx, int rank, int world);
+int ob_matvec_partial(ob_ctx *ctx, int harmonic, const double *x, double *acc);
+
+/* ---- one process, several GPUs.  The reference's solver::factory returns the serial solver unconditionally in
+ * non-MPI builds (srcAna/Solver.cpp:30-34): a serial Optimet3D gets all the GPUs of the box through this group.  One
+ * context per device, NCCL communicators created inside the process, one host worker thread per GPU for every call;
+ * rank r owns its shard exactly as with one process per GPU.  Inputs are replicated to every context, outputs are
+ * rank 0's (the replicated vectors are bit-identical on every rank), cross sections are summed over the ranks. */
+typedef struct ob_multi ob_multi;
+int ob_create_multi(int ngpu, const int *devices, ob_multi **out);
+void ob_destroy_multi(ob_multi *m);
+int ob_multi_size(const ob_multi *m);
+ob_ctx *ob_multi_ctx(ob_multi *m, int rank);
+const char *ob_multi_last_error(ob_multi *m);
+int ob_multi_set_cluster(ob_multi *m, int nobj, const double *xyz_m, const double *radius_m, int nMax, int nMaxS);
+int ob_multi_set_frequency(ob_multi *m, double omega, const double waveK[2], const double eps_b[2], const double mu_b[2],
+                           const double *eps, const double *mu, const double *eps_SH, const double *mu_SH,
+                           const double *ksippp, const double *ksiparppar, const double *gamma);
+int ob_multi_set_incident(ob_multi *m, const double *a, const double *b);
+int ob_multi_set_option(ob_multi *m, const char *name, double value);
+int ob_multi_run(ob_multi *m, const ob_gmres_opts *opts, int do_sh, double *X_sca, double *X_int, double *X_sca_SH,
+                 double *X_int_SH, double cs[5], int stats[2]);
 
 /* ---- problem definition (what solver->update(run) reads from Geometry / Excitation) ---- */
 /* positions: Cartesian metres (Tools::toCartesian of Scatterer::vR), radius in metres */

@@ -28,6 +28,9 @@ SYMBOLS = [
     "ob_source_ff", "ob_set_cg_tables", "ob_build_cg_tables", "ob_fetch_cg_table", "ob_source_sh", "ob_solve",
     "ob_unprecondition_ff", "ob_unprecondition_sh", "ob_run", "ob_cross_sections", "ob_timings", "ob_timer", "ob_set_option",
     "ob_measure_fp64_peak", "ob_dense_solve", "ob_aca_block", "ob_aca_compress", "ob_aca_stats", "ob_fields",
+    "ob_set_shard", "ob_matvec_partial", "ob_create_multi", "ob_destroy_multi", "ob_multi_size", "ob_multi_ctx",
+    "ob_multi_last_error", "ob_multi_set_cluster", "ob_multi_set_frequency", "ob_multi_set_incident", "ob_multi_set_option",
+    "ob_multi_run",
 ]
 
 _lib = None
@@ -241,6 +244,18 @@ class Context:
                                       int(bool(do_sh)), _p(out), _p(inner)))
         return out, inner
 
+    def set_shard(self, rank, world):
+        """Plan / assemble as `rank` of `world` without a communicator (see ob_set_shard)."""
+        self._chk(self._lib.ob_set_shard(self.h, int(rank), int(world)))
+        self.rank, self.world = rank, world
+
+    def matvec_partial(self, harmonic, x):
+        """This shard's partial sums of the pair / rotated-axial operator (before the cross-rank sum)."""
+        x = _cz(x, self.N(harmonic))
+        acc = np.zeros_like(x)
+        self._chk(self._lib.ob_matvec_partial(self.h, int(harmonic), _p(x), _p(acc)))
+        return acc
+
     def matvec(self, harmonic, x):
         x = _cz(x, self.N(harmonic))
         y = np.zeros_like(x)
@@ -346,3 +361,68 @@ class Context:
         v = C.c_double()
         self._chk(self._lib.ob_measure_fp64_peak(self.h, C.byref(v)))
         return v.value
+
+
+class MultiContext:
+    """ob_multi: one process, several GPUs (one context per device, one host worker thread per GPU)."""
+
+    def __init__(self, devices):
+        self._lib = load()
+        self._lib.ob_multi_ctx.restype = C.c_void_p
+        self._lib.ob_multi_last_error.restype = C.c_char_p
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        if self._lib.ob_create_multi(len(devices), devs, C.byref(h)):
+            raise RuntimeError(self._lib.ob_last_error(None).decode())
+        self.h = h
+        self.size = self._lib.ob_multi_size(self.h)
+        self.nobj = self.nMax = self.nMaxS = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._lib.ob_destroy_multi(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc:
+            raise RuntimeError(self._lib.ob_multi_last_error(self.h).decode())
+
+    def ctx(self, rank):
+        return Context.view(self._lib.ob_multi_ctx(self.h, int(rank)), self.nobj, self.nMax, self.nMaxS)
+
+    def set_cluster(self, xyz_m, radius_m, nMax, nMaxS=None):
+        xyz = np.ascontiguousarray(xyz_m, dtype=np.float64).reshape(-1, 3)
+        rad = np.ascontiguousarray(radius_m, dtype=np.float64).reshape(-1)
+        nMaxS = nMax if nMaxS is None else nMaxS
+        self._chk(self._lib.ob_multi_set_cluster(self.h, int(xyz.shape[0]), _p(xyz), _p(rad), int(nMax), int(nMaxS)))
+        self.nobj, self.nMax, self.nMaxS = xyz.shape[0], nMax, nMaxS
+
+    def set_frequency(self, omega, waveK, eps_b, mu_b, eps, mu, eps_SH, mu_SH, ksippp, ksiparppar, gamma):
+        arrs = [_cz(a, self.nobj) for a in (eps, mu, eps_SH, mu_SH, ksippp, ksiparppar, gamma)]
+        self._chk(self._lib.ob_multi_set_frequency(self.h, C.c_double(omega), _c2(waveK), _c2(eps_b), _c2(mu_b),
+                                                  *[_p(a) for a in arrs]))
+
+    def set_incident(self, a, b):
+        n = self.nMax * (self.nMax + 2)
+        self._chk(self._lib.ob_multi_set_incident(self.h, _p(_cz(a, n)), _p(_cz(b, n))))
+
+    def set_option(self, name, value):
+        self._chk(self._lib.ob_multi_set_option(self.h, name.encode(), C.c_double(value)))
+
+    def run(self, opts, do_sh=True):
+        N1 = 2 * self.nMax * (self.nMax + 2) * self.nobj
+        N2 = 2 * self.nMaxS * (self.nMaxS + 2) * self.nobj
+        outs = [np.zeros(N1, dtype=np.complex128), np.zeros(N1, dtype=np.complex128),
+                np.zeros(N2, dtype=np.complex128), np.zeros(N2, dtype=np.complex128)]
+        cs = (C.c_double * 5)()
+        st = (C.c_int * 2)()
+        self._chk(self._lib.ob_multi_run(self.h, C.byref(opts), int(do_sh), _p(outs[0]), _p(outs[1]), _p(outs[2]),
+                                        _p(outs[3]), cs, st))
+        return dict(ext=cs[0], sca=cs[1], abs=cs[2], sca_SH=cs[3], abs_SH=cs[4], iters_ff=st[0], iters_sh=st[1],
+                    X_sca=outs[0], X_int=outs[1], X_sca_SH=outs[2], X_int_SH=outs[3])

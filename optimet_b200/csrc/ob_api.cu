@@ -1010,6 +1010,25 @@ int ob_comm_init(ob_ctx *ctx, const char uid[128], int rank, int world) {
   }
   if(ctx->nobj > 0)
     partition(ctx->nobj, world, rank, ctx->first, ctx->count);
+  for(int h = 0; h < 2; ++h) { // operators assembled under another partition are stale
+    ctx->hs[h].assembled = false;
+    ctx->hs[h].pplan_world = ctx->hs[h].rplan_world = -1;
+  }
+  OB_END
+}
+
+int ob_set_shard(ob_ctx *ctx, int rank, int world) {
+  OB_BEGIN
+  need(world >= 1 && rank >= 0 && rank < world, "bad rank/world");
+  need(ctx->comm == nullptr, "ob_set_shard: the context already has a communicator");
+  ctx->rank = rank;
+  ctx->world = world;
+  if(ctx->nobj > 0)
+    partition(ctx->nobj, world, rank, ctx->first, ctx->count);
+  for(int h = 0; h < 2; ++h) { // operators assembled for another shard are stale
+    ctx->hs[h].assembled = false;
+    ctx->hs[h].pplan_world = ctx->hs[h].rplan_world = -1;
+  }
   OB_END
 }
 
@@ -1279,6 +1298,25 @@ int ob_matvec(ob_ctx *ctx, int harmonic, const double *x, double *y) {
   matvec(ctx, harmonic, ctx->tmpA.p, ctx->tmpB.p);
   download(ctx, ctx->tmpB.p, y, N);
   flush_matvec_timing(ctx);
+  OB_END
+}
+
+int ob_matvec_partial(ob_ctx *ctx, int harmonic, const double *x, double *acc) {
+  OB_BEGIN
+  check_harmonic(harmonic);
+  HarmonicState &H = ctx->hs[harmonic - 1];
+  need(H.assembled, "matrix not assembled (call ob_assemble)");
+  need(H.mode == 1 || H.mode == 3, "ob_matvec_partial: only the pair and rotated-axial forms are sharded by pairs");
+  const int N = ctx->N(harmonic);
+  upload(ctx, ctx->tmpA, x, N);
+  const cplx *T = ctx->fac[harmonic == 1 ? 0 : 1].p;
+  if(H.mode == 1) {
+    launch_matvec_pairs(H.pplan, H.AB.p, ctx->tmpA.p, T, H.pplan.acc, 0, ctx->st);
+    download(ctx, H.pplan.acc, acc, N);
+  } else {
+    launch_matvec_rot(H.rplan, H.rl, H.rot.p, ctx->tmpA.p, T, H.rplan.acc, 0, ctx->st);
+    download(ctx, H.rplan.acc, acc, N);
+  }
   OB_END
 }
 

@@ -65,6 +65,18 @@ struct Error : public std::runtime_error {
   explicit Error(std::string const &m) : std::runtime_error(m) {}
 };
 
+// true exactly once per device of this process (per-device state such as __constant__ uploads and kernel attributes
+// must be set on every device a single-process multi-GPU group uses: ob_create_multi)
+inline bool first_use_on_device(bool (&flags)[64]) {
+  int dev = 0;
+  if(cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64)
+    return true;
+  if(flags[dev])
+    return false;
+  flags[dev] = true;
+  return true;
+}
+
 #define OB_CUDA(call)                                                                                                  \
   do {                                                                                                                 \
     cudaError_t e__ = (call);                                                                                          \

@@ -447,13 +447,12 @@ int lu_solve(cplx *A, int N, size_t lda, LuWork &w, const cplx *b, cplx *x, int 
   if(N <= 0)
     return 0;
   w.alloc(N, sm_count);
-  static bool attr_set = false;
+  static bool attr_set[64] = {false};
   const size_t sm_linv = sizeof(cplx) * 2 * NB * NB, sm_sub = sizeof(cplx) * (NB * NB + NB);
-  if(!attr_set) {
+  if(first_use_on_device(attr_set)) {
     OB_CUDA(cudaFuncSetAttribute(k_lu_linv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_linv));
     OB_CUDA(cudaFuncSetAttribute(k_lu_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_sub));
     OB_CUDA(cudaFuncSetAttribute(k_lu_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_sub));
-    attr_set = true;
   }
   int occ = 1;
   OB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lu_panel, PANEL_THREADS, 0));

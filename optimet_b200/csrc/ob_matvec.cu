@@ -202,11 +202,9 @@ template <int RPT, int KB, int NS>
 static void launch_variant(MatvecPlan const &p, const cplx *S, const cplx *x, cplx *out, cudaStream_t st) {
   typedef MvCfg<RPT, KB, NS> C;
   auto fn = k_matvec<RPT, KB, NS>;
-  static bool attr_set = false;
-  if(!attr_set) {
+  static bool attr_set[64] = {false};
+  if(first_use_on_device(attr_set))
     OB_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-    attr_set = true;
-  }
   fn<<<p.grid, C::THREADS, C::SMEM, st>>>(S, p.ld, x, out, p.M, p.N, p.tiles, p.chunks, p.cols_per_chunk);
   OB_CUDA(cudaGetLastError());
 }

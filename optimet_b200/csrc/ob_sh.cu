@@ -19,15 +19,14 @@ namespace ob {
 __constant__ double c_fact[171];
 
 static void upload_factorials() {
-  static bool done = false;
-  if(done)
+  static bool done[64] = {false};
+  if(!first_use_on_device(done))
     return;
   double f[171];
   f[0] = 1.0;
   for(int i = 1; i <= 170; ++i)
     f[i] = f[i - 1] * (double)i;
   OB_CUDA(cudaMemcpyToSymbol(c_fact, f, sizeof(f)));
-  done = true;
 }
 
 __device__ __forceinline__ bool tri_bad(int a, int b, int c) { return c < abs(a - b) || c > a + b; }
