@@ -147,11 +147,14 @@ int ob_unprecondition_sh(ob_ctx *ctx, const double *X_sca_SH, const double *K1an
 
 /* ---- whole step, device resident: update() + solve() + Result cross sections for the current
  * frequency (Simulation.cpp:648-667).  Any of the output vector pointers may be NULL.
- * cs: ext_FF, sca_FF, abs_FF (= ext - sca, Simulation.cpp:659), sca_SH, abs_SH.  stats: iters_FF, iters_SH */
+ * cs: ext_FF, sca_FF, abs_FF (= ext - sca, Simulation.cpp:659), sca_SH, abs_SH.  stats: iters_FF, iters_SH.
+ * With world > 1 (ob_comm_init / ob_set_shard) cs holds THIS RANK's partial sums over its own particles, as the
+ * reference's ranks hold theirs before MPI_Gather (Simulation.cpp:510-572): the caller adds them over the ranks
+ * (ob_multi_run and optimet_b200/sharding.py do).  The coefficient vectors are complete on every rank. */
 int ob_run(ob_ctx *ctx, const ob_gmres_opts *opts, int do_sh, double *X_sca, double *X_int, double *X_sca_SH,
            double *X_int_SH, double cs[5], int stats[2]);
 
-/* ---- reductions (Result::get*CrossSection*, srcAna/Result.cpp:557-794) ---- */
+/* ---- reductions (Result::get*CrossSection*, srcAna/Result.cpp:557-794); per-rank partial sums when world > 1 ---- */
 int ob_cross_sections(ob_ctx *ctx, const double *X_sca, const double *X_int, const double *X_sca_SH,
                       const double *X_int_SH, int do_sh, double cs[5]);
 

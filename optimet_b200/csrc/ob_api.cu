@@ -166,6 +166,7 @@ struct ob_ctx {
   bool trace = false;             // "trace_iterations": GPU-timeline breakdown of a GMRES iteration into tim[11..13]
   std::vector<char> mv_ev_arn;    // whether slot 3 of an entry was recorded
   hcd *h_pinned = nullptr; // pinned staging for the per-iteration Hessenberg column read-back
+  size_t h_pinned_cap = 0;
 
   int N(int h) const { return 2 * hs[h - 1].n * nobj; }
   int Mloc(int h) const { return 2 * hs[h - 1].n * count; }
@@ -710,6 +711,23 @@ static GmresOut solve_dev(ob_ctx *c, int harmonic, const cplx *rhs, cplx *x, con
   need(o != nullptr, "ob_gmres_opts is NULL");
   if(o->flavour == OB_SOLVE_DIRECT)
     return direct_solve(c, harmonic, rhs, x);
+  // the public ABI accepts any values: reject what the drivers cannot run (the Hessenberg column of one iteration is
+  // staged in a pinned buffer grown to the basis size here)
+  need(o->tol > 0.0, "ob_gmres_opts: tol must be positive");
+  need(o->max_iters > 0, "ob_gmres_opts: max_iters must be positive");
+  need(o->max_restarts >= 0, "ob_gmres_opts: max_restarts must not be negative");
+  need(o->flavour != OB_GMRES_BELOS || o->restart > 0, "ob_gmres_opts: restart (Num Blocks) must be positive");
+  {
+    const size_t basis = (size_t)(o->flavour == OB_GMRES_BELOS ? std::min(o->restart, o->max_iters) : o->max_iters) + 8;
+    if(basis > c->h_pinned_cap) {
+      if(c->h_pinned)
+        cudaFreeHost(c->h_pinned);
+      c->h_pinned = nullptr;
+      c->h_pinned_cap = 0;
+      OB_CUDA(cudaMallocHost(&c->h_pinned, basis * sizeof(hcd)));
+      c->h_pinned_cap = basis;
+    }
+  }
   c->tmpA.alloc(c->N(harmonic));
   GmresOut r;
   struct Flush { // matvec timings are read back when the solve ends (also on the error path)
@@ -930,6 +948,7 @@ int ob_create(int device, ob_ctx **out) {
     for(auto &e : c->mv_ev)
       OB_CUDA(cudaEventCreate(&e));
     OB_CUDA(cudaMallocHost(&c->h_pinned, 512 * sizeof(hcd)));
+    c->h_pinned_cap = 512;
     *out = c;
   } catch(std::exception &e) {
     g_create_error = e.what();
@@ -1240,9 +1259,11 @@ int ob_aca_compress(ob_ctx *ctx, int dim, const double *C, int *rank, double *U,
   OB_CUDA(cudaMemcpy(V, dV.p, (size_t)r * dim * sizeof(cplx), cudaMemcpyDeviceToHost));
   std::vector<int> pv(2 * (size_t)dim);
   OB_CUDA(cudaMemcpy(pv.data(), dp.p, pv.size() * sizeof(int), cudaMemcpyDeviceToHost));
-  for(int p = 0; p < r; ++p) {
-    I[p] = pv[p];
-    J[p] = pv[dim + p];
+  for(int p = 0; p < r; ++p) { // pivot rows / columns are optional outputs, as in ob_aca_block
+    if(I)
+      I[p] = pv[p];
+    if(J)
+      J[p] = pv[dim + p];
   }
   OB_END
 }
@@ -1645,8 +1666,8 @@ int ob_set_option(ob_ctx *ctx, const char *name, double value) {
   std::string n(name ? name : "");
   if(n == "matvec_variant") {
     ctx->matvec_variant = (int)value;
-    for(int h = 0; h < 2; ++h)
-      if(ctx->hs[h].assembled)
+    for(int h = 0; h < 2; ++h) // only the dense form holds a streaming plan to rebuild; the others re-plan at assembly
+      if(ctx->hs[h].assembled && ctx->hs[h].mode == 0 && ctx->hs[h].plan.M > 0 && ctx->hs[h].plan.N > 0)
         matvec_plan(ctx->hs[h].plan, ctx->hs[h].plan.M, ctx->hs[h].plan.N, ctx->hs[h].plan.ld, ctx->sm_count,
                     ctx->matvec_variant);
   } else if(n == "keep_matrices")

@@ -752,7 +752,10 @@ void B200Matrix::update() {
   for(auto const &s : geometry->objects) { // PreconditionedMatrix.cpp:1160-1165
     if(s.nMax != nMax || s.nMaxS != nMaxS)
       throw std::runtime_error("All objects must have same number of harmonics");
-    if(s.elmag.epsilon != s.elmag.epsilon || s.elmag.epsilon_SH != s.elmag.epsilon_SH) // NaN
+    // NaN = outside the tabulated range.  The SH permittivity only enters the SH part: a fundamental-only run at
+    // 250-500 nm (lambda / 2 below the table) is accepted like the reference accepts it
+    const bool sh = incWave->SH_cond;
+    if(s.elmag.epsilon != s.elmag.epsilon || (sh && s.elmag.epsilon_SH != s.elmag.epsilon_SH))
       throw std::runtime_error("SiliconModel: wavelength (or its half) outside the tabulated 0.25-1.45 um range");
   }
   std::vector<double> xyz(3 * nobj), radius(nobj);
@@ -768,7 +771,8 @@ void B200Matrix::update() {
     radius[j] = s.radius;
     mat[0][j] = s.elmag.epsilon;
     mat[1][j] = s.elmag.mu;
-    mat[2][j] = s.elmag.epsilon_SH;
+    // unused without SH sources: a finite placeholder keeps the unused SH Mie factors from turning into NaN
+    mat[2][j] = (s.elmag.epsilon_SH != s.elmag.epsilon_SH) ? s.elmag.epsilon : s.elmag.epsilon_SH;
     mat[3][j] = s.elmag.mu_SH;
     mat[4][j] = s.elmag.ksippp;
     mat[5][j] = s.elmag.ksiparppar;

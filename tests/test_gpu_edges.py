@@ -134,3 +134,45 @@ def test_mixed_orders_are_refused_by_the_host_layer():
     solver.close()
     with pytest.raises(RuntimeError, match="outside the tabulated"):  # SiliconModel table 0.25-1.45 um incl. lambda/2
         H.Solver(H.Case(xml=xmlgen.cluster_xml([[0, 0, 0], [0, 0, 300.0]], 50.0, 3, 400.0)), device=0).step()
+
+
+def test_fundamental_only_silicon_below_the_sh_table_runs():
+    """Si spheres at 400 nm without SH sources: lambda / 2 = 200 nm is below the tabulated range, the SH permittivity is
+    NaN and never used -- the reference runs this input, the host layer must too (and still refuses it with SH on)."""
+    from optimet_b200 import host as H, xmlgen
+    xyz = [[0, 0, 0], [0, 60, 210.0]]
+    case = H.Case(xml=xmlgen.cluster_xml(xyz, 50.0, 4, 400.0, sh=False))
+    solver = H.Solver(case, device=0)
+    solver.set_gmres(ob.GmresOpts(ob.OB_GMRES_BELOS, 1e-12, 200, 60, 5))
+    res = solver.step()
+    solver.close()
+    orc = O.Case()
+    for p in xyz:
+        orc.add_sphere([v * 1e-9 for v in p], 50e-9, 4, O.MODEL_SILICON, [1.0, 0.0])
+    orc.set_source(400e-9, np.pi / 4, np.pi / 2, 1.0, 0.0, False)
+    orc.solve(O.SOLVER_DIRECT)
+    cs = orc.cross_sections()
+    assert abs(res["ext"] / cs["ext"] - 1) < 1e-9 and abs(res["sca"] / cs["sca"] - 1) < 1e-9
+    assert np.isfinite(res["X_sca"]).all()
+    case2 = H.Case(xml=xmlgen.cluster_xml(xyz, 50.0, 4, 400.0, sh=True))
+    s2 = H.Solver(case2, device=0)
+    with pytest.raises(RuntimeError, match="outside the tabulated"):
+        s2.step()
+    s2.close()
+
+
+def test_gmres_options_are_validated(gpu_ctx):
+    """The C ABI accepts any ob_gmres_opts: nonsense is refused, and a basis longer than the default pinned staging
+    (512 entries) works."""
+    spec = U.random_cluster(3, 3, seed=2)
+    orc = U.oracle_case(spec)
+    U.configure_ctx(gpu_ctx, spec, orc)
+    gpu_ctx.assemble(1)
+    Q = gpu_ctx.source_ff()
+    for bad in (ob.GmresOpts(ob.OB_GMRES_ZCOMP, 1e-6, 0, 0, 2), ob.GmresOpts(ob.OB_GMRES_BELOS, 1e-6, 50, 0, 2),
+                ob.GmresOpts(ob.OB_GMRES_BELOS, 0.0, 50, 30, 2), ob.GmresOpts(ob.OB_GMRES_ZCOMP, 1e-6, 50, 0, -1)):
+        with pytest.raises(RuntimeError, match="ob_gmres_opts"):
+            gpu_ctx.solve(1, Q, bad)
+    x, it, _ = gpu_ctx.solve(1, Q, ob.GmresOpts(ob.OB_GMRES_ZCOMP, 1e-12, 700, 0, 1))
+    assert it < 700 and U.relerr(gpu_ctx.matvec(1, x), Q) < 1e-10
+    gpu_ctx.set_option("matvec_variant", 0)   # no dense plan in the pair form: must not divide by zero
