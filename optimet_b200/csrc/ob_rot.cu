@@ -133,7 +133,7 @@ k_assemble_axial(VtacTables tb, const double *__restrict__ xyz, cplx k, const in
 static size_t rot_axial_smem_bytes(int NM) { return (size_t)ROT_AX_WARPS * rot_axial_buf_entries(NM) * sizeof(cplx); }
 __global__ void __launch_bounds__(ROT_AX_WARPS * 32)
 k_assemble_axial_only(const double *__restrict__ xyz, cplx k, const int2 *__restrict__ pair_ij, long npairs,
-                      unsigned char *__restrict__ recs, RotLayout L) {
+                      unsigned char *__restrict__ recs, RotLayout L, RotAxTab tab) {
   extern __shared__ __align__(16) unsigned char smem_ax[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int entries = rot_axial_buf_entries(L.NM);
@@ -147,9 +147,40 @@ k_assemble_axial_only(const double *__restrict__ xyz, cplx k, const int2 *__rest
                  z = xyz[3 * ij.x + 2] - xyz[3 * ij.y + 2];
     const double r = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
     unsigned char *rec = recs + (size_t)q * L.rec_bytes;
-    rot_axial_pair(L.NM, k, r, buf, (cplx *)(rec + L.offCp), (cplx *)(rec + L.offCm), lane, 32, 2);
+    rot_axial_pair(L.NM, k, r, buf, (cplx *)(rec + L.offCp), (cplx *)(rec + L.offCm), lane, 32, 2, &tab);
     __syncwarp();
   }
+}
+
+// index-only coefficient tables of the axial recursion, one set per (device, nMax)
+struct RotAxTabDev {
+  int NM = -1;
+  RotAxTab t = {nullptr, nullptr, nullptr, nullptr};
+};
+static RotAxTabDev g_axtab[16][OB_MAX_NMAX + 1];
+template <class T> static const T *rot_to_device(std::vector<T> const &v) {
+  T *d = nullptr;
+  OB_CUDA(cudaMalloc(&d, std::max<size_t>(1, v.size()) * sizeof(T)));
+  OB_CUDA(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return d;
+}
+static RotAxTab const &rot_axtab(int NM) {
+  int dev = 0;
+  OB_CUDA(cudaGetDevice(&dev));
+  if(dev < 0 || dev >= 16)
+    throw Error("rotated-axial operator: device ordinal out of range");
+  RotAxTabDev &e = g_axtab[dev][NM];
+  if(e.NM == NM)
+    return e.t;
+  std::vector<double> rec, emit;
+  std::vector<int> ridx, eidx;
+  rot_axial_tables_build(NM, rec, emit, ridx, eidx);
+  e.t.rec = rot_to_device(rec);
+  e.t.emit = rot_to_device(emit);
+  e.t.ridx = rot_to_device(ridx);
+  e.t.eidx = rot_to_device(eidx);
+  e.NM = NM;
+  return e.t;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -939,7 +970,7 @@ void launch_assemble_rot(VtacTableSet const &ts, const double *xyz, cplx k, cons
     const size_t sm = rot_axial_smem_bytes(L.NM);
     OB_CUDA(cudaFuncSetAttribute((const void *)k_assemble_axial_only, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     const long ctas = std::min<long>((npairs + ROT_AX_WARPS - 1) / ROT_AX_WARPS, (long)sm_count * 8);
-    k_assemble_axial_only<<<(unsigned)ctas, ROT_AX_WARPS * 32, sm, st>>>(xyz, k, pair_ij, npairs, recs, L);
+    k_assemble_axial_only<<<(unsigned)ctas, ROT_AX_WARPS * 32, sm, st>>>(xyz, k, pair_ij, npairs, recs, L, rot_axtab(L.NM));
   } else {
     OB_CUDA(cudaFuncSetAttribute((const void *)k_assemble_axial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ts.smem));
     OB_CUDA(cudaFuncSetAttribute((const void *)k_assemble_axial, cudaFuncAttributePreferredSharedMemoryCarveout,

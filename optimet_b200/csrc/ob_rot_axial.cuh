@@ -8,6 +8,7 @@
 #pragma once
 #include "ob_common.cuh"
 #include "ob_special.cuh"
+#include <vector>
 
 #if defined(__CUDA_ARCH__)
 #define OB_SYNCWARP() __syncwarp()
@@ -39,13 +40,78 @@ __host__ __device__ inline double ta_b_minus(int n, int m) {
 // l < m are never written and must be zero on entry (and stay zero)
 __host__ __device__ inline int rot_axial_buf_entries(int NM) { return 3 * (NM + 2) * (2 * NM + 3); }
 
+// Index-only coefficient tables of the recursion and of the A / B emission for one nMax (the square roots of the
+// reference's a+-, b+- and of the Coupling prefactors depend on (n, m, l) only; evaluating them per pair was most of the
+// assembly time).  Built on the host by rot_axial_tables_build from the very expressions of the table-free path below,
+// which stays for the host check and as the specification.
+//   rec  [offR(n) + t][4] = c0, c1, c2, 1 / denominator     of item t = m * span + (l - m) of level n
+//   emit [offE(n) + t][8] = fa, a0, a1, a2, fb, b0, b1, b2   of item t = mu * NM + (l - 1) of level n
+//   ridx / eidx           = m | l << 8  /  mu | l << 8 | live << 16
+struct RotAxTab {
+  const double *rec, *emit;
+  const int *ridx, *eidx;
+};
+__host__ __device__ inline int rot_axial_offR(int NM, int n) { // sum_{j=1}^{n-1} (j + 1)(2 NM - j + 1)
+  int o = 0;
+  for(int j = 1; j < n; ++j)
+    o += (j + 1) * (2 * NM - j + 1);
+  return o;
+}
+__host__ __device__ inline int rot_axial_offE(int NM, int n) { return NM * ((n - 1) * (n + 2) / 2); } // NM sum_{j<n} (j + 1)
+inline void rot_axial_tables_build(int NM, std::vector<double> &rec, std::vector<double> &emit, std::vector<int> &ridx,
+                                   std::vector<int> &eidx) {
+  const int LL = 2 * NM;
+  rec.assign((size_t)rot_axial_offR(NM, NM + 1) * 4, 0.0);
+  ridx.assign((size_t)rot_axial_offR(NM, NM + 1), 0);
+  emit.assign((size_t)rot_axial_offE(NM, NM + 1) * 8, 0.0);
+  eidx.assign((size_t)rot_axial_offE(NM, NM + 1), 0);
+  for(int n = 1; n <= NM; ++n) {
+    const int span = LL - n + 1;
+    for(int t = 0; t < (n + 1) * span; ++t) {
+      const int m = t / span, l = m + (t - m * span);
+      double *c = &rec[((size_t)rot_axial_offR(NM, n) + t) * 4];
+      ridx[(size_t)rot_axial_offR(NM, n) + t] = m | (l << 8) | ((l <= LL - n ? 1 : 0) << 16);
+      if(l > LL - n)
+        continue;
+      if(m == n) {
+        c[0] = l - 1 >= n - 1 ? ta_b_plus(l - 1, n - 1) : 0.0;
+        c[1] = ta_b_minus(l + 1, n - 1);
+        c[2] = 0.0;
+        c[3] = 1.0 / ta_b_plus(n - 1, n - 1);
+      } else {
+        c[0] = l - 1 >= m ? ta_a_plus(l - 1, m) : 0.0;
+        c[1] = ta_a_minus(l + 1, m);
+        c[2] = n - 2 >= m ? ta_a_minus(n - 1, m) : 0.0;
+        c[3] = 1.0 / ta_a_plus(n - 1, m);
+      }
+    }
+    for(int t = 0; t < (n + 1) * NM; ++t) {
+      const int mu = t / NM, l = 1 + (t - mu * NM);
+      const int n0 = rot_n0(mu);
+      const bool live = !(n < n0 || l < n0);
+      eidx[(size_t)rot_axial_offE(NM, n) + t] = mu | (l << 8) | ((live ? 1 : 0) << 16);
+      if(!live)
+        continue;
+      double *c = &emit[((size_t)rot_axial_offE(NM, n) + t) * 8];
+      c[0] = 0.5 / sqrt((double)(l * (l + 1) * n * (n + 1)));
+      c[1] = 2.0 * mu * mu;
+      c[2] = sqrt((double)((n - mu) * (n + mu + 1) * (l - mu) * (l + mu + 1)));
+      c[3] = sqrt((double)((n + mu) * (n - mu + 1) * (l + mu) * (l - mu + 1)));
+      c[4] = -0.5 * sqrt((2.0 * l + 1.0) / ((double)(2 * l - 1) * (double)(l * (l + 1)) * (double)(n * (n + 1))));
+      c[5] = 2.0 * mu * sqrt((double)((l - mu) * (l + mu)));
+      c[6] = sqrt((double)((n - mu) * (n + mu + 1) * (l - mu) * (l - mu - 1)));
+      c[7] = sqrt((double)((n + mu) * (n - mu + 1) * (l + mu) * (l + mu - 1)));
+    }
+  }
+}
+
 // Axial A[(n,mu),(l,mu)], B[...] for translation r along z with wavenumber k into Aout / Bout (compact layout of
 // ob_rot.cu: rot_offX(mu) + (n - n0)(NM - n0 + 1) + (l - n0)).  `lane` of `nlanes` cooperating threads; buf as above.
 // combine = 1: Aout[e] = A + B for every mu and Bout[e - NM^2] = A - B for mu >= 1 (interleaved complex).
 // combine = 2 (record layout of ob_rot.cu): the same values as planes of doubles, Aout -> [Re(A+B)[X] | Im(A+B)[X]],
 // Bout -> [Re(A-B)[X - NM^2] | Im(A-B)[X - NM^2]], X = rot_offX(NM, NM + 1).
 __host__ __device__ inline void rot_axial_pair(int NM, cplx k, double r, cplx *buf, cplx *Aout, cplx *Bout, int lane,
-                                               int nlanes, int combine = 0) {
+                                               int nlanes, int combine = 0, const RotAxTab *tab = nullptr) {
   const int LL = 2 * NM, W = LL + 3, CH = NM + 2;
   // seeds (n = m = 0): sqrt(4 pi) (-1)^l Y_l0(0) h_l = (-1)^l sqrt(2l + 1) h_l(k r); every lane runs the short upward
   // Hankel recurrence and keeps the orders it owns
@@ -62,6 +128,21 @@ __host__ __device__ inline void rot_axial_pair(int NM, cplx k, double r, cplx *b
     cplx *cur = buf + (size_t)(n % 3) * CH * W;
     const cplx *p1 = buf + (size_t)((n - 1) % 3) * CH * W, *p2 = buf + (size_t)((n + 1) % 3) * CH * W; // n-1, n-2
     const int span = LL - n + 1; // l in [m, LL - n]: index t = m * span + (l - m) over a (n + 1) x span rectangle
+    if(tab) { // tabulated coefficients: same expressions, evaluated once per nMax (rot_axial_tables_build)
+      const double *rc = tab->rec + (size_t)rot_axial_offR(NM, n) * 4;
+      const int *ri = tab->ridx + rot_axial_offR(NM, n);
+      for(int t = lane; t < (n + 1) * span; t += nlanes) {
+        const int ix = ri[t], m = ix & 0xff, l = (ix >> 8) & 0xff;
+        if(!(ix >> 16))
+          continue;
+        const double c0 = rc[4 * t], c1 = rc[4 * t + 1], c2 = rc[4 * t + 2], inv = rc[4 * t + 3];
+        const int mr = m == n ? n - 1 : m; // sectorial step reads chain n - 1 of the previous level
+        const cplx lo = l - 1 >= mr ? p1[mr * W + (l - 1)] : mk(0, 0);
+        const cplx up = p1[mr * W + (l + 1)];
+        const cplx o = (m != n && n - 2 >= m) ? p2[m * W + l] : mk(0, 0);
+        cur[m * W + l] = mk((lo.x * c0 + up.x * c1 - o.x * c2) * inv, (lo.y * c0 + up.y * c1 - o.y * c2) * inv);
+      }
+    } else
     for(int t = lane; t < (n + 1) * span; t += nlanes) {
       const int m = t / span, l = m + (t - m * span);
       if(l > LL - n)
@@ -86,28 +167,41 @@ __host__ __device__ inline void rot_axial_pair(int NM, cplx k, double r, cplx *b
     OB_SYNCWARP();
     // A, B of column degree n for every mu <= n and row degree l (Coupling.cpp:30-51 with k = m = mu)
     for(int t = lane; t < (n + 1) * NM; t += nlanes) {
-      const int mu = t / NM, l = 1 + (t - mu * NM);
+      int mu, l;
+      double fa, a0, a1, a2, fb, b0, b1, b2;
+      if(tab) { // tabulated: same expressions, evaluated once per nMax (rot_axial_tables_build)
+        const int ix = tab->eidx[rot_axial_offE(NM, n) + t];
+        if(!(ix >> 16))
+          continue;
+        mu = ix & 0xff;
+        l = (ix >> 8) & 0xff;
+        const double *ec = tab->emit + ((size_t)rot_axial_offE(NM, n) + t) * 8;
+        fa = ec[0], a0 = ec[1], a1 = ec[2], a2 = ec[3], fb = ec[4], b0 = ec[5], b1 = ec[6], b2 = ec[7];
+      } else {
+        mu = t / NM;
+        l = 1 + (t - mu * NM);
+        if(n < rot_n0(mu) || l < rot_n0(mu))
+          continue;
+        fa = 0.5 / sqrt((double)(l * (l + 1) * n * (n + 1)));
+        a0 = 2.0 * mu * mu;
+        a1 = sqrt((double)((n - mu) * (n + mu + 1) * (l - mu) * (l + mu + 1)));
+        a2 = sqrt((double)((n + mu) * (n - mu + 1) * (l + mu) * (l - mu + 1)));
+        fb = -0.5 * sqrt((2.0 * l + 1.0) / ((double)(2 * l - 1) * (double)(l * (l + 1)) * (double)(n * (n + 1))));
+        b0 = 2.0 * mu * sqrt((double)((l - mu) * (l + mu)));
+        b1 = sqrt((double)((n - mu) * (n + mu + 1) * (l - mu) * (l - mu - 1)));
+        b2 = sqrt((double)((n + mu) * (n - mu + 1) * (l + mu) * (l + mu - 1)));
+      }
       const int n0 = rot_n0(mu);
-      if(n < n0 || l < n0)
-        continue;
       const int mp1 = mu + 1, mm1 = mu > 0 ? mu - 1 : 1; // |mu - 1|: beta(n,-m,l,-m) = beta(n,m,l,m)
       // beta(n, m', l', m') at this level; zero outside 0 <= m' <= min(n, l')
       const cplx t0 = (mu <= n && mu <= l) ? cur[mu * W + l] : mk(0, 0);
       const cplx tp = (mp1 <= n && mp1 <= l) ? cur[mp1 * W + l] : mk(0, 0);
       const cplx tm = (mm1 <= n && mm1 <= l) ? cur[mm1 * W + l] : mk(0, 0);
-      const double fa = 0.5 / sqrt((double)(l * (l + 1) * n * (n + 1)));
-      const double a0 = 2.0 * mu * mu;
-      const double a1 = sqrt((double)((n - mu) * (n + mu + 1) * (l - mu) * (l + mu + 1)));
-      const double a2 = sqrt((double)((n + mu) * (n - mu + 1) * (l + mu) * (l - mu + 1)));
       const cplx Av = mk(fa * (a0 * t0.x + a1 * tp.x + a2 * tm.x), fa * (a0 * t0.y + a1 * tp.y + a2 * tm.y));
       const int lm = l - 1;
       const cplx u0 = (lm >= 0 && mu <= n && mu <= lm) ? cur[mu * W + lm] : mk(0, 0);
       const cplx up = (lm >= 0 && mp1 <= n && mp1 <= lm) ? cur[mp1 * W + lm] : mk(0, 0);
       const cplx um = (lm >= 0 && mm1 <= n && mm1 <= lm) ? cur[mm1 * W + lm] : mk(0, 0);
-      const double fb = -0.5 * sqrt((2.0 * l + 1.0) / ((double)(2 * l - 1) * (double)(l * (l + 1)) * (double)(n * (n + 1))));
-      const double b0 = 2.0 * mu * sqrt((double)((l - mu) * (l + mu)));
-      const double b1 = sqrt((double)((n - mu) * (n + mu + 1) * (l - mu) * (l - mu - 1)));
-      const double b2 = sqrt((double)((n + mu) * (n - mu + 1) * (l + mu) * (l + mu - 1)));
       const cplx sB = mk(b0 * u0.x + b1 * up.x - b2 * um.x, b0 * u0.y + b1 * up.y - b2 * um.y);
       const cplx Bv = mk(-fb * sB.y, fb * sB.x); // times i fb (factor = (0, fb))
       const int w = NM - n0 + 1, e = rot_offX(NM, mu) + (n - n0) * w + (l - n0);

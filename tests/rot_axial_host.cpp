@@ -22,3 +22,15 @@ extern "C" int rot_axial_host_combined(int NM, const double k[2], double r, doub
   ob::rot_axial_pair(NM, ob::mk(k[0], k[1]), r, buf.data(), (ob::cplx *)Cp, (ob::cplx *)Cm, 0, 1, mode);
   return ob::rot_offX(NM, NM + 1);
 }
+
+// the tabulated path of the kernel (coefficients from rot_axial_tables_build), planar output
+extern "C" int rot_axial_host_tabulated(int NM, const double k[2], double r, double *Cp, double *Cm) {
+  std::vector<double> rec, emit;
+  std::vector<int> ridx, eidx;
+  ob::rot_axial_tables_build(NM, rec, emit, ridx, eidx);
+  ob::RotAxTab tab = {rec.data(), emit.data(), ridx.data(), eidx.data()};
+  std::vector<ob::cplx> buf((size_t)ob::rot_axial_buf_entries(NM), ob::mk(0, 0));
+  ob::rot_axial_pair(NM, ob::mk(k[0] * 0.7, k[1]), 1.3 * r, buf.data(), (ob::cplx *)Cp, (ob::cplx *)Cm, 0, 1, 2, &tab);
+  ob::rot_axial_pair(NM, ob::mk(k[0], k[1]), r, buf.data(), (ob::cplx *)Cp, (ob::cplx *)Cm, 0, 1, 2, &tab);
+  return ob::rot_offX(NM, NM + 1);
+}

@@ -146,9 +146,13 @@ def test_fundamental_only_silicon_below_the_sh_table_runs():
     solver.set_gmres(ob.GmresOpts(ob.OB_GMRES_BELOS, 1e-12, 200, 60, 5))
     res = solver.step()
     solver.close()
+    # the oracle's silicon model refuses the wavelength outright (it evaluates both permittivities): give it the
+    # fundamental permittivity the host layer read from the table as a fixed material
+    eps_r = complex(case.arrays()["eps"][0]) / U.EPS0
     orc = O.Case()
     for p in xyz:
-        orc.add_sphere([v * 1e-9 for v in p], 50e-9, 4, O.MODEL_SILICON, [1.0, 0.0])
+        model, params = U.fixed(eps_r, eps_r)
+        orc.add_sphere([v * 1e-9 for v in p], 50e-9, 4, model, params)
     orc.set_source(400e-9, np.pi / 4, np.pi / 2, 1.0, 0.0, False)
     orc.solve(O.SOLVER_DIRECT)
     cs = orc.cross_sections()

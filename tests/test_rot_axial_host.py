@@ -61,7 +61,7 @@ def test_device_source_of_the_axial_recursion_on_the_host(host_lib, NM, k, d):
                     assert abs(B[e] - Bz[_flat(n, mu), _flat(l, mu)]) < 1e-12 * sb, (mu, n, l)
 
 
-@pytest.mark.parametrize("NM", [1, 4, 10])
+@pytest.mark.parametrize("NM", [1, 4, 10, 13])
 def test_combined_output_of_the_axial_recursion(host_lib, NM):
     """combine = 1 / 2 (2 is what k_assemble_axial_only passes): A + B for every mu, A - B for mu >= 1 behind the mu = 0 block."""
     k, d = 2 * np.pi / 500e-9 * (1.1 + 0.03j), 230e-9
@@ -82,4 +82,9 @@ def test_combined_output_of_the_axial_recursion(host_lib, NM):
     host_lib.rot_axial_host_combined(int(NM), kk, C.c_double(d), Pp.ctypes.data_as(C.c_void_p),
                                      Pm.ctypes.data_as(C.c_void_p), 2)
     assert np.array_equal(Pp[:X] + 1j * Pp[X:], Cp) and np.array_equal(Pm[:X - NM * NM] + 1j * Pm[X - NM * NM:], Cm)
+    # the tabulated path the kernel runs (index-only coefficients from rot_axial_tables_build): bit-identical
+    Tp = np.zeros(2 * X)
+    Tm = np.zeros(2 * (X - NM * NM))
+    host_lib.rot_axial_host_tabulated(int(NM), kk, C.c_double(d), Tp.ctypes.data_as(C.c_void_p), Tm.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(Tp, Pp) and np.array_equal(Tm, Pm)
     assert not np.abs(B[:NM * NM]).any()      # mu = 0: B = 0, so Cm = Cp there and is not stored
