@@ -27,3 +27,15 @@ def gpu_ctx():
     ctx = ob.Context(0)
     yield ctx
     ctx.close()
+
+
+@pytest.fixture(autouse=True)
+def _oracle_threads_reset():
+    """The oracle's thread count is process-wide; the reference's AMOS (oracle/_ref) is not thread-safe: every test starts
+    and ends single-threaded unless it asks otherwise."""
+    yield
+    try:
+        from oracle import oracle as O
+        O.set_threads(1)
+    except Exception:
+        pass

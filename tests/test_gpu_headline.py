@@ -213,7 +213,6 @@ def test_c3_pinned_by_the_direct_solve():
     Q = ctx.source_ff()
     assert U.relerr(ctx.matvec(1, res["X_sca"]), Q) < 1e-12      # the device's direct solve solves ITS system
     solver.close()
-    O.set_threads(8)
     orc = O.Case()
     for p, r in zip(ELEVEN, ELEVEN_R):
         orc.add_sphere([v * 1e-9 for v in p], r * 1e-9, 12, U.SI[0], U.SI[1])
@@ -221,7 +220,11 @@ def test_c3_pinned_by_the_direct_solve():
     assert U.relerr(Q, orc.source()) < 1e-11
     # cross sections of the oracle's tight GMRES (seconds; its direct solve of N = 3696 takes minutes on the CPU): the two
     # differ by 3.7e-9 / 1.6e-9 from each other, see above
-    orc.solve(O.SOLVER_BELOS, tol=1e-13, maxit=2000, restart=300, max_restarts=5)
+    O.set_threads(8)
+    try:
+        orc.solve(O.SOLVER_BELOS, tol=1e-13, maxit=2000, restart=300, max_restarts=5)
+    finally:
+        O.set_threads(1)
     cs = orc.cross_sections()
     for key in ("ext", "sca"):
         assert abs(res[key] / cs[key] - 1) < 2e-8, (key, res[key], cs[key])

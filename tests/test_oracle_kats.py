@@ -394,13 +394,16 @@ def test_second_harmonic_at_nmax_10_is_solver_dependent_in_the_reference():
     the SH source reads them (PreconditionedMatrix.cpp:1347-1436): the oracle's direct solve and its Belos-flavoured GMRES at
     tol 1e-13 agree to 1e-9 on the fundamental harmonic and differ by more than 1e-6 in C_sca,SH.  This is why
     tests/test_gpu_headline.py checks the SH chain at nMax 10 stage by stage on identical inputs."""
-    O.set_threads(8)
     spec = U.random_cluster(4, 10, seed=5)
     orc = U.oracle_case(spec)
-    orc.solve(O.SOLVER_DIRECT)
-    cd, xd = orc.cross_sections(), orc.vector(0)
-    orc.solve(O.SOLVER_BELOS, tol=1e-13, maxit=600, restart=150, max_restarts=5)
-    cb, xb = orc.cross_sections(), orc.vector(0)
+    O.set_threads(8)
+    try:
+        orc.solve(O.SOLVER_DIRECT)
+        cd, xd = orc.cross_sections(), orc.vector(0)
+        orc.solve(O.SOLVER_BELOS, tol=1e-13, maxit=600, restart=150, max_restarts=5)
+        cb, xb = orc.cross_sections(), orc.vector(0)
+    finally:
+        O.set_threads(1)   # later test modules run the reference's AMOS, which is not thread-safe
     assert abs(cb["ext"] / cd["ext"] - 1) < 1e-9 and abs(cb["sca"] / cd["sca"] - 1) < 1e-9
     assert U.relerr(xb, xd) < 1e-9
     assert abs(cb["sca_SH"] / cd["sca_SH"] - 1) > 1e-6
