@@ -405,7 +405,9 @@ def main():
     barrier()
     lib.ob_timer(ctx, 0, None)
     for _ in range(args.steps):
-        res = solver.step(fetch=True)
+        # host arrays in (geometry, materials, incident coefficients), the four coefficient vectors and the cross sections
+        # out, into the host adaptor's own page-locked vectors (numpy views of them)
+        res = solver.step(fetch="view")
     lib.ob_timer(ctx, 1, C.byref(ms))
     barrier()
     e2e_ms = torch.tensor([ms.value], dtype=torch.float64, device="cuda")

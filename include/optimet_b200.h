@@ -64,6 +64,11 @@ int ob_comm_init(ob_ctx *ctx, const char uid[128], int rank, int world); /* NCCL
 int ob_set_shard(ob_ctx *ctx, int rank, int world);
 int ob_matvec_partial(ob_ctx *ctx, int harmonic, const double *x, double *acc);
 
+/* page-lock / release caller memory that ob_run copies results into (cudaHostRegister / cudaHostUnregister): the host
+ * layer does this once for its persistent coefficient vectors so that the device -> host copies run at PCIe speed */
+int ob_host_register(ob_ctx *ctx, void *ptr, size_t bytes);
+int ob_host_unregister(ob_ctx *ctx, void *ptr);
+
 /* ---- one process, several GPUs.  The reference's solver::factory returns the serial solver unconditionally in
  * non-MPI builds (srcAna/Solver.cpp:30-34): a serial Optimet3D gets all the GPUs of the box through this group.  One
  * context per device, NCCL communicators created inside the process, one host worker thread per GPU for every call;

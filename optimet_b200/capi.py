@@ -28,7 +28,7 @@ SYMBOLS = [
     "ob_source_ff", "ob_set_cg_tables", "ob_build_cg_tables", "ob_fetch_cg_table", "ob_source_sh", "ob_solve",
     "ob_unprecondition_ff", "ob_unprecondition_sh", "ob_run", "ob_cross_sections", "ob_timings", "ob_timer", "ob_set_option",
     "ob_measure_fp64_peak", "ob_dense_solve", "ob_aca_block", "ob_aca_compress", "ob_aca_stats", "ob_fields",
-    "ob_set_shard", "ob_matvec_partial", "ob_create_multi", "ob_destroy_multi", "ob_multi_size", "ob_multi_ctx",
+    "ob_set_shard", "ob_matvec_partial", "ob_host_register", "ob_host_unregister", "ob_create_multi", "ob_destroy_multi", "ob_multi_size", "ob_multi_ctx",
     "ob_multi_last_error", "ob_multi_set_cluster", "ob_multi_set_frequency", "ob_multi_set_incident", "ob_multi_set_option",
     "ob_multi_run",
 ]

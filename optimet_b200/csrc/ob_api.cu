@@ -1056,6 +1056,15 @@ int ob_set_cluster(ob_ctx *ctx, int nobj, const double *xyz_m, const double *rad
   need(nobj > 0, "No scatterers defined in input");
   need(nMax >= 1 && nMax <= OB_MAX_NMAX && nMaxS >= 1 && nMaxS <= OB_MAX_NMAX,
        "nMax out of range (1..13 supported by the shared-memory VTAC kernel)");
+  // the same cluster as last time (a wavelength sweep calls update() per wavelength): nothing to check or upload again
+  if(nobj == ctx->nobj && nMax == ctx->nMax && nMaxS == ctx->nMaxS && ctx->h_xyz.size() == 3 * (size_t)nobj &&
+     std::memcmp(ctx->h_xyz.data(), xyz_m, 3 * (size_t)nobj * sizeof(double)) == 0 &&
+     std::memcmp(ctx->h_radius.data(), radius_m, (size_t)nobj * sizeof(double)) == 0) {
+    ctx->fac_valid = false;
+    ctx->hs[0].assembled = ctx->hs[1].assembled = false;
+    ctx->have_inc = false;
+    return 0;
+  }
   // overlap check of Geometry::pushObject (srcAna/Geometry.cpp:39-52), O(N^2) on the host only for small clusters
   if(nobj <= 4096)
     for(int i = 0; i < nobj; ++i)
@@ -1319,6 +1328,20 @@ int ob_matvec(ob_ctx *ctx, int harmonic, const double *x, double *y) {
   matvec(ctx, harmonic, ctx->tmpA.p, ctx->tmpB.p);
   download(ctx, ctx->tmpB.p, y, N);
   flush_matvec_timing(ctx);
+  OB_END
+}
+
+// page-lock caller memory the coefficient vectors are copied into (cudaHostRegister): device -> host at PCIe speed
+int ob_host_register(ob_ctx *ctx, void *ptr, size_t bytes) {
+  OB_BEGIN
+  need(ptr != nullptr && bytes > 0, "ob_host_register: empty range");
+  OB_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+  OB_END
+}
+int ob_host_unregister(ob_ctx *ctx, void *ptr) {
+  OB_BEGIN
+  if(ptr)
+    cudaHostUnregister(ptr);
   OB_END
 }
 

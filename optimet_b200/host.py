@@ -14,7 +14,7 @@ _lib = None
 HOST_SYMBOLS = ["obh_load_xml", "obh_load_xml_string", "obh_free", "obh_error", "obh_info", "obh_set_wavelength",
                 "obh_get_arrays", "obh_gmres_defaults", "obh_solver_create", "obh_solver_free", "obh_solver_error",
                 "obh_solver_ctx", "obh_solver_comm", "obh_solver_set_gmres", "obh_solver_set_aca_mode", "obh_solver_step", "obh_scan",
-                "obh_field_simulation", "obh_grid_points"]
+                "obh_field_simulation", "obh_grid_points", "obh_solver_vectors"]
 
 
 def load():
@@ -181,13 +181,20 @@ class Solver:
         i = self.case.info()
         N1 = 2 * i["nMax"] * (i["nMax"] + 2) * i["nobj"]
         N2 = 2 * i["nMaxS"] * (i["nMaxS"] + 2) * i["nobj"]
+        view = fetch == "view"   # results stay in the solver's own page-locked vectors; numpy views, valid until the next step
         outs = [np.zeros(N1, dtype=np.complex128), np.zeros(N1, dtype=np.complex128),
-                np.zeros(N2, dtype=np.complex128), np.zeros(N2, dtype=np.complex128)] if fetch else [None] * 4
+                np.zeros(N2, dtype=np.complex128), np.zeros(N2, dtype=np.complex128)] if (fetch and not view) else [None] * 4
         cs = (C.c_double * 5)()
         it = (C.c_int * 2)()
         self._chk(load().obh_solver_step(self.s, self.case.h, C.c_double(lam_m), _p(outs[0]), _p(outs[1]), _p(outs[2]),
                                         _p(outs[3]), cs, it))
         res = dict(ext=cs[0], sca=cs[1], abs=cs[2], sca_SH=cs[3], abs_SH=cs[4], iters_ff=it[0], iters_sh=it[1])
+        if view:
+            ptrs = (C.POINTER(C.c_double) * 4)()
+            sizes = (C.c_long * 4)()
+            load().obh_solver_vectors(self.s, ptrs, sizes)
+            outs = [np.ctypeslib.as_array(ptrs[k], shape=(2 * sizes[k],)).view(np.complex128) if sizes[k] else
+                    np.zeros(0, dtype=np.complex128) for k in range(4)]
         if fetch:
             res.update(X_sca=outs[0], X_int=outs[1], X_sca_SH=outs[2], X_int_SH=outs[3])
         return res

@@ -799,12 +799,18 @@ void B200Matrix::solve(Vector &X_sca_, Vector &X_int_, Vector &X_sca_SH, Vector 
   const size_t N1 = scattering_size();
   const size_t nS = geometry->nMaxS();
   const size_t N2 = 2 * nS * (nS + 2) * geometry->objects.size();
-  X_sca_.assign(N1, t_complex(0, 0));
-  X_int_.assign(N1, t_complex(0, 0));
+  // every entry is overwritten by the device -> host copies of ob_run: size only (a caller that keeps its vectors
+  // across wavelengths, like the C ABI layer does with page-locked ones, pays no allocation or clearing)
+  if(X_sca_.size() != N1)
+    X_sca_.assign(N1, t_complex(0, 0));
+  if(X_int_.size() != N1)
+    X_int_.assign(N1, t_complex(0, 0));
   const bool sh = incWave->SH_cond;
   if(sh) {
-    X_sca_SH.assign(N2, t_complex(0, 0));
-    X_int_SH.assign(N2, t_complex(0, 0));
+    if(X_sca_SH.size() != N2)
+      X_sca_SH.assign(N2, t_complex(0, 0));
+    if(X_int_SH.size() != N2)
+      X_int_SH.assign(N2, t_complex(0, 0));
     if(CGcoeff.size() == 9 && !tables_set) {
       const double *t[9];
       for(int i = 0; i < 9; ++i)

@@ -12,6 +12,24 @@ struct HostCase {
 struct HostSolver {
   std::unique_ptr<solver::B200Matrix> s;
   std::string err;
+  // the coefficient vectors of the last step, kept across steps and page-locked once they have their size
+  Vector x[4];
+  void *pinned[4] = {nullptr, nullptr, nullptr, nullptr};
+  void pin() {
+    for(int i = 0; i < 4; ++i)
+      if(!x[i].empty() && pinned[i] != (void *)x[i].data()) {
+        if(pinned[i])
+          ob_host_unregister(s->context(), pinned[i]);
+        pinned[i] = nullptr;
+        if(ob_host_register(s->context(), (void *)x[i].data(), x[i].size() * sizeof(t_complex)) == 0)
+          pinned[i] = (void *)x[i].data();
+      }
+  }
+  ~HostSolver() {
+    for(int i = 0; i < 4; ++i)
+      if(pinned[i] && s)
+        ob_host_unregister(s->context(), pinned[i]);
+  }
 };
 void set_err(char *err, int errlen, const char *msg) {
   if(err && errlen > 0) {
@@ -153,20 +171,40 @@ int obh_solver_step(void *s_, void *h, double lambda_m, double *X_sca, double *X
     c->run.geometry->update(c->run.excitation);
   }
   s->s->update(c->run);
-  Vector xs, xi, xss, xis;
-  s->s->solve(xs, xi, xss, xis);
-  auto put = [](Vector const &v, double *dst) {
+  {
+    // size the persistent vectors before the solve so that they can be page-locked (solve() keeps vectors of the right
+    // size as they are)
+    const size_t nobj = c->run.geometry->objects.size();
+    const size_t n1 = c->run.geometry->nMax(), n2 = c->run.geometry->nMaxS();
+    const size_t N1 = 2 * n1 * (n1 + 2) * nobj, N2 = 2 * n2 * (n2 + 2) * nobj;
+    const size_t want[4] = {N1, N1, c->run.excitation->SH_cond ? N2 : 0, c->run.excitation->SH_cond ? N2 : 0};
+    for(int i = 0; i < 4; ++i)
+      if(s->x[i].size() != want[i])
+        s->x[i].assign(want[i], t_complex(0, 0));
+    s->pin();
+  }
+  s->s->solve(s->x[0], s->x[1], s->x[2], s->x[3]);
+  auto put = [](Vector const &v, double *dst) { // optional copies into caller buffers (obh_solver_vectors gives views)
     if(dst && !v.empty())
       std::memcpy(dst, v.data(), v.size() * sizeof(t_complex));
   };
-  put(xs, X_sca);
-  put(xi, X_int);
-  put(xss, X_sca_SH);
-  put(xis, X_int_SH);
+  put(s->x[0], X_sca);
+  put(s->x[1], X_int);
+  put(s->x[2], X_sca_SH);
+  put(s->x[3], X_int_SH);
   s->s->cross_sections(cs);
   iters[0] = s->s->iterations(1);
   iters[1] = s->s->iterations(2);
   OBH_CATCH(s)
+}
+// the solver's own (page-locked) coefficient vectors of the last step: X_sca, X_int, X_sca_SH, X_int_SH
+int obh_solver_vectors(void *s_, const double *ptrs[4], long sizes[4]) {
+  HostSolver *s = (HostSolver *)s_;
+  for(int i = 0; i < 4; ++i) {
+    ptrs[i] = s->x[i].empty() ? nullptr : (const double *)s->x[i].data();
+    sizes[i] = (long)s->x[i].size();
+  }
+  return 0;
 }
 // Simulation::scan_wavelengths; lines: lambda, abs_FF, sca_FF, sca_SH, abs_SH, ext_FF, iters_FF, iters_SH per wavelength
 int obh_scan(void *s_, void *h, const char *caseFile, double *lines, int maxlines, int *nlines) {
