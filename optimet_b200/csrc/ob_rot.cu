@@ -130,24 +130,20 @@ k_assemble_axial(VtacTables tb, const double *__restrict__ xyz, cplx k, const in
 // GPU against the vtac_block path and the oracle (tests/test_gpu_rot.py).
 // ---------------------------------------------------------------------------------------------
 #define ROT_AX_WARPS 4
-static size_t rot_axial_smem_bytes(int NM) { return (size_t)ROT_AX_WARPS * rot_axial_buf_entries(NM) * sizeof(cplx); }
+static size_t rot_axial_smem_bytes(int NM) { return (size_t)ROT_AX_WARPS * rot_axial_fast_entries(NM) * sizeof(cplx); }
 __global__ void __launch_bounds__(ROT_AX_WARPS * 32)
 k_assemble_axial_only(const double *__restrict__ xyz, cplx k, const int2 *__restrict__ pair_ij, long npairs,
                       unsigned char *__restrict__ recs, RotLayout L, RotAxTab tab) {
   extern __shared__ __align__(16) unsigned char smem_ax[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int entries = rot_axial_buf_entries(L.NM);
-  cplx *buf = (cplx *)smem_ax + (size_t)warp * entries;
-  for(int e = lane; e < entries; e += 32)
-    buf[e] = mk(0, 0);
-  __syncwarp();
+  cplx *buf = (cplx *)smem_ax + (size_t)warp * rot_axial_fast_entries(L.NM);
   for(long q = (long)blockIdx.x * ROT_AX_WARPS + warp; q < npairs; q += (long)gridDim.x * ROT_AX_WARPS) {
     const int2 ij = pair_ij[q];
     const double x = xyz[3 * ij.x] - xyz[3 * ij.y], y = xyz[3 * ij.x + 1] - xyz[3 * ij.y + 1],
                  z = xyz[3 * ij.x + 2] - xyz[3 * ij.y + 2];
     const double r = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
     unsigned char *rec = recs + (size_t)q * L.rec_bytes;
-    rot_axial_pair(L.NM, k, r, buf, (cplx *)(rec + L.offCp), (cplx *)(rec + L.offCm), lane, 32, 2, &tab);
+    rot_axial_pair_fast(L.NM, k, r, buf, (double *)(rec + L.offCp), (double *)(rec + L.offCm), lane, 32, tab);
     __syncwarp();
   }
 }
@@ -155,7 +151,7 @@ k_assemble_axial_only(const double *__restrict__ xyz, cplx k, const int2 *__rest
 // index-only coefficient tables of the axial recursion, one set per (device, nMax)
 struct RotAxTabDev {
   int NM = -1;
-  RotAxTab t = {nullptr, nullptr, nullptr, nullptr};
+  RotAxTab t = {nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 static RotAxTabDev g_axtab[16][OB_MAX_NMAX + 1];
 template <class T> static const T *rot_to_device(std::vector<T> const &v) {
@@ -173,12 +169,13 @@ static RotAxTab const &rot_axtab(int NM) {
   if(e.NM == NM)
     return e.t;
   std::vector<double> rec, emit;
-  std::vector<int> ridx, eidx;
-  rot_axial_tables_build(NM, rec, emit, ridx, eidx);
+  std::vector<int> ridx, eidx, eout;
+  rot_axial_tables_build(NM, rec, emit, ridx, eidx, eout);
   e.t.rec = rot_to_device(rec);
   e.t.emit = rot_to_device(emit);
   e.t.ridx = rot_to_device(ridx);
   e.t.eidx = rot_to_device(eidx);
+  e.t.eout = rot_to_device(eout);
   e.NM = NM;
   return e.t;
 }
@@ -969,7 +966,8 @@ void launch_assemble_rot(VtacTableSet const &ts, const double *xyz, cplx k, cons
   if(g_rot_assembly == 1) {
     const size_t sm = rot_axial_smem_bytes(L.NM);
     OB_CUDA(cudaFuncSetAttribute((const void *)k_assemble_axial_only, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    const long ctas = std::min<long>((npairs + ROT_AX_WARPS - 1) / ROT_AX_WARPS, (long)sm_count * 8);
+    const long per_sm = std::max<long>(1, std::min<long>(16, (long)(220 * 1024) / (long)(sm + 1024)));
+    const long ctas = std::min<long>((npairs + ROT_AX_WARPS - 1) / ROT_AX_WARPS, (long)sm_count * per_sm);
     k_assemble_axial_only<<<(unsigned)ctas, ROT_AX_WARPS * 32, sm, st>>>(xyz, k, pair_ij, npairs, recs, L, rot_axtab(L.NM));
   } else {
     OB_CUDA(cudaFuncSetAttribute((const void *)k_assemble_axial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ts.smem));

@@ -46,10 +46,12 @@ __host__ __device__ inline int rot_axial_buf_entries(int NM) { return 3 * (NM + 
 // which stays for the host check and as the specification.
 //   rec  [offR(n) + t][4] = c0, c1, c2, 1 / denominator     of item t = m * span + (l - m) of level n
 //   emit [offE(n) + t][8] = fa, a0, a1, a2, fb, b0, b1, b2   of item t = mu * NM + (l - 1) of level n
-//   ridx / eidx           = m | l << 8  /  mu | l << 8 | live << 16
+//   ridx = m | l << 8 | flags << 16: 1 live, 2 beta(n-1, m, l-1) exists, 4 beta(n-2, m, l) exists, 8 sectorial step
+//   eidx = mu | l << 8 | flags << 16: 1 live, then one bit per term of the A / B sums that exists (2, 4, 8: beta(mu, l),
+//          beta(mu + 1, l), beta(|mu - 1|, l); 16, 32, 64: the same at l - 1); eout = index of the entry in the record
 struct RotAxTab {
   const double *rec, *emit;
-  const int *ridx, *eidx;
+  const int *ridx, *eidx, *eout;
 };
 __host__ __device__ inline int rot_axial_offR(int NM, int n) { // sum_{j=1}^{n-1} (j + 1)(2 NM - j + 1)
   int o = 0;
@@ -59,20 +61,27 @@ __host__ __device__ inline int rot_axial_offR(int NM, int n) { // sum_{j=1}^{n-1
 }
 __host__ __device__ inline int rot_axial_offE(int NM, int n) { return NM * ((n - 1) * (n + 2) / 2); } // NM sum_{j<n} (j + 1)
 inline void rot_axial_tables_build(int NM, std::vector<double> &rec, std::vector<double> &emit, std::vector<int> &ridx,
-                                   std::vector<int> &eidx) {
+                                   std::vector<int> &eidx, std::vector<int> &eout) {
   const int LL = 2 * NM;
   rec.assign((size_t)rot_axial_offR(NM, NM + 1) * 4, 0.0);
   ridx.assign((size_t)rot_axial_offR(NM, NM + 1), 0);
   emit.assign((size_t)rot_axial_offE(NM, NM + 1) * 8, 0.0);
   eidx.assign((size_t)rot_axial_offE(NM, NM + 1), 0);
+  eout.assign((size_t)rot_axial_offE(NM, NM + 1), 0);
   for(int n = 1; n <= NM; ++n) {
     const int span = LL - n + 1;
     for(int t = 0; t < (n + 1) * span; ++t) {
       const int m = t / span, l = m + (t - m * span);
       double *c = &rec[((size_t)rot_axial_offR(NM, n) + t) * 4];
-      ridx[(size_t)rot_axial_offR(NM, n) + t] = m | (l << 8) | ((l <= LL - n ? 1 : 0) << 16);
-      if(l > LL - n)
+      if(l > LL - n) {
+        ridx[(size_t)rot_axial_offR(NM, n) + t] = m | (l << 8);
         continue;
+      }
+      {
+        const int mr = m == n ? n - 1 : m;
+        const int fl = 1 | (l - 1 >= mr ? 2 : 0) | ((m != n && n - 2 >= m) ? 4 : 0) | (m == n ? 8 : 0);
+        ridx[(size_t)rot_axial_offR(NM, n) + t] = m | (l << 8) | (fl << 16);
+      }
       if(m == n) {
         c[0] = l - 1 >= n - 1 ? ta_b_plus(l - 1, n - 1) : 0.0;
         c[1] = ta_b_minus(l + 1, n - 1);
@@ -89,9 +98,18 @@ inline void rot_axial_tables_build(int NM, std::vector<double> &rec, std::vector
       const int mu = t / NM, l = 1 + (t - mu * NM);
       const int n0 = rot_n0(mu);
       const bool live = !(n < n0 || l < n0);
-      eidx[(size_t)rot_axial_offE(NM, n) + t] = mu | (l << 8) | ((live ? 1 : 0) << 16);
-      if(!live)
+      if(!live) {
+        eidx[(size_t)rot_axial_offE(NM, n) + t] = mu | (l << 8);
         continue;
+      }
+      {
+        const int mp1 = mu + 1, mm1 = mu > 0 ? mu - 1 : 1, lm = l - 1;
+        const int fl = 1 | ((mu <= n && mu <= l) ? 2 : 0) | ((mp1 <= n && mp1 <= l) ? 4 : 0) | ((mm1 <= n && mm1 <= l) ? 8 : 0) |
+                       ((mu <= n && mu <= lm) ? 16 : 0) | ((mp1 <= n && mp1 <= lm) ? 32 : 0) | ((mm1 <= n && mm1 <= lm) ? 64 : 0);
+        eidx[(size_t)rot_axial_offE(NM, n) + t] = mu | (l << 8) | (fl << 16);
+        const int w = NM - n0 + 1;
+        eout[(size_t)rot_axial_offE(NM, n) + t] = rot_offX(NM, mu) + (n - n0) * w + (l - n0);
+      }
       double *c = &emit[((size_t)rot_axial_offE(NM, n) + t) * 8];
       c[0] = 0.5 / sqrt((double)(l * (l + 1) * n * (n + 1)));
       c[1] = 2.0 * mu * mu;
@@ -111,7 +129,7 @@ inline void rot_axial_tables_build(int NM, std::vector<double> &rec, std::vector
 // combine = 2 (record layout of ob_rot.cu): the same values as planes of doubles, Aout -> [Re(A+B)[X] | Im(A+B)[X]],
 // Bout -> [Re(A-B)[X - NM^2] | Im(A-B)[X - NM^2]], X = rot_offX(NM, NM + 1).
 __host__ __device__ inline void rot_axial_pair(int NM, cplx k, double r, cplx *buf, cplx *Aout, cplx *Bout, int lane,
-                                               int nlanes, int combine = 0, const RotAxTab *tab = nullptr) {
+                                               int nlanes, int combine = 0) {
   const int LL = 2 * NM, W = LL + 3, CH = NM + 2;
   // seeds (n = m = 0): sqrt(4 pi) (-1)^l Y_l0(0) h_l = (-1)^l sqrt(2l + 1) h_l(k r); every lane runs the short upward
   // Hankel recurrence and keeps the orders it owns
@@ -128,21 +146,6 @@ __host__ __device__ inline void rot_axial_pair(int NM, cplx k, double r, cplx *b
     cplx *cur = buf + (size_t)(n % 3) * CH * W;
     const cplx *p1 = buf + (size_t)((n - 1) % 3) * CH * W, *p2 = buf + (size_t)((n + 1) % 3) * CH * W; // n-1, n-2
     const int span = LL - n + 1; // l in [m, LL - n]: index t = m * span + (l - m) over a (n + 1) x span rectangle
-    if(tab) { // tabulated coefficients: same expressions, evaluated once per nMax (rot_axial_tables_build)
-      const double *rc = tab->rec + (size_t)rot_axial_offR(NM, n) * 4;
-      const int *ri = tab->ridx + rot_axial_offR(NM, n);
-      for(int t = lane; t < (n + 1) * span; t += nlanes) {
-        const int ix = ri[t], m = ix & 0xff, l = (ix >> 8) & 0xff;
-        if(!(ix >> 16))
-          continue;
-        const double c0 = rc[4 * t], c1 = rc[4 * t + 1], c2 = rc[4 * t + 2], inv = rc[4 * t + 3];
-        const int mr = m == n ? n - 1 : m; // sectorial step reads chain n - 1 of the previous level
-        const cplx lo = l - 1 >= mr ? p1[mr * W + (l - 1)] : mk(0, 0);
-        const cplx up = p1[mr * W + (l + 1)];
-        const cplx o = (m != n && n - 2 >= m) ? p2[m * W + l] : mk(0, 0);
-        cur[m * W + l] = mk((lo.x * c0 + up.x * c1 - o.x * c2) * inv, (lo.y * c0 + up.y * c1 - o.y * c2) * inv);
-      }
-    } else
     for(int t = lane; t < (n + 1) * span; t += nlanes) {
       const int m = t / span, l = m + (t - m * span);
       if(l > LL - n)
@@ -167,30 +170,17 @@ __host__ __device__ inline void rot_axial_pair(int NM, cplx k, double r, cplx *b
     OB_SYNCWARP();
     // A, B of column degree n for every mu <= n and row degree l (Coupling.cpp:30-51 with k = m = mu)
     for(int t = lane; t < (n + 1) * NM; t += nlanes) {
-      int mu, l;
-      double fa, a0, a1, a2, fb, b0, b1, b2;
-      if(tab) { // tabulated: same expressions, evaluated once per nMax (rot_axial_tables_build)
-        const int ix = tab->eidx[rot_axial_offE(NM, n) + t];
-        if(!(ix >> 16))
-          continue;
-        mu = ix & 0xff;
-        l = (ix >> 8) & 0xff;
-        const double *ec = tab->emit + ((size_t)rot_axial_offE(NM, n) + t) * 8;
-        fa = ec[0], a0 = ec[1], a1 = ec[2], a2 = ec[3], fb = ec[4], b0 = ec[5], b1 = ec[6], b2 = ec[7];
-      } else {
-        mu = t / NM;
-        l = 1 + (t - mu * NM);
-        if(n < rot_n0(mu) || l < rot_n0(mu))
-          continue;
-        fa = 0.5 / sqrt((double)(l * (l + 1) * n * (n + 1)));
-        a0 = 2.0 * mu * mu;
-        a1 = sqrt((double)((n - mu) * (n + mu + 1) * (l - mu) * (l + mu + 1)));
-        a2 = sqrt((double)((n + mu) * (n - mu + 1) * (l + mu) * (l - mu + 1)));
-        fb = -0.5 * sqrt((2.0 * l + 1.0) / ((double)(2 * l - 1) * (double)(l * (l + 1)) * (double)(n * (n + 1))));
-        b0 = 2.0 * mu * sqrt((double)((l - mu) * (l + mu)));
-        b1 = sqrt((double)((n - mu) * (n + mu + 1) * (l - mu) * (l - mu - 1)));
-        b2 = sqrt((double)((n + mu) * (n - mu + 1) * (l + mu) * (l + mu - 1)));
-      }
+      const int mu = t / NM, l = 1 + (t - mu * NM);
+      if(n < rot_n0(mu) || l < rot_n0(mu))
+        continue;
+      const double fa = 0.5 / sqrt((double)(l * (l + 1) * n * (n + 1)));
+      const double a0 = 2.0 * mu * mu;
+      const double a1 = sqrt((double)((n - mu) * (n + mu + 1) * (l - mu) * (l + mu + 1)));
+      const double a2 = sqrt((double)((n + mu) * (n - mu + 1) * (l + mu) * (l - mu + 1)));
+      const double fb = -0.5 * sqrt((2.0 * l + 1.0) / ((double)(2 * l - 1) * (double)(l * (l + 1)) * (double)(n * (n + 1))));
+      const double b0 = 2.0 * mu * sqrt((double)((l - mu) * (l + mu)));
+      const double b1 = sqrt((double)((n - mu) * (n + mu + 1) * (l - mu) * (l - mu - 1)));
+      const double b2 = sqrt((double)((n + mu) * (n - mu + 1) * (l + mu) * (l + mu - 1)));
       const int n0 = rot_n0(mu);
       const int mp1 = mu + 1, mm1 = mu > 0 ? mu - 1 : 1; // |mu - 1|: beta(n,-m,l,-m) = beta(n,m,l,m)
       // beta(n, m', l', m') at this level; zero outside 0 <= m' <= min(n, l')
@@ -224,6 +214,73 @@ __host__ __device__ inline void rot_axial_pair(int NM, cplx k, double r, cplx *b
       }
     }
     OB_SYNCWARP();
+  }
+}
+
+// The path the kernel runs: the same recursion and emission with every index-only quantity read from RotAxTab, planar
+// record output (combine = 2 of rot_axial_pair), and TWO level buffers instead of three: level n overwrites level n - 2 in
+// place (an item reads the n - 2 value of its own (m, l) only, then writes there; everything else it reads is level
+// n - 1).  buf: [2][NM + 2][2 NM + 3] complex per warp; stale entries are never read (the flags say which terms exist).
+// tests/test_rot_axial_host.py holds it bit-identical to rot_axial_pair on the host.
+__host__ __device__ inline int rot_axial_fast_entries(int NM) { return 2 * (NM + 2) * (2 * NM + 3); }
+__host__ __device__ inline void rot_axial_pair_fast(int NM, cplx k, double r, cplx *buf, double *Cp, double *Cm, int lane,
+                                                    int nlanes, RotAxTab const &tab) {
+  const int LL = 2 * NM, W = LL + 3, CH = NM + 2;
+  const int X = rot_offX(NM, NM + 1), XM = X - NM * NM;
+  {
+    cplx h[2 * 13 + 2];
+    sph_hankel1(cscale(k, r), LL + 1, h);
+    for(int l = lane; l <= LL; l += nlanes) {
+      const double f = ((l & 1) ? -1.0 : 1.0) * sqrt(2.0 * l + 1.0);
+      buf[l] = cscale(h[l], f); // level 0, chain 0
+    }
+  }
+  OB_SYNCWARP();
+  int offR = 0, offE = 0;
+  for(int n = 1; n <= NM; ++n) {
+    cplx *cur = buf + (size_t)(n & 1) * CH * W;            // holds level n - 2, becomes level n
+    const cplx *p1 = buf + (size_t)((n & 1) ^ 1) * CH * W; // level n - 1
+    const int nrec = (n + 1) * (LL - n + 1), nem = (n + 1) * NM;
+    const double *rc = tab.rec + (size_t)offR * 4;
+    const int *ri = tab.ridx + offR;
+    for(int t = lane; t < nrec; t += nlanes) {
+      const int ix = ri[t], fl = ix >> 16;
+      if(!(fl & 1))
+        continue;
+      const int m = ix & 0xff, l = (ix >> 8) & 0xff;
+      const double c0 = rc[4 * t], c1 = rc[4 * t + 1], c2 = rc[4 * t + 2], inv = rc[4 * t + 3];
+      const cplx *q = p1 + ((fl & 8) ? n - 1 : m) * W + l; // the sectorial step reads chain n - 1
+      const cplx lo = (fl & 2) ? q[-1] : mk(0, 0), up = q[1];
+      const cplx o = (fl & 4) ? cur[m * W + l] : mk(0, 0);
+      cur[m * W + l] = mk((lo.x * c0 + up.x * c1 - o.x * c2) * inv, (lo.y * c0 + up.y * c1 - o.y * c2) * inv);
+    }
+    OB_SYNCWARP();
+    const double *ec = tab.emit + (size_t)offE * 8;
+    const int *ei = tab.eidx + offE, *eo = tab.eout + offE;
+    for(int t = lane; t < nem; t += nlanes) {
+      const int ix = ei[t], fl = ix >> 16;
+      if(!(fl & 1))
+        continue;
+      const int mu = ix & 0xff, l = (ix >> 8) & 0xff, mm1 = mu > 0 ? mu - 1 : 1;
+      const double *c = ec + 8 * t;
+      const cplx *b0p = cur + mu * W + l, *bpp = b0p + W, *bmp = cur + mm1 * W + l;
+      const cplx t0 = (fl & 2) ? b0p[0] : mk(0, 0), tp = (fl & 4) ? bpp[0] : mk(0, 0), tm = (fl & 8) ? bmp[0] : mk(0, 0);
+      const cplx u0 = (fl & 16) ? b0p[-1] : mk(0, 0), up = (fl & 32) ? bpp[-1] : mk(0, 0), um = (fl & 64) ? bmp[-1] : mk(0, 0);
+      const double fa = c[0], a0 = c[1], a1 = c[2], a2 = c[3], fb = c[4], b0 = c[5], b1 = c[6], b2 = c[7];
+      const cplx Av = mk(fa * (a0 * t0.x + a1 * tp.x + a2 * tm.x), fa * (a0 * t0.y + a1 * tp.y + a2 * tm.y));
+      const cplx sB = mk(b0 * u0.x + b1 * up.x - b2 * um.x, b0 * u0.y + b1 * up.y - b2 * um.y);
+      const cplx Bv = mk(-fb * sB.y, fb * sB.x); // times i fb
+      const int e = eo[t];
+      Cp[e] = Av.x + Bv.x;
+      Cp[X + e] = Av.y + Bv.y;
+      if(mu >= 1) {
+        Cm[e - NM * NM] = Av.x - Bv.x;
+        Cm[XM + e - NM * NM] = Av.y - Bv.y;
+      }
+    }
+    OB_SYNCWARP();
+    offR += nrec;
+    offE += nem;
   }
 }
 

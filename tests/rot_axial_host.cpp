@@ -23,14 +23,15 @@ extern "C" int rot_axial_host_combined(int NM, const double k[2], double r, doub
   return ob::rot_offX(NM, NM + 1);
 }
 
-// the tabulated path of the kernel (coefficients from rot_axial_tables_build), planar output
+// the tabulated path the kernel runs (coefficients and flags from rot_axial_tables_build, two level buffers), planar
+// output; two pairs through the same buffers: the second run sees the stale level data a warp sees between pairs
 extern "C" int rot_axial_host_tabulated(int NM, const double k[2], double r, double *Cp, double *Cm) {
   std::vector<double> rec, emit;
-  std::vector<int> ridx, eidx;
-  ob::rot_axial_tables_build(NM, rec, emit, ridx, eidx);
-  ob::RotAxTab tab = {rec.data(), emit.data(), ridx.data(), eidx.data()};
-  std::vector<ob::cplx> buf((size_t)ob::rot_axial_buf_entries(NM), ob::mk(0, 0));
-  ob::rot_axial_pair(NM, ob::mk(k[0] * 0.7, k[1]), 1.3 * r, buf.data(), (ob::cplx *)Cp, (ob::cplx *)Cm, 0, 1, 2, &tab);
-  ob::rot_axial_pair(NM, ob::mk(k[0], k[1]), r, buf.data(), (ob::cplx *)Cp, (ob::cplx *)Cm, 0, 1, 2, &tab);
+  std::vector<int> ridx, eidx, eout;
+  ob::rot_axial_tables_build(NM, rec, emit, ridx, eidx, eout);
+  ob::RotAxTab tab = {rec.data(), emit.data(), ridx.data(), eidx.data(), eout.data()};
+  std::vector<ob::cplx> buf((size_t)ob::rot_axial_fast_entries(NM), ob::mk(1e300, -1e300)); // poison: must never be read
+  ob::rot_axial_pair_fast(NM, ob::mk(k[0] * 0.7, k[1]), 1.3 * r, buf.data(), Cp, Cm, 0, 1, tab);
+  ob::rot_axial_pair_fast(NM, ob::mk(k[0], k[1]), r, buf.data(), Cp, Cm, 0, 1, tab);
   return ob::rot_offX(NM, NM + 1);
 }
