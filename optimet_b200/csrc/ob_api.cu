@@ -167,6 +167,8 @@ struct ob_ctx {
   std::vector<char> mv_ev_arn;    // whether slot 3 of an entry was recorded
   hcd *h_pinned = nullptr; // pinned staging for the per-iteration Hessenberg column read-back
   size_t h_pinned_cap = 0;
+  cudaEvent_t evh = nullptr; // read-back of the Hessenberg column complete
+  bool speculate = true;     // enqueue the next operator apply ahead of the host's convergence test (gmres_belos)
 
   int N(int h) const { return 2 * hs[h - 1].n * nobj; }
   int Mloc(int h) const { return 2 * hs[h - 1].n * count; }
@@ -581,15 +583,30 @@ static GmresOut gmres_belos(ob_ctx *c, int harmonic, const cplx *b, cplx *x, dou
     g.assign(1, hcd(beta, 0));
     int j = 0;
     bool staged = false; // v_j already staged for the pair operator by the previous fused step
+    bool in_flight = false; // the product with v_j was enqueued ahead of the host's convergence test of step j - 1
+    double rel_m1 = 1.0, rel_m2 = 1.0; // implicit residuals of the two previous steps of this cycle
     while(j < num_blocks && out.iters < max_iters) {
-      matvec(c, harmonic, V + (size_t)j * N, w, staged);
+      if(!in_flight)
+        matvec(c, harmonic, V + (size_t)j * N, w, staged);
+      in_flight = false;
       double norm_after;
       if(fused) {
         // classical Gram-Schmidt + DGKS second pass (decided on the device) + normalisation: one launch
         fused_step(c, harmonic, j, 0);
         staged = c->hs[harmonic - 1].mode == 1;
         OB_CUDA(cudaMemcpyAsync(c->h_pinned, c->h_dev.p, (size_t)(j + 3) * sizeof(cplx), cudaMemcpyDeviceToHost, c->st));
-        OB_CUDA(cudaStreamSynchronize(c->st));
+        OB_CUDA(cudaEventRecord(c->evh, c->st));
+        // The host's part of a step (Hessenberg column read-back, Givens rotations, convergence test) sits between two
+        // operator applies.  v_{j+1} is already on the device, so the next apply is enqueued BEFORE waiting for the
+        // read-back whenever the residual history predicts that step j does not converge (geometric extrapolation of the
+        // last two implicit residuals, one decade of margin); a wrong prediction costs one product whose result is never
+        // used (it only writes the work vector w).  The iterates, the iteration count and every result are unchanged.
+        if(c->speculate && !c->trace && j >= 2 && j + 1 < num_blocks && out.iters + 1 < max_iters &&
+           rel_m1 * std::min(1.0, rel_m1 / rel_m2) > 10.0 * tol) {
+          matvec(c, harmonic, V + (size_t)(j + 1) * N, w, staged);
+          in_flight = true;
+        }
+        OB_CUDA(cudaEventSynchronize(c->evh));
         h.assign(c->h_pinned, c->h_pinned + j + 3);
         norm_after = std::sqrt(h[j + 2].real());
         h.resize(j + 2);
@@ -651,6 +668,8 @@ static GmresOut gmres_belos(ob_ctx *c, int harmonic, const cplx *b, cplx *x, dou
       ++j;
       ++out.iters;
       rel = std::abs(g[j]) / r0norm;
+      rel_m2 = rel_m1;
+      rel_m1 = rel;
       if(rel <= tol) {
         out.converged = true;
         break;
@@ -943,6 +962,7 @@ int ob_create(int device, ob_ctx **out) {
     OB_CUDA(cudaEventCreate(&c->evm1));
     OB_CUDA(cudaEventCreate(&c->evt0));
     OB_CUDA(cudaEventCreate(&c->evt1));
+    OB_CUDA(cudaEventCreateWithFlags(&c->evh, cudaEventDisableTiming));
     c->mv_ev.resize(256);
     c->mv_ev_arn.assign(64, 0);
     for(auto &e : c->mv_ev)
@@ -1699,6 +1719,8 @@ int ob_set_option(ob_ctx *ctx, const char *name, double value) {
     ctx->trace = value != 0;
   else if(n == "fused_arnoldi")
     ctx->fused_arnoldi = value != 0;
+  else if(n == "speculate") // 1 (default): the next apply is enqueued ahead of the host's convergence test when safe
+    ctx->speculate = value != 0;
   else if(n == "pairs_kb" || n == "pairs_groups") { // tuning: columns per pipeline stage / column groups (0 = auto)
     static int kb = 0, gr = 0;
     (n == "pairs_kb" ? kb : gr) = (int)value;

@@ -322,6 +322,9 @@ k_rot_tables(const double *__restrict__ xyz, const int2 *__restrict__ pair_ij, l
 // apply
 // ---------------------------------------------------------------------------------------------
 #define ROT_WARPS 4
+#ifndef ROT_MIN_CTAS
+#define ROT_MIN_CTAS 3 // resident CTAs per SM the kernel is compiled for (168 registers: the natural count is 176 at nMax 10)
+#endif
 #define ROT_THREADS (32 * ROT_WARPS)
 #define ROT_MAX_UNITS 32
 // Static work lists, evaluated at COMPILE TIME per nMax (the kernel is a template on nMax: every offset, stride, K-step
@@ -593,7 +596,7 @@ template <int NM, int... U> __device__ __forceinline__ void rot_p3_all(RotLane c
 }
 
 template <int NM>
-__global__ void __launch_bounds__(ROT_THREADS, 3) k_matvec_rot(const __grid_constant__ RotArgs a) {
+__global__ void __launch_bounds__(ROT_THREADS, ROT_MIN_CTAS) k_matvec_rot(const __grid_constant__ RotArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr RotCT T = rot_ct(NM);
   constexpr int nH = NM * (NM + 2), n2 = 2 * nH, LF = NM * (NM + 3), NH = LF / 2;
