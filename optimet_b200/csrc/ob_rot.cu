@@ -507,10 +507,10 @@ __device__ __forceinline__ void rot_dchains(RotLane const &c, double (&accS)[2],
 }
 
 // P1 unit: u = D^T t, channel sums p+- = TE_s +- TM_a (TE lanes), r+- = TM_s +- TE_a (TM lanes)
-template <int NM, int U> __device__ __forceinline__ void rot_p1_unit(RotLane const &c) {
+template <int NM, int W, int U> __device__ __forceinline__ void rot_p1_unit(RotLane const &c) {
   constexpr RotCT T = rot_ct(NM);
   constexpr int n = T.dn[U], m0 = T.dm[U], SS = rot_plane_doubles(NM * (NM + 3));
-  if(c.warp != T.dw[U])
+  if constexpr(T.dw[U] != W)
     return;
   double aS[2], aA[2];
   rot_dchains<NM, U>(c, aS, aA);
@@ -530,11 +530,11 @@ template <int NM, int U> __device__ __forceinline__ void rot_p1_unit(RotLane con
 
 // P2 unit: q = C p for order a, rows n = n0 + m0 .. + 7 (Re and Im of C as two real DMMAs on one B fragment), back to
 // the class vectors: v_s = (-1)^a (q+ + q-) / 2, v_a = (-1)^a (q+ - q-) / 2
-template <int NM, int U> __device__ __forceinline__ void rot_p2_unit(RotLane const &c) {
+template <int NM, int W, int U> __device__ __forceinline__ void rot_p2_unit(RotLane const &c) {
   constexpr RotCT T = rot_ct(NM);
   constexpr int a = T.ca[U], m0 = T.cm[U], n0 = rot_n0(a), w = NM - n0 + 1, ks = (w + 3) / 4;
   constexpr int XC = rot_offX(NM, NM + 1), XM = XC - NM * NM, SS = rot_plane_doubles(NM * (NM + 3));
-  if(c.warp != T.cw[U])
+  if constexpr(T.cw[U] != W)
     return;
   double apr[2] = {0, 0}, api[2] = {0, 0};
   const double *pb = c.pb + 4 * rot_offP(NM, a) + 4 * c.fc;
@@ -559,10 +559,10 @@ template <int NM, int U> __device__ __forceinline__ void rot_p2_unit(RotLane con
 }
 
 // P3 + P4 unit: w = D v, flip basis -> m, conjugate phase, parity signs of direction 1, accumulate (owner lanes)
-template <int NM, int U> __device__ __forceinline__ void rot_p3_unit(RotLane const &c) {
+template <int NM, int W, int U> __device__ __forceinline__ void rot_p3_unit(RotLane const &c) {
   constexpr RotCT T = rot_ct(NM);
   constexpr int n = T.dn[U], m0 = T.dm[U];
-  if(c.warp != T.dw[U])
+  if constexpr(T.dw[U] != W)
     return;
   double aS[2], aA[2];
   rot_dchains<NM, U>(c, aS, aA);
@@ -585,15 +585,33 @@ template <int NM, int U> __device__ __forceinline__ void rot_p3_unit(RotLane con
   d[2 * ap] = mk(o2.x + (phm.x * dx + phm.y * dy), o2.y + (phm.x * dy - phm.y * dx));
 }
 
-template <int NM, int... U> __device__ __forceinline__ void rot_p1_all(RotLane const &c, std::integer_sequence<int, U...>) {
-  (rot_p1_unit<NM, U>(c), ...);
+// The units of ONE warp, selected at compile time, inlined into one straight-line block: the loads and DMMAs of a warp's
+// three or four units interleave (with a run-time owner test per unit every unit was its own basic block).
+template <int NM, int W, int... U> __device__ __forceinline__ void rot_p1_warp(RotLane const &c, std::integer_sequence<int, U...>) {
+  (rot_p1_unit<NM, W, U>(c), ...);
 }
-template <int NM, int... U> __device__ __forceinline__ void rot_p2_all(RotLane const &c, std::integer_sequence<int, U...>) {
-  (rot_p2_unit<NM, U>(c), ...);
+template <int NM, int W, int... U> __device__ __forceinline__ void rot_p2_warp(RotLane const &c, std::integer_sequence<int, U...>) {
+  (rot_p2_unit<NM, W, U>(c), ...);
 }
-template <int NM, int... U> __device__ __forceinline__ void rot_p3_all(RotLane const &c, std::integer_sequence<int, U...>) {
-  (rot_p3_unit<NM, U>(c), ...);
+template <int NM, int W, int... U> __device__ __forceinline__ void rot_p3_warp(RotLane const &c, std::integer_sequence<int, U...>) {
+  (rot_p3_unit<NM, W, U>(c), ...);
 }
+#define ROT_PER_WARP(fn, seq)                                                                                          \
+  switch(c.warp) {                                                                                                     \
+  case 0:                                                                                                              \
+    fn<NM, 0>(c, seq);                                                                                                 \
+    break;                                                                                                             \
+  case 1:                                                                                                              \
+    fn<NM, 1>(c, seq);                                                                                                 \
+    break;                                                                                                             \
+  case 2:                                                                                                              \
+    fn<NM, 2>(c, seq);                                                                                                 \
+    break;                                                                                                             \
+  default:                                                                                                             \
+    fn<NM, 3>(c, seq);                                                                                                 \
+    break;                                                                                                             \
+  }
+static_assert(ROT_WARPS == 4, "ROT_PER_WARP enumerates four warps");
 
 template <int NM>
 __global__ void __launch_bounds__(ROT_THREADS, ROT_MIN_CTAS) k_matvec_rot(const __grid_constant__ RotArgs a) {
@@ -734,11 +752,11 @@ __global__ void __launch_bounds__(ROT_THREADS, ROT_MIN_CTAS) k_matvec_rot(const 
         load_x(xi, pnext.x);
       }
     }
-    rot_p1_all<NM>(c, std::make_integer_sequence<int, T.nd>{}); // P1: u = D^T t, channel combinations
-    __syncthreads();                                            // B2
-    rot_p2_all<NM>(c, std::make_integer_sequence<int, T.nc>{}); // P2: q = C p, back to the class vectors
-    __syncthreads();                                            // B3
-    rot_p3_all<NM>(c, std::make_integer_sequence<int, T.nd>{}); // P3: w = D v; P4: accumulate
+    ROT_PER_WARP(rot_p1_warp, (std::make_integer_sequence<int, T.nd>{})) // P1: u = D^T t, channel combinations
+    __syncthreads();                                                     // B2
+    ROT_PER_WARP(rot_p2_warp, (std::make_integer_sequence<int, T.nc>{})) // P2: q = C p, back to the class vectors
+    __syncthreads();                                                     // B3
+    ROT_PER_WARP(rot_p3_warp, (std::make_integer_sequence<int, T.nd>{})) // P3: w = D v; P4: accumulate
     if(pi.w & 3) { // last pair of the strip / of the segment: the finished sums go to HBM
       __syncthreads();
       if(pi.w & 1) {
