@@ -457,17 +457,27 @@ struct RotLane {
 
 // accumulation chain of KS K-steps over K columns: straight-line loads, then DMMAs; A advances stepA doubles per step,
 // B 16 doubles; only the last step can run past the K range (compile-time known), where the lane's A entry is zeroed
-template <int KS, int K>
+// KEEP: 0 = load the A fragments, 1 = load them and keep them in `keep` (registers), 2 = take them from `keep` (the
+// small-d fragments of P1 serve P3 again: D[a', a] = (-1)^(a' - a) D[a, a'] makes both phases read the same entries)
+template <int KS, int K, int KEEP = 0>
 __device__ __forceinline__ void rot_chain(double (&acc)[2], const double *__restrict__ pa, int stepA,
-                                          const double *__restrict__ pb, int fc) {
+                                          const double *__restrict__ pb, int fc, double *keep = nullptr) {
   double av[KS], bv[KS];
 #pragma unroll
   for(int s = 0; s < KS; ++s) {
-    av[s] = pa[s * stepA];
+    if(KEEP == 2)
+      av[s] = keep[s];
+    else
+      av[s] = pa[s * stepA];
     bv[s] = pb[16 * s];
   }
-  if(4 * KS > K)
+  if(KEEP != 2 && 4 * KS > K)
     av[KS - 1] = 4 * (KS - 1) + fc < K ? av[KS - 1] : 0.0;
+  if(KEEP == 1) {
+#pragma unroll
+    for(int s = 0; s < KS; ++s)
+      keep[s] = av[s];
+  }
 #pragma unroll
   for(int s = 0; s < KS; ++s)
     dmma(acc, av[s], bv[s]);
@@ -497,23 +507,51 @@ __device__ __forceinline__ void rot_chain2(double (&accR)[2], double (&accI)[2],
 
 // d-phase unit U of nMax NM (P1 and P3): rows a = m0 .. m0 + 7 of degree n, both classes.
 //   accS[(a, col)] = sum_{a' = 0..n} Ds[a' (n + 1) + a] v_s[a'][col],  accA[(a, col)] = sum_{a' = 1..n} Da[(a' - 1) n + (a - 1)] v_a[a'][col]
-template <int NM, int U>
-__device__ __forceinline__ void rot_dchains(RotLane const &c, double (&accS)[2], double (&accA)[2]) {
+// register slots of the kept A fragments: units of the same warp before U (compile time)
+#ifndef ROT_KEEP_S
+#define ROT_KEEP_S 1 // keep the s-class small-d fragments of P1 in registers for P3
+#endif
+#ifndef ROT_KEEP_A
+#define ROT_KEEP_A 1 // the a-class ones too (168 registers with three CTAs per SM: no spills up to nMax 13)
+#endif
+__host__ __device__ constexpr inline int rot_keep_slots(int NM, int W, int U) { // fragments kept by W's units before U
+  const RotCT T = rot_ct(NM);
+  int k = 0;
+  for(int u = 0; u < U; ++u)
+    if(T.dw[u] == W)
+      k += (ROT_KEEP_S ? (T.dn[u] + 1 + 3) / 4 : 0) + (ROT_KEEP_A ? (T.dn[u] + 3) / 4 : 0);
+  return k;
+}
+__host__ __device__ constexpr inline int rot_keep_total(int NM) {
+  const RotCT T = rot_ct(NM);
+  int best = 1;
+  for(int w = 0; w < ROT_WARPS; ++w) {
+    const int k = rot_keep_slots(NM, w, T.nd);
+    best = k > best ? k : best;
+  }
+  return best;
+}
+// PHASE 1: P1 (fragments loaded and kept), 3: P3 (kept fragments reused)
+template <int NM, int W, int U, int PHASE>
+__device__ __forceinline__ void rot_dchains(RotLane const &c, double (&accS)[2], double (&accA)[2], double *keep) {
   constexpr RotCT T = rot_ct(NM);
-  constexpr int n = T.dn[U], m0 = T.dm[U], n1 = n + 1;
+  constexpr int n = T.dn[U], m0 = T.dm[U], n1 = n + 1, slot = rot_keep_slots(NM, W, U);
+  constexpr int KS = ROT_KEEP_S ? (PHASE == 1 ? 1 : 2) : 0, KA = ROT_KEEP_A ? (PHASE == 1 ? 1 : 2) : 0;
   accS[0] = accS[1] = accA[0] = accA[1] = 0.0;
-  rot_chain<(n1 + 3) / 4, n1>(accS, c.Ds + rot_offDs(n) + m0 + c.fc * n1, 4 * n1, c.vb + 4 * rot_offF(n) + 4 * c.fc, c.fc);
-  rot_chain<(n + 3) / 4, n>(accA, c.Da + rot_offDa(n) + m0 - 1 + c.fc * n, 4 * n, c.vb + 4 * (rot_offF(n) + n + 2) + 4 * c.fc, c.fc);
+  rot_chain<(n1 + 3) / 4, n1, KS>(accS, c.Ds + rot_offDs(n) + m0 + c.fc * n1, 4 * n1, c.vb + 4 * rot_offF(n) + 4 * c.fc, c.fc,
+                                  keep + slot);
+  rot_chain<(n + 3) / 4, n, KA>(accA, c.Da + rot_offDa(n) + m0 - 1 + c.fc * n, 4 * n, c.vb + 4 * (rot_offF(n) + n + 2) + 4 * c.fc,
+                                c.fc, keep + slot + (ROT_KEEP_S ? (n1 + 3) / 4 : 0));
 }
 
 // P1 unit: u = D^T t, channel sums p+- = TE_s +- TM_a (TE lanes), r+- = TM_s +- TE_a (TM lanes)
-template <int NM, int W, int U> __device__ __forceinline__ void rot_p1_unit(RotLane const &c) {
+template <int NM, int W, int U> __device__ __forceinline__ void rot_p1_unit(RotLane const &c, double *keep) {
   constexpr RotCT T = rot_ct(NM);
   constexpr int n = T.dn[U], m0 = T.dm[U], SS = rot_plane_doubles(NM * (NM + 3));
   if constexpr(T.dw[U] != W)
     return;
   double aS[2], aA[2];
-  rot_dchains<NM, U>(c, aS, aA);
+  rot_dchains<NM, W, U, 1>(c, aS, aA, keep);
   const int aa = m0 + c.fr;
   if(m0 == 0 && c.fr == 0) // the a class has no a = 0 row (its fragment row was read from outside the block)
     aA[0] = aA[1] = 0.0;
@@ -530,7 +568,7 @@ template <int NM, int W, int U> __device__ __forceinline__ void rot_p1_unit(RotL
 
 // P2 unit: q = C p for order a, rows n = n0 + m0 .. + 7 (Re and Im of C as two real DMMAs on one B fragment), back to
 // the class vectors: v_s = (-1)^a (q+ + q-) / 2, v_a = (-1)^a (q+ - q-) / 2
-template <int NM, int W, int U> __device__ __forceinline__ void rot_p2_unit(RotLane const &c) {
+template <int NM, int W, int U> __device__ __forceinline__ void rot_p2_unit(RotLane const &c, double *) {
   constexpr RotCT T = rot_ct(NM);
   constexpr int a = T.ca[U], m0 = T.cm[U], n0 = rot_n0(a), w = NM - n0 + 1, ks = (w + 3) / 4;
   constexpr int XC = rot_offX(NM, NM + 1), XM = XC - NM * NM, SS = rot_plane_doubles(NM * (NM + 3));
@@ -559,13 +597,13 @@ template <int NM, int W, int U> __device__ __forceinline__ void rot_p2_unit(RotL
 }
 
 // P3 + P4 unit: w = D v, flip basis -> m, conjugate phase, parity signs of direction 1, accumulate (owner lanes)
-template <int NM, int W, int U> __device__ __forceinline__ void rot_p3_unit(RotLane const &c) {
+template <int NM, int W, int U> __device__ __forceinline__ void rot_p3_unit(RotLane const &c, double *keep) {
   constexpr RotCT T = rot_ct(NM);
   constexpr int n = T.dn[U], m0 = T.dm[U];
   if constexpr(T.dw[U] != W)
     return;
   double aS[2], aA[2];
-  rot_dchains<NM, U>(c, aS, aA);
+  rot_dchains<NM, W, U, 3>(c, aS, aA, keep);
   const int ap = m0 + c.fr;
   if(m0 + 7 > n && ap > n)
     return;
@@ -587,28 +625,28 @@ template <int NM, int W, int U> __device__ __forceinline__ void rot_p3_unit(RotL
 
 // The units of ONE warp, selected at compile time, inlined into one straight-line block: the loads and DMMAs of a warp's
 // three or four units interleave (with a run-time owner test per unit every unit was its own basic block).
-template <int NM, int W, int... U> __device__ __forceinline__ void rot_p1_warp(RotLane const &c, std::integer_sequence<int, U...>) {
-  (rot_p1_unit<NM, W, U>(c), ...);
+template <int NM, int W, int... U> __device__ __forceinline__ void rot_p1_warp(RotLane const &c, double *keep, std::integer_sequence<int, U...>) {
+  (rot_p1_unit<NM, W, U>(c, keep), ...);
 }
-template <int NM, int W, int... U> __device__ __forceinline__ void rot_p2_warp(RotLane const &c, std::integer_sequence<int, U...>) {
-  (rot_p2_unit<NM, W, U>(c), ...);
+template <int NM, int W, int... U> __device__ __forceinline__ void rot_p2_warp(RotLane const &c, double *keep, std::integer_sequence<int, U...>) {
+  (rot_p2_unit<NM, W, U>(c, keep), ...);
 }
-template <int NM, int W, int... U> __device__ __forceinline__ void rot_p3_warp(RotLane const &c, std::integer_sequence<int, U...>) {
-  (rot_p3_unit<NM, W, U>(c), ...);
+template <int NM, int W, int... U> __device__ __forceinline__ void rot_p3_warp(RotLane const &c, double *keep, std::integer_sequence<int, U...>) {
+  (rot_p3_unit<NM, W, U>(c, keep), ...);
 }
 #define ROT_PER_WARP(fn, seq)                                                                                          \
   switch(c.warp) {                                                                                                     \
   case 0:                                                                                                              \
-    fn<NM, 0>(c, seq);                                                                                                 \
+    fn<NM, 0>(c, keep, seq);                                                                                                 \
     break;                                                                                                             \
   case 1:                                                                                                              \
-    fn<NM, 1>(c, seq);                                                                                                 \
+    fn<NM, 1>(c, keep, seq);                                                                                                 \
     break;                                                                                                             \
   case 2:                                                                                                              \
-    fn<NM, 2>(c, seq);                                                                                                 \
+    fn<NM, 2>(c, keep, seq);                                                                                                 \
     break;                                                                                                             \
   default:                                                                                                             \
-    fn<NM, 3>(c, seq);                                                                                                 \
+    fn<NM, 3>(c, keep, seq);                                                                                                 \
     break;                                                                                                             \
   }
 static_assert(ROT_WARPS == 4, "ROT_PER_WARP enumerates four warps");
@@ -691,6 +729,7 @@ __global__ void __launch_bounds__(ROT_THREADS, ROT_MIN_CTAS) k_matvec_rot(const 
     load_x(xi, pi.x);
   }
   int sg = a.cta_seg[blockIdx.x];
+  double keep[rot_keep_total(NM)]; // small-d A fragments of P1, reused by P3 (registers: every index is a constant)
   double *bufA = bufX, *bufB = bufY; // class vectors T / V in bufA, channels in bufB; roles swap every pair
   for(int q = qbeg; q < qend; ++q) {
     const int cur = (q - qbeg) & 1;
