@@ -716,7 +716,7 @@ __global__ void __launch_bounds__(ROT_THREADS, ROT_MIN_CTAS) k_matvec_rot(const 
   }
   // x of the pair about to be processed, at m = +pa (TE, TM) and m = -pa (TE, TM): xj = x_j (direction 0), xi = x_i
   cplx xj[4], xi[4];
-  int4 pi = a.pinfo[qbeg];
+  int4 pi = a.pinfo[qbeg], pnext = a.pinfo[qbeg + 1 < qend ? qbeg + 1 : qbeg];
   auto load_x = [&](cplx (&xr)[4], int part) {
     const cplx *xs = a.x + (size_t)part * n2;
     xr[0] = xs[fpos];
@@ -755,42 +755,33 @@ __global__ void __launch_bounds__(ROT_THREADS, ROT_MIN_CTAS) k_matvec_rot(const 
         const double ge = dir ? psn : 1.0, gm = dir ? -psn : 1.0; // direction 1: x_i with (-1)^deg, and -1 on TM
         const cplx te_p = cmul(pp, xr[0]), tm_p = cmul(pp, xr[1]);
         cplx *ts = (cplx *)(bufA + dir * PS + 4 * pfs), *ta = (cplx *)(bufA + dir * PS + 4 * pfa);
-        // consecutive lanes write consecutive 32-byte rows, 16 bytes per store: lanes 4..7 of every eight take the TM half
-        // first so that one store instruction covers eight distinct 16-byte bank groups
-        const int h0 = (tid >> 2) & 1, h1 = h0 ^ 1;
         if(pa == 0) {
-          const cplx v[2] = {cscale(te_p, ge), cscale(tm_p, gm)};
-          ts[h0] = h0 ? v[1] : v[0];
-          ts[h1] = h1 ? v[1] : v[0];
+          ts[0] = cscale(te_p, ge);
+          ts[1] = cscale(tm_p, gm);
         } else {
           const cplx te_m = cmul(pm, xr[2]), tm_m = cmul(pm, xr[3]);
           const double fe = ge * ROT_SQH, fm = gm * ROT_SQH;
-          const cplx se = mk(fe * (te_p.x + psa * te_m.x), fe * (te_p.y + psa * te_m.y));
-          const cplx sm = mk(fm * (tm_p.x + psa * tm_m.x), fm * (tm_p.y + psa * tm_m.y));
-          const cplx ae = mk(fe * (te_p.x - psa * te_m.x), fe * (te_p.y - psa * te_m.y));
-          const cplx am = mk(fm * (tm_p.x - psa * tm_m.x), fm * (tm_p.y - psa * tm_m.y));
-          ts[h0] = h0 ? sm : se;
-          ta[h0] = h0 ? am : ae;
-          ts[h1] = h1 ? sm : se;
-          ta[h1] = h1 ? am : ae;
+          ts[0] = mk(fe * (te_p.x + psa * te_m.x), fe * (te_p.y + psa * te_m.y));
+          ts[1] = mk(fm * (tm_p.x + psa * tm_m.x), fm * (tm_p.y + psa * tm_m.y));
+          ta[0] = mk(fe * (te_p.x - psa * te_m.x), fe * (te_p.y - psa * te_m.y));
+          ta[1] = mk(fm * (tm_p.x - psa * tm_m.x), fm * (tm_p.y - psa * tm_m.y));
         }
       }
     }
     __syncthreads(); // B1: T complete; every thread is past P3/P4 of the previous pair -> the other record slot is free
-    int4 pnext = pi;
     if(q + 1 < qend) {
       if(tid == 0) {
         r_mbar_expect_tx(&full[cur ^ 1], (uint32_t)L.rec_bytes);
         r_bulk_g2s(smem + (size_t)(cur ^ 1) * L.rec_bytes, a.recs + (size_t)(q + 1) * L.rec_bytes, (uint32_t)L.rec_bytes,
                    &full[cur ^ 1], pol);
       }
-      pnext = a.pinfo[q + 1];
-      if(p0live) { // next pair's x into registers (L2 hits), consumed by its P0
+      if(p0live) { // next pair's x into registers (L2 hits), consumed by its P0; its (i, j) was fetched a pair ago
         if(pnext.y != pi.y)
           load_x(xj, pnext.y);
         load_x(xi, pnext.x);
       }
     }
+    const int4 pnext2 = a.pinfo[q + 2 < qend ? q + 2 : qend - 1]; // (i, j) of the pair after the next one
     ROT_PER_WARP(rot_p1_warp, (std::make_integer_sequence<int, T.nd>{})) // P1: u = D^T t, channel combinations
     __syncthreads();                                                     // B2
     ROT_PER_WARP(rot_p2_warp, (std::make_integer_sequence<int, T.nc>{})) // P2: q = C p, back to the class vectors
@@ -818,6 +809,7 @@ __global__ void __launch_bounds__(ROT_THREADS, ROT_MIN_CTAS) k_matvec_rot(const 
       }
     }
     pi = pnext;
+    pnext = pnext2;
     double *tb = bufA;
     bufA = bufB;
     bufB = tb;
