@@ -681,20 +681,44 @@ __global__ void __launch_bounds__(ROT_THREADS, ROT_MIN_CTAS) k_matvec_rot(const 
       z[e] = 0.0;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy writes before the bulk copies into the slots
   }
-  // ---- P0 item of this thread: (pn, pa), pa = 0..pn, sorted by degree ----
-  const bool p0live = tid < NH;
+  // ---- P0 item of this thread.  SPLIT (nMax <= 10): one direction per thread, 2 Q items over all four warps, where an
+  // item is either (pn, pa >= 1) [x at m = +-pa, TE and TM] or two m = 0 entries of degrees pn, pn + 1 [TE and TM each]:
+  // four complex values of x per thread either way.  Otherwise both directions per thread, item (pn, pa >= 0). ----
+  constexpr int NA = NM * (NM + 1) / 2, NZ = (NM + 1) / 2, Q = NA + NZ;
+  constexpr bool SPLIT = 2 * Q <= ROT_THREADS;
+  const bool p0live = SPLIT ? tid < 2 * Q : tid < NH;
+  const int pdir = SPLIT ? (tid >= Q ? 1 : 0) : 0; // SPLIT: the direction of this thread
   int pn = 1, pa = 0;
+  bool pz = false; // SPLIT: item of two m = 0 entries
   if(p0live) {
-    pn = (int)((-1.0 + sqrt(9.0 + 8.0 * tid)) * 0.5);
-    while((pn - 1) * (pn + 2) / 2 > tid)
-      --pn;
-    while(pn * (pn + 3) / 2 <= tid)
-      ++pn;
-    pa = tid - (pn - 1) * (pn + 2) / 2;
+    if(SPLIT) {
+      const int u = tid - pdir * Q;
+      if(u < NA) {
+        pn = (int)((1.0 + sqrt(1.0 + 8.0 * u)) * 0.5);
+        while(pn * (pn - 1) / 2 > u)
+          --pn;
+        while(pn * (pn + 1) / 2 <= u)
+          ++pn;
+        pa = u - pn * (pn - 1) / 2 + 1;
+      } else {
+        pz = true;
+        pn = 2 * (u - NA) + 1;
+      }
+    } else {
+      pn = (int)((-1.0 + sqrt(9.0 + 8.0 * tid)) * 0.5);
+      while((pn - 1) * (pn + 2) / 2 > tid)
+        --pn;
+      while(pn * (pn + 3) / 2 <= tid)
+        ++pn;
+      pa = tid - (pn - 1) * (pn + 2) / 2;
+    }
   }
-  const int fpos = flat_index(pn, pa), fneg = flat_index(pn, -pa);
+  const bool pz2 = pz && pn + 1 <= NM; // the second degree of a two-entry item exists
+  // x entries this thread reads: (fpos, fneg) = m = +pa, -pa of degree pn, or m = 0 of degrees pn, pn + 1
+  const int fpos = flat_index(pn, pa), fneg = pz ? flat_index(pz2 ? pn + 1 : pn, 0) : flat_index(pn, -pa);
   const double psa = (pa & 1) ? -1.0 : 1.0, psn = (pn & 1) ? -1.0 : 1.0;
   const int pfs = rot_offF(pn) + pa, pfa = pfs + pn + 1;
+  const int pfs2 = rot_offF(pz2 ? pn + 1 : pn); // F index of s_0 of the second degree
   // ---- fragment geometry of this lane ----
   RotLane c;
   c.warp = tid >> 5;
@@ -715,7 +739,7 @@ __global__ void __launch_bounds__(ROT_THREADS, ROT_MIN_CTAS) k_matvec_rot(const 
     r_bulk_g2s(smem, a.recs + (size_t)qbeg * L.rec_bytes, (uint32_t)L.rec_bytes, &full[0], pol);
   }
   // x of the pair about to be processed, at m = +pa (TE, TM) and m = -pa (TE, TM): xj = x_j (direction 0), xi = x_i
-  cplx xj[4], xi[4];
+  cplx xj[4], xi[SPLIT ? 1 : 4]; // SPLIT: xj holds the thread's own direction (x_j or x_i)
   int4 pi = a.pinfo[qbeg], pnext = a.pinfo[qbeg + 1 < qend ? qbeg + 1 : qbeg];
   auto load_x = [&](cplx (&xr)[4], int part) {
     const cplx *xs = a.x + (size_t)part * n2;
@@ -725,8 +749,12 @@ __global__ void __launch_bounds__(ROT_THREADS, ROT_MIN_CTAS) k_matvec_rot(const 
     xr[3] = xs[nH + fneg];
   };
   if(p0live) {
-    load_x(xj, pi.y);
-    load_x(xi, pi.x);
+    if(SPLIT)
+      load_x(xj, pdir ? pi.x : pi.y);
+    else {
+      load_x(xj, pi.y);
+      load_x(*(cplx(*)[4])xi, pi.x);
+    }
   }
   int sg = a.cta_seg[blockIdx.x];
   double keep[rot_keep_total(NM)]; // small-d A fragments of P1, reused by P3 (registers: every index is a constant)
@@ -749,16 +777,23 @@ __global__ void __launch_bounds__(ROT_THREADS, ROT_MIN_CTAS) k_matvec_rot(const 
     // ---- P0: phases, parity signs of the reversed direction, flip basis ----
     if(p0live) {
       const cplx pp = s_ph[NM + pa], pm = s_ph[NM - pa];
-#pragma unroll
-      for(int dir = 0; dir < 2; ++dir) {
-        const cplx *xr = dir ? xi : xj;
-        const double ge = dir ? psn : 1.0, gm = dir ? -psn : 1.0; // direction 1: x_i with (-1)^deg, and -1 on TM
-        const cplx te_p = cmul(pp, xr[0]), tm_p = cmul(pp, xr[1]);
+      // one direction: phases, (-1)^deg and -1 on TM for direction 1 (x_i), flip basis, store
+      auto p0_dir = [&](int dir, const cplx *xr) {
+        const double ge = dir ? psn : 1.0, gm = dir ? -psn : 1.0;
         cplx *ts = (cplx *)(bufA + dir * PS + 4 * pfs), *ta = (cplx *)(bufA + dir * PS + 4 * pfa);
-        if(pa == 0) {
-          ts[0] = cscale(te_p, ge);
-          ts[1] = cscale(tm_p, gm);
+        if(SPLIT && pz) { // exp(i 0 phi) = 1; the second degree has the opposite parity
+          ts[0] = cscale(xr[0], ge);
+          ts[1] = cscale(xr[1], gm);
+          if(pz2) {
+            cplx *t2 = (cplx *)(bufA + dir * PS + 4 * pfs2);
+            t2[0] = cscale(xr[2], dir ? -ge : ge);
+            t2[1] = cscale(xr[3], dir ? -gm : gm);
+          }
+        } else if(pa == 0) {
+          ts[0] = cscale(xr[0], ge);
+          ts[1] = cscale(xr[1], gm);
         } else {
+          const cplx te_p = cmul(pp, xr[0]), tm_p = cmul(pp, xr[1]);
           const cplx te_m = cmul(pm, xr[2]), tm_m = cmul(pm, xr[3]);
           const double fe = ge * ROT_SQH, fm = gm * ROT_SQH;
           ts[0] = mk(fe * (te_p.x + psa * te_m.x), fe * (te_p.y + psa * te_m.y));
@@ -766,6 +801,12 @@ __global__ void __launch_bounds__(ROT_THREADS, ROT_MIN_CTAS) k_matvec_rot(const 
           ta[0] = mk(fe * (te_p.x - psa * te_m.x), fe * (te_p.y - psa * te_m.y));
           ta[1] = mk(fm * (tm_p.x - psa * tm_m.x), fm * (tm_p.y - psa * tm_m.y));
         }
+      };
+      if(SPLIT)
+        p0_dir(pdir, xj);
+      else {
+        p0_dir(0, xj);
+        p0_dir(1, xi);
       }
     }
     __syncthreads(); // B1: T complete; every thread is past P3/P4 of the previous pair -> the other record slot is free
@@ -776,9 +817,16 @@ __global__ void __launch_bounds__(ROT_THREADS, ROT_MIN_CTAS) k_matvec_rot(const 
                    &full[cur ^ 1], pol);
       }
       if(p0live) { // next pair's x into registers (L2 hits), consumed by its P0; its (i, j) was fetched a pair ago
-        if(pnext.y != pi.y)
-          load_x(xj, pnext.y);
-        load_x(xi, pnext.x);
+        if(SPLIT) {
+          if(pdir)
+            load_x(xj, pnext.x);
+          else if(pnext.y != pi.y)
+            load_x(xj, pnext.y);
+        } else {
+          if(pnext.y != pi.y)
+            load_x(xj, pnext.y);
+          load_x(*(cplx(*)[4])xi, pnext.x);
+        }
       }
     }
     const int4 pnext2 = a.pinfo[q + 2 < qend ? q + 2 : qend - 1]; // (i, j) of the pair after the next one
