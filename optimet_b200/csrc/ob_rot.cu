@@ -129,15 +129,50 @@ k_assemble_axial(VtacTables tb, const double *__restrict__ xyz, cplx k, const in
 // warp runs is checked on the CPU against the oracle's Coupling (tests/test_rot_axial_host.py, lane 0 of 1) and on the
 // GPU against the vtac_block path and the oracle (tests/test_gpu_rot.py).
 // ---------------------------------------------------------------------------------------------
-#define ROT_AX_WARPS 4
-static size_t rot_axial_smem_bytes(int NM) { return (size_t)ROT_AX_WARPS * rot_axial_fast_entries(NM) * sizeof(cplx); }
-__global__ void __launch_bounds__(ROT_AX_WARPS * 32)
+// One persistent CTA per SM with as many warps as fit beside the TABLES IN SHARED MEMORY: the first tabulated version
+// read them from global memory with 212 KB of the SM's 256 KB configured as shared memory, so the 80 KB of tables
+// thrashed what was left of L1 and every item paid two dependent L2 round trips (8.9 ms per C5 harmonic).
+#define ROT_AX_MAX_WARPS 16
+struct RotAxSizes {
+  int nrec, nem; // table entries (recursion, emission)
+};
+static RotAxSizes rot_axial_sizes(int NM) { return {rot_axial_offR(NM, NM + 1), rot_axial_offE(NM, NM + 1)}; }
+static size_t rot_axial_table_bytes(int NM) {
+  const RotAxSizes z = rot_axial_sizes(NM);
+  return ((size_t)z.nrec * (4 * sizeof(double) + sizeof(int)) + (size_t)z.nem * (8 * sizeof(double) + 2 * sizeof(int)) + 15) &
+         ~(size_t)15;
+}
+__global__ void __launch_bounds__(ROT_AX_MAX_WARPS * 32)
 k_assemble_axial_only(const double *__restrict__ xyz, cplx k, const int2 *__restrict__ pair_ij, long npairs,
-                      unsigned char *__restrict__ recs, RotLayout L, RotAxTab tab) {
+                      unsigned char *__restrict__ recs, RotLayout L, RotAxTab gtab, int nrec, int nem, int tab_in_smem) {
   extern __shared__ __align__(16) unsigned char smem_ax[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  cplx *buf = (cplx *)smem_ax + (size_t)warp * rot_axial_fast_entries(L.NM);
-  for(long q = (long)blockIdx.x * ROT_AX_WARPS + warp; q < npairs; q += (long)gridDim.x * ROT_AX_WARPS) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  RotAxTab tab = gtab;
+  unsigned char *wbuf = smem_ax;
+  if(tab_in_smem) { // doubles first (16-byte aligned), then the three index arrays
+    double *s_rec = (double *)smem_ax, *s_emit = s_rec + (size_t)nrec * 4;
+    int *s_ridx = (int *)(s_emit + (size_t)nem * 8), *s_eidx = s_ridx + nrec, *s_eout = s_eidx + nem;
+    for(int e = threadIdx.x; e < nrec * 4; e += blockDim.x)
+      s_rec[e] = gtab.rec[e];
+    for(int e = threadIdx.x; e < nem * 8; e += blockDim.x)
+      s_emit[e] = gtab.emit[e];
+    for(int e = threadIdx.x; e < nrec; e += blockDim.x)
+      s_ridx[e] = gtab.ridx[e];
+    for(int e = threadIdx.x; e < nem; e += blockDim.x) {
+      s_eidx[e] = gtab.eidx[e];
+      s_eout[e] = gtab.eout[e];
+    }
+    tab.rec = s_rec;
+    tab.emit = s_emit;
+    tab.ridx = s_ridx;
+    tab.eidx = s_eidx;
+    tab.eout = s_eout;
+    wbuf = smem_ax + (((size_t)nrec * (4 * sizeof(double) + sizeof(int)) + (size_t)nem * (8 * sizeof(double) + 2 * sizeof(int)) + 15) &
+                      ~(size_t)15);
+    __syncthreads();
+  }
+  cplx *buf = (cplx *)wbuf + (size_t)warp * rot_axial_fast_entries(L.NM);
+  for(long q = (long)blockIdx.x * nwarps + warp; q < npairs; q += (long)gridDim.x * nwarps) {
     const int2 ij = pair_ij[q];
     const double x = xyz[3 * ij.x] - xyz[3 * ij.y], y = xyz[3 * ij.x + 1] - xyz[3 * ij.y + 1],
                  z = xyz[3 * ij.x + 2] - xyz[3 * ij.y + 2];
@@ -1064,11 +1099,27 @@ void launch_assemble_rot(VtacTableSet const &ts, const double *xyz, cplx k, cons
     return;
   RotDTable const &dt = rot_dtable(L.NM);
   if(g_rot_assembly == 1) {
-    const size_t sm = rot_axial_smem_bytes(L.NM);
+    const RotAxSizes z = rot_axial_sizes(L.NM);
+    const size_t per_warp = (size_t)rot_axial_fast_entries(L.NM) * sizeof(cplx), tb = rot_axial_table_bytes(L.NM);
+    const size_t budget = (size_t)224 * 1024;
+    int warps, in_smem;
+    long ctas;
+    size_t sm;
+    if(tb + 4 * per_warp <= budget) { // tables in shared memory, one persistent CTA per SM
+      in_smem = 1;
+      warps = (int)std::min<size_t>(ROT_AX_MAX_WARPS, (budget - tb) / per_warp);
+      sm = tb + (size_t)warps * per_warp;
+      ctas = std::min<long>((npairs + warps - 1) / warps, (long)sm_count);
+    } else { // very large nMax: tables stay in global memory, small CTAs
+      in_smem = 0;
+      warps = 4;
+      sm = (size_t)warps * per_warp;
+      const long per_sm = std::max<long>(1, std::min<long>(16, (long)(220 * 1024) / (long)(sm + 1024)));
+      ctas = std::min<long>((npairs + warps - 1) / warps, (long)sm_count * per_sm);
+    }
     OB_CUDA(cudaFuncSetAttribute((const void *)k_assemble_axial_only, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    const long per_sm = std::max<long>(1, std::min<long>(16, (long)(220 * 1024) / (long)(sm + 1024)));
-    const long ctas = std::min<long>((npairs + ROT_AX_WARPS - 1) / ROT_AX_WARPS, (long)sm_count * per_sm);
-    k_assemble_axial_only<<<(unsigned)ctas, ROT_AX_WARPS * 32, sm, st>>>(xyz, k, pair_ij, npairs, recs, L, rot_axtab(L.NM));
+    k_assemble_axial_only<<<(unsigned)ctas, warps * 32, sm, st>>>(xyz, k, pair_ij, npairs, recs, L, rot_axtab(L.NM), z.nrec, z.nem,
+                                                                 in_smem);
   } else {
     OB_CUDA(cudaFuncSetAttribute((const void *)k_assemble_axial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ts.smem));
     OB_CUDA(cudaFuncSetAttribute((const void *)k_assemble_axial, cudaFuncAttributePreferredSharedMemoryCarveout,
