@@ -186,7 +186,7 @@ k_assemble_axial_only(const double *__restrict__ xyz, cplx k, const int2 *__rest
 // index-only coefficient tables of the axial recursion, one set per (device, nMax)
 struct RotAxTabDev {
   int NM = -1;
-  RotAxTab t = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  RotAxTab t = {nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0};
 };
 static RotAxTabDev g_axtab[16][OB_MAX_NMAX + 1];
 template <class T> static const T *rot_to_device(std::vector<T> const &v) {
@@ -211,6 +211,8 @@ static RotAxTab const &rot_axtab(int NM) {
   e.t.ridx = rot_to_device(ridx);
   e.t.eidx = rot_to_device(eidx);
   e.t.eout = rot_to_device(eout);
+  e.t.nrec = (int)ridx.size();
+  e.t.nem = (int)eidx.size();
   e.NM = NM;
   return e.t;
 }

@@ -44,14 +44,16 @@ __host__ __device__ inline int rot_axial_buf_entries(int NM) { return 3 * (NM + 
 // reference's a+-, b+- and of the Coupling prefactors depend on (n, m, l) only; evaluating them per pair was most of the
 // assembly time).  Built on the host by rot_axial_tables_build from the very expressions of the table-free path below,
 // which stays for the host check and as the specification.
-//   rec  [offR(n) + t][4] = c0, c1, c2, 1 / denominator     of item t = m * span + (l - m) of level n
-//   emit [offE(n) + t][8] = fa, a0, a1, a2, fb, b0, b1, b2   of item t = mu * NM + (l - 1) of level n
+//   rec  [c][offR(n) + t], c = 0..3: c0, c1, c2, 1 / denominator     of item t = m * span + (l - m) of level n
+//   emit [c][offE(n) + t], c = 0..7: fa, a0, a1, a2, fb, b0, b1, b2   of item t = mu * NM + (l - 1) of level n
+//   (structure of arrays: the lanes of a warp read consecutive items, i.e. consecutive doubles of one component)
 //   ridx = m | l << 8 | flags << 16: 1 live, 2 beta(n-1, m, l-1) exists, 4 beta(n-2, m, l) exists, 8 sectorial step
 //   eidx = mu | l << 8 | flags << 16: 1 live, then one bit per term of the A / B sums that exists (2, 4, 8: beta(mu, l),
 //          beta(mu + 1, l), beta(|mu - 1|, l); 16, 32, 64: the same at l - 1); eout = index of the entry in the record
 struct RotAxTab {
   const double *rec, *emit;
   const int *ridx, *eidx, *eout;
+  int nrec, nem; // entries per component
 };
 __host__ __device__ inline int rot_axial_offR(int NM, int n) { // sum_{j=1}^{n-1} (j + 1)(2 NM - j + 1)
   int o = 0;
@@ -72,7 +74,8 @@ inline void rot_axial_tables_build(int NM, std::vector<double> &rec, std::vector
     const int span = LL - n + 1;
     for(int t = 0; t < (n + 1) * span; ++t) {
       const int m = t / span, l = m + (t - m * span);
-      double *c = &rec[((size_t)rot_axial_offR(NM, n) + t) * 4];
+      const size_t NR = (size_t)rot_axial_offR(NM, NM + 1), ir = (size_t)rot_axial_offR(NM, n) + t;
+      double c[4] = {0, 0, 0, 0};
       if(l > LL - n) {
         ridx[(size_t)rot_axial_offR(NM, n) + t] = m | (l << 8);
         continue;
@@ -93,6 +96,8 @@ inline void rot_axial_tables_build(int NM, std::vector<double> &rec, std::vector
         c[2] = n - 2 >= m ? ta_a_minus(n - 1, m) : 0.0;
         c[3] = 1.0 / ta_a_plus(n - 1, m);
       }
+      for(int q = 0; q < 4; ++q)
+        rec[q * NR + ir] = c[q];
     }
     for(int t = 0; t < (n + 1) * NM; ++t) {
       const int mu = t / NM, l = 1 + (t - mu * NM);
@@ -110,7 +115,8 @@ inline void rot_axial_tables_build(int NM, std::vector<double> &rec, std::vector
         const int w = NM - n0 + 1;
         eout[(size_t)rot_axial_offE(NM, n) + t] = rot_offX(NM, mu) + (n - n0) * w + (l - n0);
       }
-      double *c = &emit[((size_t)rot_axial_offE(NM, n) + t) * 8];
+      const size_t NE = (size_t)rot_axial_offE(NM, NM + 1), ie = (size_t)rot_axial_offE(NM, n) + t;
+      double c[8];
       c[0] = 0.5 / sqrt((double)(l * (l + 1) * n * (n + 1)));
       c[1] = 2.0 * mu * mu;
       c[2] = sqrt((double)((n - mu) * (n + mu + 1) * (l - mu) * (l + mu + 1)));
@@ -119,6 +125,8 @@ inline void rot_axial_tables_build(int NM, std::vector<double> &rec, std::vector
       c[5] = 2.0 * mu * sqrt((double)((l - mu) * (l + mu)));
       c[6] = sqrt((double)((n - mu) * (n + mu + 1) * (l - mu) * (l - mu - 1)));
       c[7] = sqrt((double)((n + mu) * (n - mu + 1) * (l + mu) * (l + mu - 1)));
+      for(int q = 0; q < 8; ++q)
+        emit[q * NE + ie] = c[q];
     }
   }
 }
@@ -241,32 +249,34 @@ __host__ __device__ inline void rot_axial_pair_fast(int NM, cplx k, double r, cp
     cplx *cur = buf + (size_t)(n & 1) * CH * W;            // holds level n - 2, becomes level n
     const cplx *p1 = buf + (size_t)((n & 1) ^ 1) * CH * W; // level n - 1
     const int nrec = (n + 1) * (LL - n + 1), nem = (n + 1) * NM;
-    const double *rc = tab.rec + (size_t)offR * 4;
+    const double *rc = tab.rec + offR;
     const int *ri = tab.ridx + offR;
+    const int NR = tab.nrec, NE = tab.nem;
     for(int t = lane; t < nrec; t += nlanes) {
       const int ix = ri[t], fl = ix >> 16;
       if(!(fl & 1))
         continue;
       const int m = ix & 0xff, l = (ix >> 8) & 0xff;
-      const double c0 = rc[4 * t], c1 = rc[4 * t + 1], c2 = rc[4 * t + 2], inv = rc[4 * t + 3];
+      const double c0 = rc[t], c1 = rc[NR + t], c2 = rc[2 * NR + t], inv = rc[3 * NR + t];
       const cplx *q = p1 + ((fl & 8) ? n - 1 : m) * W + l; // the sectorial step reads chain n - 1
       const cplx lo = (fl & 2) ? q[-1] : mk(0, 0), up = q[1];
       const cplx o = (fl & 4) ? cur[m * W + l] : mk(0, 0);
       cur[m * W + l] = mk((lo.x * c0 + up.x * c1 - o.x * c2) * inv, (lo.y * c0 + up.y * c1 - o.y * c2) * inv);
     }
     OB_SYNCWARP();
-    const double *ec = tab.emit + (size_t)offE * 8;
+    const double *ec = tab.emit + offE;
     const int *ei = tab.eidx + offE, *eo = tab.eout + offE;
     for(int t = lane; t < nem; t += nlanes) {
       const int ix = ei[t], fl = ix >> 16;
       if(!(fl & 1))
         continue;
       const int mu = ix & 0xff, l = (ix >> 8) & 0xff, mm1 = mu > 0 ? mu - 1 : 1;
-      const double *c = ec + 8 * t;
+      const double *c = ec + t;
       const cplx *b0p = cur + mu * W + l, *bpp = b0p + W, *bmp = cur + mm1 * W + l;
       const cplx t0 = (fl & 2) ? b0p[0] : mk(0, 0), tp = (fl & 4) ? bpp[0] : mk(0, 0), tm = (fl & 8) ? bmp[0] : mk(0, 0);
       const cplx u0 = (fl & 16) ? b0p[-1] : mk(0, 0), up = (fl & 32) ? bpp[-1] : mk(0, 0), um = (fl & 64) ? bmp[-1] : mk(0, 0);
-      const double fa = c[0], a0 = c[1], a1 = c[2], a2 = c[3], fb = c[4], b0 = c[5], b1 = c[6], b2 = c[7];
+      const double fa = c[0], a0 = c[NE], a1 = c[2 * NE], a2 = c[3 * NE], fb = c[4 * NE], b0 = c[5 * NE], b1 = c[6 * NE],
+                   b2 = c[7 * NE];
       const cplx Av = mk(fa * (a0 * t0.x + a1 * tp.x + a2 * tm.x), fa * (a0 * t0.y + a1 * tp.y + a2 * tm.y));
       const cplx sB = mk(b0 * u0.x + b1 * up.x - b2 * um.x, b0 * u0.y + b1 * up.y - b2 * um.y);
       const cplx Bv = mk(-fb * sB.y, fb * sB.x); // times i fb

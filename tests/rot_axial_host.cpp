@@ -29,7 +29,7 @@ extern "C" int rot_axial_host_tabulated(int NM, const double k[2], double r, dou
   std::vector<double> rec, emit;
   std::vector<int> ridx, eidx, eout;
   ob::rot_axial_tables_build(NM, rec, emit, ridx, eidx, eout);
-  ob::RotAxTab tab = {rec.data(), emit.data(), ridx.data(), eidx.data(), eout.data()};
+  ob::RotAxTab tab = {rec.data(), emit.data(), ridx.data(), eidx.data(), eout.data(), (int)ridx.size(), (int)eidx.size()};
   std::vector<ob::cplx> buf((size_t)ob::rot_axial_fast_entries(NM), ob::mk(1e300, -1e300)); // poison: must never be read
   ob::rot_axial_pair_fast(NM, ob::mk(k[0] * 0.7, k[1]), 1.3 * r, buf.data(), Cp, Cm, 0, 1, tab);
   ob::rot_axial_pair_fast(NM, ob::mk(k[0], k[1]), r, buf.data(), Cp, Cm, 0, 1, tab);
