@@ -218,17 +218,22 @@ __device__ __forceinline__ cplx warp_sum(cplx v) {
   return v;
 }
 
+// SH_P particles per CTA: every table entry (nine scattered 8-byte reads per (k, p, q), the L2-bound part of the kernel)
+// is loaded once and applied to all of them
+#define SH_P 4
 __global__ void __launch_bounds__(512)
-k_sh_source(ShInputs in, int j0, const cplx *__restrict__ Xint_conj, const cplx *__restrict__ TSH1o,
+k_sh_source(ShInputs in, int j0, int count, const cplx *__restrict__ Xint_conj, const cplx *__restrict__ TSH1o,
             const cplx *__restrict__ TSH2o, const cplx *__restrict__ IauxSH2, cplx *__restrict__ K,
             cplx *__restrict__ K1ana) {
-  __shared__ cplx A0[OB_MAX_FLAT], A1[OB_MAX_FLAT], Am1[OB_MAX_FLAT];
-  __shared__ cplx fa0[OB_MAX_NMAX + 2], fa1[OB_MAX_NMAX + 2], fam1[OB_MAX_NMAX + 2];
-  const int j = j0 + blockIdx.x;
+  __shared__ cplx A0[SH_P][OB_MAX_FLAT], A1[SH_P][OB_MAX_FLAT], Am1[SH_P][OB_MAX_FLAT];
+  __shared__ cplx fa0[SH_P][OB_MAX_NMAX + 2], fa1[SH_P][OB_MAX_NMAX + 2], fam1[SH_P][OB_MAX_NMAX + 2];
+  const int jb = j0 + blockIdx.x * SH_P;           // first particle of this CTA
+  const int np = min(SH_P, j0 + count - jb);       // particles of this CTA (the last CTA may hold fewer)
   const int nMax = in.nMax, n = flat_max(nMax), ns = flat_max(in.nMaxS);
-  const double R = in.radius[j];
-  const cplx waveK_j1 = cscale(csqrt_(cmul(in.eps[j], in.mu[j])), in.omega);
-  if(threadIdx.x == 0) {
+  if(threadIdx.x < SH_P) {
+    const int j = jb + min((int)threadIdx.x, np - 1), pp = threadIdx.x;
+    const double R = in.radius[j];
+    const cplx waveK_j1 = cscale(csqrt_(cmul(in.eps[j], in.mu[j])), in.omega);
     // per-order prefactors of A_0, A_1, A_m1 (Symbol.cpp:52-78)
     cplx d[OB_MAX_NMAX + 2], dd[OB_MAX_NMAX + 2];
     cplx z = cscale(waveK_j1, R);
@@ -238,24 +243,23 @@ k_sh_source(ShInputs in, int j0, const cplx *__restrict__ Xint_conj, const cplx 
       dd[i] = csub(cscale(cmul(iz, d[i]), (double)i), d[i + 1]);
     cplx ik = cdiv(mk(1, 0), waveK_j1);
     for(int i = 0; i <= nMax; ++i) {
-      fa0[i] = d[i];
-      fa1[i] = cmuli(cmul(ik, cadd(cmul(waveK_j1, dd[i]), cscale(d[i], 1.0 / R))));
-      fam1[i] = cmuli(cscale(cmul(cscale(ik, 1.0 / R), d[i]), sqrt((double)i * (i + 1.0))));
+      fa0[pp][i] = d[i];
+      fa1[pp][i] = cmuli(cmul(ik, cadd(cmul(waveK_j1, dd[i]), cscale(d[i], 1.0 / R))));
+      fam1[pp][i] = cmuli(cscale(cmul(cscale(ik, 1.0 / R), d[i]), sqrt((double)i * (i + 1.0))));
     }
   }
   __syncthreads();
-  for(int p = threadIdx.x; p < n; p += blockDim.x) {
+  for(int e = threadIdx.x; e < SH_P * n; e += blockDim.x) {
+    const int pp = e / n, p = e - pp * n, j = jb + min(pp, np - 1);
     int l, m;
     unflatten(p, l, m);
     cplx c = Xint_conj[(size_t)j * 2 * n + p], d = Xint_conj[(size_t)j * 2 * n + n + p];
-    A0[p] = cmul(fa0[l], c);
-    A1[p] = cmul(fa1[l], d);
-    Am1[p] = cmul(fam1[l], d);
+    A0[pp][p] = cmul(fa0[pp][l], c);
+    A1[pp][p] = cmul(fa1[pp][l], d);
+    Am1[pp][p] = cmul(fam1[pp][l], d);
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  const cplx eps_0 = mk(8.854187817620389e-12, 0); // recomputed exactly below
-  (void)eps_0;
   const double mu0 = 4.0 * 3.14159265358979323846 * 1e-7;
   const double eps0 = 1.0 / (mu0 * 299792458.0 * 299792458.0);
   const cplx eta_ratio = cdiv(csqrt_(cdiv(in.mu_b, in.eps_b)), csqrt_(mk(mu0 / eps0, 0))); // sqrt(mu_b/eps_b)/sqrt(mu_0/eps_0)
@@ -264,59 +268,66 @@ k_sh_source(ShInputs in, int j0, const cplx *__restrict__ Xint_conj, const cplx 
     int J, M;
     unflatten(kk, J, M);
     const size_t kbase = (size_t)kk * n * n;
-    cplx sum_v = mk(0, 0), sum_u = mk(0, 0), gmn = mk(0, 0), fmn = mk(0, 0);
+    cplx sum_v[SH_P], sum_u[SH_P], gmn[SH_P], fmn[SH_P];
+#pragma unroll
+    for(int pp = 0; pp < SH_P; ++pp)
+      sum_v[pp] = sum_u[pp] = gmn[pp] = fmn[pp] = mk(0, 0);
     for(int p = lane; p < n; p += 32) {
       int J1, M1;
       unflatten(p, J1, M1);
       const int M2 = M - M1;
-      const cplx a0p = A0[p], a1p = A1[p], am1p = Am1[p];
       const int aM2 = M2 < 0 ? -M2 : M2;
       for(int J2 = max(1, aM2); J2 <= nMax; ++J2) {
         const int q = flat_index(J2, M2);
         const size_t t = kbase + (size_t)p * n + q;
-        const cplx a0q = A0[q], a1q = A1[q], am1q = Am1[q];
-        const cplx a1p_am1q = cmul(a1p, am1q), a0p_am1q = cmul(a0p, am1q);
-        // v' (Symbol.cpp:256-260), u' (:199-203)
+        // v' (Symbol.cpp:256-260), u' (:199-203), u'' (Symbol.cpp:322-336)
         const double c00 = __ldg(in.tab[2] + t), c01 = __ldg(in.tab[3] + t);
         const double c10 = __ldg(in.tab[0] + t), c11 = __ldg(in.tab[1] + t);
-        sum_v.x += a1p_am1q.x * c00 + a0p_am1q.x * c01;
-        sum_v.y += a1p_am1q.y * c00 + a0p_am1q.y * c01;
-        sum_u.x += a1p_am1q.x * c10 + a0p_am1q.x * c11;
-        sum_u.y += a1p_am1q.y * c10 + a0p_am1q.y * c11;
-        // u'' (Symbol.cpp:322-336)
-        const cplx mm = cmul(am1p, am1q);
         const double wm = __ldg(in.tab[4] + t);
-        gmn.x += mm.x * wm;
-        gmn.y += mm.y * wm;
-        const cplx t11 = cmul(a1p, a1q), t00 = cmul(a0p, a0q), t10 = cmul(a1p, a0q), t01 = cmul(a0p, a1q);
         const double w11 = __ldg(in.tab[5] + t), w00 = __ldg(in.tab[6] + t), w10 = __ldg(in.tab[7] + t),
                      w01 = __ldg(in.tab[8] + t);
-        fmn.x += t11.x * w11 + t00.x * w00 + t10.x * w10 + t01.x * w01;
-        fmn.y += t11.y * w11 + t00.y * w00 + t10.y * w10 + t01.y * w01;
+#pragma unroll
+        for(int pp = 0; pp < SH_P; ++pp) {
+          const cplx a0p = A0[pp][p], a1p = A1[pp][p], am1p = Am1[pp][p];
+          const cplx a0q = A0[pp][q], a1q = A1[pp][q], am1q = Am1[pp][q];
+          const cplx a1p_am1q = cmul(a1p, am1q), a0p_am1q = cmul(a0p, am1q);
+          sum_v[pp].x += a1p_am1q.x * c00 + a0p_am1q.x * c01;
+          sum_v[pp].y += a1p_am1q.y * c00 + a0p_am1q.y * c01;
+          sum_u[pp].x += a1p_am1q.x * c10 + a0p_am1q.x * c11;
+          sum_u[pp].y += a1p_am1q.y * c10 + a0p_am1q.y * c11;
+          const cplx mm = cmul(am1p, am1q);
+          gmn[pp].x += mm.x * wm;
+          gmn[pp].y += mm.y * wm;
+          const cplx t11 = cmul(a1p, a1q), t00 = cmul(a0p, a0q), t10 = cmul(a1p, a0q), t01 = cmul(a0p, a1q);
+          fmn[pp].x += t11.x * w11 + t00.x * w00 + t10.x * w10 + t01.x * w01;
+          fmn[pp].y += t11.y * w11 + t00.y * w00 + t10.y * w10 + t01.y * w01;
+        }
       }
     }
-    sum_v = warp_sum(sum_v);
-    sum_u = warp_sum(sum_u);
-    gmn = warp_sum(gmn);
-    fmn = warp_sum(fmn);
-    if(lane == 0) {
-      const cplx ksiparppar = in.ksiparppar[j], ksippp = in.ksippp[j], gamma = in.gamma[j];
-      // Symbol.cpp:266-267 / :210-211
-      cplx vp = cmul(cmul(cscale(sum_v, 2.0), ksiparppar), eta_ratio);
-      cplx up = cmul(cmul(cmuli(cscale(sum_u, 2.0)), ksiparppar), eta_ratio);
-      // Symbol.cpp:347-351
-      const double sq = sqrt((double)(J * (J + 1)));
-      cplx inv = cdiv(mk(1.0, 0), cscale(waveK_01, R));
-      cplx term1 = cmul(cmuli(cscale(cmul(ksippp, gmn), sq)), inv);
-      cplx ge = cmul(gamma, cdiv(mk(eps0, 0), in.eps_SH[j]));
-      cplx term2 = cmul(cmuli(cscale(cmul(ge, cadd(gmn, fmn)), sq)), inv);
-      cplx upp = cadd(term1, term2);
-      // PreconditionedMatrix.cpp:1381-1383 and :1424-1426 (v'' == 0, Geometry.cpp:296)
-      const size_t o = (size_t)j * 2 * ns;
-      K[o + kk] = cmul(TSH1o[o + kk], vp);
-      K[o + ns + kk] = cadd(cmul(TSH1o[o + ns + kk], up), cmul(TSH2o[o + ns + kk], upp));
-      K1ana[o + kk] = mk(0, 0);
-      K1ana[o + ns + kk] = cmul(IauxSH2[o + ns + kk], upp);
+#pragma unroll
+    for(int pp = 0; pp < SH_P; ++pp) {
+      const cplx sv = warp_sum(sum_v[pp]), su = warp_sum(sum_u[pp]), gm = warp_sum(gmn[pp]), fm = warp_sum(fmn[pp]);
+      if(lane == 0 && pp < np) {
+        const int j = jb + pp;
+        const double R = in.radius[j];
+        const cplx ksiparppar = in.ksiparppar[j], ksippp = in.ksippp[j], gamma = in.gamma[j];
+        // Symbol.cpp:266-267 / :210-211
+        cplx vp = cmul(cmul(cscale(sv, 2.0), ksiparppar), eta_ratio);
+        cplx up = cmul(cmul(cmuli(cscale(su, 2.0)), ksiparppar), eta_ratio);
+        // Symbol.cpp:347-351
+        const double sq = sqrt((double)(J * (J + 1)));
+        cplx inv = cdiv(mk(1.0, 0), cscale(waveK_01, R));
+        cplx term1 = cmul(cmuli(cscale(cmul(ksippp, gm), sq)), inv);
+        cplx ge = cmul(gamma, cdiv(mk(eps0, 0), in.eps_SH[j]));
+        cplx term2 = cmul(cmuli(cscale(cmul(ge, cadd(gm, fm)), sq)), inv);
+        cplx upp = cadd(term1, term2);
+        // PreconditionedMatrix.cpp:1381-1383 and :1424-1426 (v'' == 0, Geometry.cpp:296)
+        const size_t o = (size_t)j * 2 * ns;
+        K[o + kk] = cmul(TSH1o[o + kk], vp);
+        K[o + ns + kk] = cadd(cmul(TSH1o[o + ns + kk], up), cmul(TSH2o[o + ns + kk], upp));
+        K1ana[o + kk] = mk(0, 0);
+        K1ana[o + ns + kk] = cmul(IauxSH2[o + ns + kk], upp);
+      }
     }
   }
 }
@@ -325,7 +336,7 @@ void launch_sh_source(ShInputs const &in, int j0, int count, const cplx *Xint_co
                       const cplx *TSH2o, const cplx *IauxSH2, cplx *K, cplx *K1ana, cudaStream_t st) {
   if(count <= 0)
     return;
-  k_sh_source<<<count, 512, 0, st>>>(in, j0, Xint_conj, TSH1o, TSH2o, IauxSH2, K, K1ana);
+  k_sh_source<<<(count + SH_P - 1) / SH_P, 512, 0, st>>>(in, j0, count, Xint_conj, TSH1o, TSH2o, IauxSH2, K, K1ana);
   OB_CUDA(cudaGetLastError());
 }
 
