@@ -17,10 +17,16 @@
 //     [A B; B A]: q+ = (A^T + B^T) p+, q- = (A^T - B^T) p-.
 // Record per unordered pair (i < j):
 //   ph[m + NM] = exp(i m phi)                                                      (2 NM + 1 complex)
-//   Cp = A + B as two planes of doubles [Re | Im], entry offX(a) + (n - n0) w + (l - n0) holds (n,a),(l,a),
-//        a = 0..NM, n0 = max(a,1), w = NM - n0 + 1;   Cm = A - B likewise for a = 1..NM (a = 0: B = 0)
-//   Ds[offDs(n) + a' (n + 1) + a],  Da[offDa(n) + (a' - 1) n + (a - 1)]                 (reals)
+//   Cp = A + B as two planes of doubles [Re | Im], one w x w block per order a = 0..NM at offX(a), n0 = max(a,1),
+//        w = NM - n0 + 1, holding (n,a),(l,a);   Cm = A - B likewise for a = 1..NM (a = 0: B = 0)
+//   Ds (n + 1) x (n + 1) at offDs(n),  Da n x n at offDa(n) for every degree n            (reals)
 // 21.4 KB at nMax 10 (v1 30 KB, pair form 460.8 KB), 11.7 KB at nMax 8.
+// Inside a block the entries are in FRAGMENT ORDER (rot_frag_index / rot_cidx in ob_rot_axial.cuh): every DMMA A
+// fragment the apply loads is one contiguous run in lane order, compacted to its valid rows and K entries: same bytes
+// as the plain row-major blocks, but 2 shared-memory wavefronts per fragment load instead of 4 (a half-warp reads 16
+// consecutive doubles; with the odd leading dimensions of these blocks it hit every bank twice).  The assembly
+// kernels write through the transpose symmetries (C(n,l) = (-1)^(n+l) C(l,n), D[a',a] = (-1)^(a'-a) D[a,a']) so that
+// the lanes of one recursion level fill runs of consecutive K entries.
 //
 // Work decomposition: rows are grouped in blocks of I; a strip (b, j) holds the pairs (i, j), i in block b, i < j.
 // Records are stored strip by strip (block-major); ranks and CTAs own contiguous strip ranges of equal pair counts.
@@ -94,8 +100,7 @@ struct EmitAxial {
     unflatten(r, l, k);
     if(mu != k || mu < 0)
       return;
-    const int n0 = rot_n0(mu), w = NM - n0 + 1;
-    const int e = rot_offX(NM, mu) + (n - n0) * w + (l - n0);
+    const int e = rot_cidx(NM, mu, n, l); // fragment order (ob_rot_axial.cuh)
     Cp[e] = a.x + b.x;
     Cp[X + e] = a.y + b.y;
     if(mu >= 1) {
@@ -338,7 +343,11 @@ k_rot_tables(const double *__restrict__ xyz, const int2 *__restrict__ pair_ij, l
         }
         if(j < 1)
           continue;
-        // flip basis (tests/rot2_model.py build_pair): rows a' = mp, columns a = m
+        // flip basis (tests/rot2_model.py build_pair): D[a' = mp, a = m].  Fragment order (ob_rot_axial.cuh) has row a and
+        // K index a'; this thread's (mp, m) would be one K index of row m, 32 bytes from its neighbour's.  With
+        // D[a', a] = (-1)^(a' - a) D[a, a'] it writes the entry (a' = m, a = mp) instead: consecutive threads fill
+        // consecutive K entries of row mp
+        const double st = ((mp - m) & 1) ? -1.0 : 1.0;
         double vs;
         if(mp == 0 && m == 0)
           vs = dP;
@@ -346,9 +355,9 @@ k_rot_tables(const double *__restrict__ xyz, const int2 *__restrict__ pair_ij, l
           vs = 1.41421356237309504880 * dP;
         else {
           vs = dP + sa * dM;
-          Da[rot_offDa(j) + (mp - 1) * j + (m - 1)] = dP - sa * dM;
+          Da[rot_offDa(j) + rot_frag_index_a(j, mp, m - 1)] = st * (dP - sa * dM);
         }
-        Ds[rot_offDs(j) + mp * (j + 1) + m] = vs;
+        Ds[rot_offDs(j) + rot_frag_index(j + 1, j + 1, mp, m)] = st * vs;
       }
     }
     __syncthreads();
@@ -358,7 +367,9 @@ k_rot_tables(const double *__restrict__ xyz, const int2 *__restrict__ pair_ij, l
 // ---------------------------------------------------------------------------------------------
 // apply
 // ---------------------------------------------------------------------------------------------
+#ifndef ROT_WARPS
 #define ROT_WARPS 4
+#endif
 #ifndef ROT_MIN_CTAS
 #define ROT_MIN_CTAS 3 // resident CTAs per SM the kernel is compiled for (168 registers: the natural count is 176 at nMax 10)
 #endif
@@ -481,7 +492,7 @@ static size_t rot_smem_bytes(RotLayout const &L, int I) {
 // per-lane state of the pair being processed (everything else is an immediate)
 struct RotLane {
   int warp, fr, fc, cpol;
-  const double *Ds, *Da, *Cp, *Cm; // sections of the current record, already offset by this lane's fragment row (+ fr)
+  const double *Ds, *Da, *Cp, *Cm; // sections of the current record, already offset by this lane's place in a fragment (+ 4 fr + fc = lane)
   const double *vb;                // class-vector buffer + plane / in-row offset of the B fragment
   const double *pb;                // channel buffer + plane / in-row offset of the B fragment
   double *pst;                     // channel buffer + direction plane + 2 * pol (P1 stores)
@@ -492,20 +503,23 @@ struct RotLane {
   bool dir1;
 };
 
-// accumulation chain of KS K-steps over K columns: straight-line loads, then DMMAs; A advances stepA doubles per step,
-// B 16 doubles; only the last step can run past the K range (compile-time known), where the lane's A entry is zeroed
+// accumulation chain of KS K-steps over K columns: straight-line loads, then DMMAs; the A fragments of a row tile are
+// consecutive runs in the record (fragment order, ob_rot_axial.cuh): pa = first fragment + 4 fr + fc, stepA = 4 Rt doubles
+// per step; a last step of Kv < 4 valid K entries is compacted to row stride Kv (pt = its address for this lane) and
+// the lane's A entry is zeroed past the K range (compile-time known); B advances 16 doubles per step
 // KEEP: 0 = load the A fragments, 1 = load them and keep them in `keep` (registers), 2 = take them from `keep` (the
 // small-d fragments of P1 serve P3 again: D[a', a] = (-1)^(a' - a) D[a, a'] makes both phases read the same entries)
 template <int KS, int K, int KEEP = 0>
 __device__ __forceinline__ void rot_chain(double (&acc)[2], const double *__restrict__ pa, int stepA,
-                                          const double *__restrict__ pb, int fc, double *keep = nullptr) {
+                                          const double *__restrict__ pt, const double *__restrict__ pb, int fc,
+                                          double *keep = nullptr) {
   double av[KS], bv[KS];
 #pragma unroll
   for(int s = 0; s < KS; ++s) {
     if(KEEP == 2)
       av[s] = keep[s];
     else
-      av[s] = pa[s * stepA];
+      av[s] = (4 * KS > K && s == KS - 1) ? pt[0] : pa[s * stepA];
     bv[s] = pb[16 * s];
   }
   if(KEEP != 2 && 4 * KS > K)
@@ -522,12 +536,13 @@ __device__ __forceinline__ void rot_chain(double (&acc)[2], const double *__rest
 // two chains on the same B fragments: real and imaginary plane of one complex matrix (planes dI doubles apart)
 template <int KS, int K>
 __device__ __forceinline__ void rot_chain2(double (&accR)[2], double (&accI)[2], const double *__restrict__ pa, int dI,
-                                           int stepA, const double *__restrict__ pb, int fc) {
+                                           int stepA, const double *__restrict__ pt, const double *__restrict__ pb, int fc) {
   double ar[KS], ai[KS], bv[KS];
 #pragma unroll
   for(int s = 0; s < KS; ++s) {
-    ar[s] = pa[s * stepA];
-    ai[s] = pa[s * stepA + dI];
+    const double *q = (4 * KS > K && s == KS - 1) ? pt : pa + s * stepA;
+    ar[s] = q[0];
+    ai[s] = q[dI];
     bv[s] = pb[16 * s];
   }
   if(4 * KS > K) {
@@ -575,10 +590,17 @@ __device__ __forceinline__ void rot_dchains(RotLane const &c, double (&accS)[2],
   constexpr int n = T.dn[U], m0 = T.dm[U], n1 = n + 1, slot = rot_keep_slots(NM, W, U);
   constexpr int KS = ROT_KEEP_S ? (PHASE == 1 ? 1 : 2) : 0, KA = ROT_KEEP_A ? (PHASE == 1 ? 1 : 2) : 0;
   accS[0] = accS[1] = accA[0] = accA[1] = 0.0;
-  rot_chain<(n1 + 3) / 4, n1, KS>(accS, c.Ds + rot_offDs(n) + m0 + c.fc * n1, 4 * n1, c.vb + 4 * rot_offF(n) + 4 * c.fc, c.fc,
-                                  keep + slot);
-  rot_chain<(n + 3) / 4, n, KA>(accA, c.Da + rot_offDa(n) + m0 - 1 + c.fc * n, 4 * n, c.vb + 4 * (rot_offF(n) + n + 2) + 4 * c.fc,
-                                c.fc, keep + slot + (ROT_KEEP_S ? (n1 + 3) / 4 : 0));
+  // s class: rows a = m0 .. of the (n + 1) x (n + 1) matrix, Rt valid rows in this tile
+  constexpr int RtS = n1 - m0 < 8 ? n1 - m0 : 8, ksS = (n1 + 3) / 4, kvS = n1 - 4 * (ksS - 1);
+  const double *paS = c.Ds + rot_offDs(n) + m0 * n1;
+  rot_chain<ksS, n1, KS>(accS, paS, 4 * RtS, paS + 4 * RtS * (ksS - 1) - (4 - kvS) * c.fr, c.vb + 4 * rot_offF(n) + 4 * c.fc, c.fc,
+                         keep + slot);
+  // a class: rows a = max(m0, 1) .. of the n x n matrix (tile 0: a phantom row 0 in front of the seven rows a = 1 .. 7)
+  constexpr int firstA = m0 ? m0 : 1, lastA = m0 + 7 < n ? m0 + 7 : n, RtA = lastA - firstA + 1, ksA = (n + 3) / 4,
+                kvA = n - 4 * (ksA - 1), radj = m0 ? 0 : -1;
+  const double *paA = c.Da + rot_offDa(n) + (firstA - 1) * n + 4 * radj;
+  rot_chain<ksA, n, KA>(accA, paA, 4 * RtA, paA + 4 * RtA * (ksA - 1) - (4 - kvA) * c.fr - (4 - kvA) * radj,
+                        c.vb + 4 * (rot_offF(n) + n + 2) + 4 * c.fc, c.fc, keep + slot + (ROT_KEEP_S ? ksS : 0));
 }
 
 // P1 unit: u = D^T t, channel sums p+- = TE_s +- TM_a (TE lanes), r+- = TM_s +- TE_a (TM lanes)
@@ -613,7 +635,9 @@ template <int NM, int W, int U> __device__ __forceinline__ void rot_p2_unit(RotL
     return;
   double apr[2] = {0, 0}, api[2] = {0, 0};
   const double *pb = c.pb + 4 * rot_offP(NM, a) + 4 * c.fc;
-  rot_chain2<ks, w>(apr, api, c.Cp + rot_offX(NM, a) + m0 + c.fc * w, XC, 4 * w, pb, c.fc);
+  constexpr int Rt = w - m0 < 8 ? w - m0 : 8, kv = w - 4 * (ks - 1); // fragment order: tile m0 / 8 of the w x w block of order a
+  const int tofs = rot_offX(NM, a) + m0 * w + 4 * Rt * (ks - 1) - (4 - kv) * c.fr;
+  rot_chain2<ks, w>(apr, api, c.Cp + rot_offX(NM, a) + m0 * w, XC, 4 * Rt, c.Cp + tofs, pb, c.fc);
   // complex products: (Re C p_re - Im C p_im, Re C p_im + Im C p_re); lane = (row n, channel fc = direction * 2 + family)
   const double qpx = apr[0] - api[1], qpy = apr[1] + api[0];
   const int row = m0 + c.fr, n = n0 + row;
@@ -623,7 +647,7 @@ template <int NM, int W, int U> __device__ __forceinline__ void rot_p2_unit(RotL
       *(cplx *)V = mk(qpx, qpy);
   } else {
     double amr[2] = {0, 0}, ami[2] = {0, 0};
-    rot_chain2<ks, w>(amr, ami, c.Cm + rot_offX(NM, a) + m0 + c.fc * w, XM, 4 * w, pb + SS, c.fc);
+    rot_chain2<ks, w>(amr, ami, c.Cm + rot_offX(NM, a) + m0 * w, XM, 4 * Rt, c.Cm + tofs, pb + SS, c.fc);
     const double qmx = amr[0] - ami[1], qmy = amr[1] + ami[0];
     constexpr double h = (a & 1) ? -0.5 : 0.5; // (-1)^a of the transposed small-d read, and the 1/2 of the channel split
     if(m0 + 7 < w || row < w) {
@@ -682,11 +706,23 @@ template <int NM, int W, int... U> __device__ __forceinline__ void rot_p3_warp(R
   case 2:                                                                                                              \
     fn<NM, 2>(c, keep, seq);                                                                                                 \
     break;                                                                                                             \
-  default:                                                                                                             \
+  case 3:                                                                                                              \
     fn<NM, 3>(c, keep, seq);                                                                                                 \
     break;                                                                                                             \
+  case 4:                                                                                                              \
+    fn<NM, 4>(c, keep, seq);                                                                                                 \
+    break;                                                                                                             \
+  case 5:                                                                                                              \
+    fn<NM, 5>(c, keep, seq);                                                                                                 \
+    break;                                                                                                             \
+  case 6:                                                                                                              \
+    fn<NM, 6>(c, keep, seq);                                                                                                 \
+    break;                                                                                                             \
+  default:                                                                                                             \
+    fn<NM, 7>(c, keep, seq);                                                                                                 \
+    break;                                                                                                             \
   }
-static_assert(ROT_WARPS == 4, "ROT_PER_WARP enumerates four warps");
+static_assert(ROT_WARPS == 4 || ROT_WARPS == 8, "ROT_PER_WARP enumerates up to eight warps (no unit is owned by a warp >= ROT_WARPS)");
 
 template <int NM>
 __global__ void __launch_bounds__(ROT_THREADS, ROT_MIN_CTAS) k_matvec_rot(const __grid_constant__ RotArgs a) {
@@ -756,6 +792,11 @@ __global__ void __launch_bounds__(ROT_THREADS, ROT_MIN_CTAS) k_matvec_rot(const 
   const double psa = (pa & 1) ? -1.0 : 1.0, psn = (pn & 1) ? -1.0 : 1.0;
   const int pfs = rot_offF(pn) + pa, pfa = pfs + pn + 1;
   const int pfs2 = rot_offF(pz2 ? pn + 1 : pn); // F index of s_0 of the second degree
+  // Consecutive P0 threads own consecutive 32-byte rows [TE | TM] of the class vectors: a quarter-warp storing the same
+  // half of its rows hits every 16-byte bank group twice (ncu: 8.5 - 9 wavefronts per STS.128 where 4 is the minimum).
+  // Lanes 4 .. 7 of each quarter therefore carry TM in slot 0 and TE in slot 1 from the x loads on (the flip-basis
+  // arithmetic is the same for both polarisations up to the sign gm / ge): every store covers eight bank groups
+  const int psw = (lane >> 2) & 1;
   // ---- fragment geometry of this lane ----
   RotLane c;
   c.warp = tid >> 5;
@@ -780,10 +821,10 @@ __global__ void __launch_bounds__(ROT_THREADS, ROT_MIN_CTAS) k_matvec_rot(const 
   int4 pi = a.pinfo[qbeg], pnext = a.pinfo[qbeg + 1 < qend ? qbeg + 1 : qbeg];
   auto load_x = [&](cplx (&xr)[4], int part) {
     const cplx *xs = a.x + (size_t)part * n2;
-    xr[0] = xs[fpos];
-    xr[1] = xs[nH + fpos];
-    xr[2] = xs[fneg];
-    xr[3] = xs[nH + fneg];
+    xr[0] = xs[fpos + (psw ? nH : 0)]; // slot 0 = TE, slot 1 = TM; swapped in the lanes with psw (see p0_dir)
+    xr[1] = xs[fpos + (psw ? 0 : nH)];
+    xr[2] = xs[fneg + (psw ? nH : 0)];
+    xr[3] = xs[fneg + (psw ? 0 : nH)];
   };
   if(p0live) {
     if(SPLIT)
@@ -801,10 +842,10 @@ __global__ void __launch_bounds__(ROT_THREADS, ROT_MIN_CTAS) k_matvec_rot(const 
     const unsigned char *rec = smem + (size_t)cur * L.rec_bytes;
     const cplx *s_ph = (const cplx *)rec;
     c.ph = s_ph + NM;
-    c.Cp = (const double *)(rec + L.offCp) + c.fr;
-    c.Cm = (const double *)(rec + L.offCm) - NM * NM + c.fr;
-    c.Ds = (const double *)(rec + L.offDs) + c.fr;
-    c.Da = (const double *)(rec + L.offDa) + c.fr;
+    c.Cp = (const double *)(rec + L.offCp) + lane;
+    c.Cm = (const double *)(rec + L.offCm) - NM * NM + lane;
+    c.Ds = (const double *)(rec + L.offDs) + lane;
+    c.Da = (const double *)(rec + L.offDa) + lane;
     c.vb = bufA + bofs;
     c.pb = bufB + bofsP;
     c.pst = bufB + sofsP;
@@ -816,27 +857,29 @@ __global__ void __launch_bounds__(ROT_THREADS, ROT_MIN_CTAS) k_matvec_rot(const 
       const cplx pp = s_ph[NM + pa], pm = s_ph[NM - pa];
       // one direction: phases, (-1)^deg and -1 on TM for direction 1 (x_i), flip basis, store
       auto p0_dir = [&](int dir, const cplx *xr) {
-        const double ge = dir ? psn : 1.0, gm = dir ? -psn : 1.0;
-        cplx *ts = (cplx *)(bufA + dir * PS + 4 * pfs), *ta = (cplx *)(bufA + dir * PS + 4 * pfa);
+        const double ge0 = dir ? psn : 1.0, gm0 = dir ? -psn : 1.0;
+        const double ge = psw ? gm0 : ge0, gm = psw ? ge0 : gm0; // signs of slot 0 / slot 1
+        const int o1 = 1 - 2 * psw;                              // slot 0 goes to ts[0] (ts already at its half), slot 1 to ts[o1]
+        cplx *ts = (cplx *)(bufA + dir * PS + 4 * pfs) + psw, *ta = (cplx *)(bufA + dir * PS + 4 * pfa) + psw;
         if(SPLIT && pz) { // exp(i 0 phi) = 1; the second degree has the opposite parity
           ts[0] = cscale(xr[0], ge);
-          ts[1] = cscale(xr[1], gm);
+          ts[o1] = cscale(xr[1], gm);
           if(pz2) {
-            cplx *t2 = (cplx *)(bufA + dir * PS + 4 * pfs2);
+            cplx *t2 = (cplx *)(bufA + dir * PS + 4 * pfs2) + psw;
             t2[0] = cscale(xr[2], dir ? -ge : ge);
-            t2[1] = cscale(xr[3], dir ? -gm : gm);
+            t2[o1] = cscale(xr[3], dir ? -gm : gm);
           }
         } else if(pa == 0) {
           ts[0] = cscale(xr[0], ge);
-          ts[1] = cscale(xr[1], gm);
+          ts[o1] = cscale(xr[1], gm);
         } else {
           const cplx te_p = cmul(pp, xr[0]), tm_p = cmul(pp, xr[1]);
           const cplx te_m = cmul(pm, xr[2]), tm_m = cmul(pm, xr[3]);
           const double fe = ge * ROT_SQH, fm = gm * ROT_SQH;
           ts[0] = mk(fe * (te_p.x + psa * te_m.x), fe * (te_p.y + psa * te_m.y));
-          ts[1] = mk(fm * (tm_p.x + psa * tm_m.x), fm * (tm_p.y + psa * tm_m.y));
+          ts[o1] = mk(fm * (tm_p.x + psa * tm_m.x), fm * (tm_p.y + psa * tm_m.y));
           ta[0] = mk(fe * (te_p.x - psa * te_m.x), fe * (te_p.y - psa * te_m.y));
-          ta[1] = mk(fm * (tm_p.x - psa * tm_m.x), fm * (tm_p.y - psa * tm_m.y));
+          ta[o1] = mk(fm * (tm_p.x - psa * tm_m.x), fm * (tm_p.y - psa * tm_m.y));
         }
       };
       if(SPLIT)
@@ -978,7 +1021,7 @@ void rot_plan_build(RotPlan &p, int nobj, int NM, int world, int rank, int sm_co
   // rows per block: as many (<= 4) as keep three CTAs per SM resident (the row sums of a block live in shared memory)
   int I = g_rot_rows > 0 ? g_rot_rows : 4;
   const size_t sm_total = (size_t)228 * 1024, cta_max = (size_t)227 * 1024;
-  while(I > 1 && 3 * (rot_smem_bytes(L, I) + 1024) > sm_total)
+  while(I > 1 && ROT_MIN_CTAS * (rot_smem_bytes(L, I) + 1024) > sm_total)
     --I;
   if(rot_smem_bytes(L, I) > cta_max)
     throw Error("rotated-axial operator: record does not fit in shared memory");

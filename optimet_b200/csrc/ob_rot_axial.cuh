@@ -24,6 +24,32 @@ __host__ __device__ constexpr inline int rot_offX(int NM, int mu) { // sum_{u<mu
   return mu <= 0 ? 0
                  : NM * NM + (NM * (NM + 1) * (2 * NM + 1) / 6 - (NM - mu + 1) * (NM - mu + 2) * (2 * (NM - mu + 1) + 1) / 6);
 }
+// FRAGMENT ORDER of the record's matrices.  The apply kernel (k_matvec_rot) reads every matrix as A operands of the FP64
+// tensor-core instruction DMMA.8x8x4: lane (fr, fc) = (lane >> 2, lane & 3) holds element (row 8 t + fr, K index 4 s + fc)
+// of row tile t and K step s.  Stored row- or column-major with the odd leading dimensions of these matrices, the 16
+// lanes of a half-warp hit every 8-byte bank up to twice (4 shared-memory wavefronts per fragment where 2 is the
+// minimum: ncu, profiles/r3c_matvec_rot_full.txt).  So the assembly kernels write each fragment as ONE CONTIGUOUS RUN in
+// lane order, compacted to its valid rows (Rt <= 8) and valid K entries (Kv <= 4): element (row, kcol) of a rows x K
+// matrix sits at  8 t K + Rt 4 s + (row - 8 t) Kv + (kcol - 4 s).  Same bytes as the plain layout (no padding), and a
+// half-warp reads <= 16 consecutive doubles: conflict-free.  Lanes past Rt or Kv read neighbouring finite entries
+// (rows of a product are independent; K-tail entries are zeroed in registers).
+__host__ __device__ constexpr inline int rot_frag_index(int rows, int K, int row, int kcol) {
+  const int t = row >> 3, Rt = rows - 8 * t < 8 ? rows - 8 * t : 8, s = kcol >> 2, Kv = K - 4 * s < 4 ? K - 4 * s : 4;
+  return 8 * t * K + Rt * 4 * s + (row - 8 * t) * Kv + (kcol - 4 * s);
+}
+// the a class of a small-d matrix: rows a = 1 .. n keep the lane of row a of the s class (fr = a - 8 t), so tile 0 holds
+// the seven rows a = 1 .. 7 behind a phantom row 0; K index kcol = a' - 1
+__host__ __device__ constexpr inline int rot_frag_index_a(int n, int a, int kcol) {
+  const int t = a >> 3, first = t ? 8 * t : 1, last = 8 * t + 7 < n ? 8 * t + 7 : n, Rt = last - first + 1;
+  const int s = kcol >> 2, Kv = n - 4 * s < 4 ? n - 4 * s : 4;
+  return (first - 1) * n + Rt * 4 * s + (a - first) * Kv + (kcol - 4 * s);
+}
+// record index of the axial coefficient (mu; column degree n, row degree l): the apply contracts over n (K index) and
+// produces l (row); the plain layout was rot_offX(mu) + (n - n0) w + (l - n0)
+__host__ __device__ constexpr inline int rot_cidx(int NM, int mu, int n, int l) {
+  const int n0 = rot_n0(mu), w = NM - n0 + 1;
+  return rot_offX(NM, mu) + rot_frag_index(w, w, l - n0, n - n0);
+}
 __host__ __device__ inline double ta_a_plus(int n, int m) {
   return -sqrt((double)((n + m + 1) * (n - m + 1)) / (double)((2 * n + 1) * (2 * n + 3)));
 }
@@ -112,8 +138,7 @@ inline void rot_axial_tables_build(int NM, std::vector<double> &rec, std::vector
         const int fl = 1 | ((mu <= n && mu <= l) ? 2 : 0) | ((mp1 <= n && mp1 <= l) ? 4 : 0) | ((mm1 <= n && mm1 <= l) ? 8 : 0) |
                        ((mu <= n && mu <= lm) ? 16 : 0) | ((mp1 <= n && mp1 <= lm) ? 32 : 0) | ((mm1 <= n && mm1 <= lm) ? 64 : 0);
         eidx[(size_t)rot_axial_offE(NM, n) + t] = mu | (l << 8) | (fl << 16);
-        const int w = NM - n0 + 1;
-        eout[(size_t)rot_axial_offE(NM, n) + t] = rot_offX(NM, mu) + (n - n0) * w + (l - n0);
+        eout[(size_t)rot_axial_offE(NM, n) + t] = rot_cidx(NM, mu, l, n); // written through the transpose symmetry, see below
       }
       const size_t NE = (size_t)rot_axial_offE(NM, NM + 1), ie = (size_t)rot_axial_offE(NM, n) + t;
       double c[8];
@@ -125,17 +150,25 @@ inline void rot_axial_tables_build(int NM, std::vector<double> &rec, std::vector
       c[5] = 2.0 * mu * sqrt((double)((l - mu) * (l + mu)));
       c[6] = sqrt((double)((n - mu) * (n + mu + 1) * (l - mu) * (l - mu - 1)));
       c[7] = sqrt((double)((n + mu) * (n - mu + 1) * (l + mu) * (l + mu - 1)));
+      // Level n produces (n, l) for every l, i.e. one K index of every ROW of the fragment order: 8-byte stores 32 bytes
+      // apart.  A(n, l) = (-1)^(n + l) A(l, n) and the same for B (reciprocity of the axial translation), so the level
+      // writes sg (n, l) into the place of (l, n) instead: the lanes of a level fill runs of consecutive K entries.  The
+      // sign rides on the two prefactors (exact)
+      if((n + l) & 1) {
+        c[0] = -c[0];
+        c[4] = -c[4];
+      }
       for(int q = 0; q < 8; ++q)
         emit[q * NE + ie] = c[q];
     }
   }
 }
 
-// Axial A[(n,mu),(l,mu)], B[...] for translation r along z with wavenumber k into Aout / Bout (compact layout of
-// ob_rot.cu: rot_offX(mu) + (n - n0)(NM - n0 + 1) + (l - n0)).  `lane` of `nlanes` cooperating threads; buf as above.
+// Axial A[(n,mu),(l,mu)], B[...] for translation r along z with wavenumber k into Aout / Bout (plain compact layout
+// e = rot_offX(mu) + (n - n0)(NM - n0 + 1) + (l - n0)).  `lane` of `nlanes` cooperating threads; buf as above.
 // combine = 1: Aout[e] = A + B for every mu and Bout[e - NM^2] = A - B for mu >= 1 (interleaved complex).
-// combine = 2 (record layout of ob_rot.cu): the same values as planes of doubles, Aout -> [Re(A+B)[X] | Im(A+B)[X]],
-// Bout -> [Re(A-B)[X - NM^2] | Im(A-B)[X - NM^2]], X = rot_offX(NM, NM + 1).
+// combine = 2 (record layout of ob_rot.cu): planes of doubles in FRAGMENT ORDER, entry (l, n) written as (-1)^(n + l) (n, l),
+// Aout -> [Re(A+B)[X] | Im(A+B)[X]], Bout -> [Re(A-B)[X - NM^2] | Im(A-B)[X - NM^2]], X = rot_offX(NM, NM + 1).
 __host__ __device__ inline void rot_axial_pair(int NM, cplx k, double r, cplx *buf, cplx *Aout, cplx *Bout, int lane,
                                                int nlanes, int combine = 0) {
   const int LL = 2 * NM, W = LL + 3, CH = NM + 2;
@@ -204,13 +237,15 @@ __host__ __device__ inline void rot_axial_pair(int NM, cplx k, double r, cplx *b
       const cplx Bv = mk(-fb * sB.y, fb * sB.x); // times i fb (factor = (0, fb))
       const int w = NM - n0 + 1, e = rot_offX(NM, mu) + (n - n0) * w + (l - n0);
       if(combine == 2) {
-        const int X = rot_offX(NM, NM + 1), XM = X - NM * NM;
+        // sg (n, l) stored as entry (l, n): (n, l) = (-1)^(n + l) (l, n), see rot_axial_tables_build
+        const int X = rot_offX(NM, NM + 1), XM = X - NM * NM, f = rot_cidx(NM, mu, l, n);
+        const double sg = ((n + l) & 1) ? -1.0 : 1.0;
         double *P = (double *)Aout, *M = (double *)Bout;
-        P[e] = Av.x + Bv.x;
-        P[X + e] = Av.y + Bv.y;
+        P[f] = sg * (Av.x + Bv.x);
+        P[X + f] = sg * (Av.y + Bv.y);
         if(mu >= 1) {
-          M[e - NM * NM] = Av.x - Bv.x;
-          M[XM + e - NM * NM] = Av.y - Bv.y;
+          M[f - NM * NM] = sg * (Av.x - Bv.x);
+          M[XM + f - NM * NM] = sg * (Av.y - Bv.y);
         }
       } else if(combine) {
         Aout[e] = cadd(Av, Bv);

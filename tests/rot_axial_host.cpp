@@ -35,3 +35,8 @@ extern "C" int rot_axial_host_tabulated(int NM, const double k[2], double r, dou
   ob::rot_axial_pair_fast(NM, ob::mk(k[0], k[1]), r, buf.data(), Cp, Cm, 0, 1, tab);
   return ob::rot_offX(NM, NM + 1);
 }
+
+// fragment order of the record's matrices (ob_rot_axial.cuh), for tests/test_rot_axial_host.py
+extern "C" int rot_frag_index_host(int rows, int K, int row, int kcol) { return ob::rot_frag_index(rows, K, row, kcol); }
+extern "C" int rot_frag_index_a_host(int n, int a, int kcol) { return ob::rot_frag_index_a(n, a, kcol); }
+extern "C" int rot_cidx_host(int NM, int mu, int n, int l) { return ob::rot_cidx(NM, mu, n, l); }
