@@ -185,7 +185,7 @@ int ob_timer(ob_ctx *ctx, int op, double *ms);
  * the assembly is reported "as achieved FP64 FLOP/s against B200 FP64 peak" */
 int ob_measure_fp64_peak(ob_ctx *ctx, double *tflops);
 /* options: "operator" (0 dense slab | 1 pair form, default | 2 ACA-compressed | 3 rotated-axial form: exact, 12-15x
- * fewer bytes than the pair form, see csrc/ob_rot.cu), "eps_aca" (1e-3), "aca_budget_mb", "assemble_minb", "rot_assembly" (0 | 1: axial-only recursion, pending validation), "keep_matrices", "fused_arnoldi", "matvec_variant",
+ * fewer bytes than the pair form, see csrc/ob_rot.cu), "eps_aca" (1e-3), "aca_budget_mb", "assemble_minb", "rot_assembly" (1, default: axial-only recursion | 0: cross-check path through the full translation block), "rot_share" (1, default: the harmonic assembled second reads phases / small-d matrices from the first one's records), "keep_matrices", "fused_arnoldi", "matvec_variant",
  * "pairs_kb", "pairs_groups" (tuning), "trace_iterations", "reset_timings" */
 int ob_set_option(ob_ctx *ctx, const char *name, double value);
 

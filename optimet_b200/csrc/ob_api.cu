@@ -101,6 +101,9 @@ struct HarmonicState {
   AcaOperator aca;
   // rotated-axial form (ob_rot.cu): one record per local pair i < j
   DevBuf<unsigned char> rot;
+  // records the apply takes the geometry sections (phases, small-d matrices) from: the harmonic's own, or those of the
+  // other harmonic when that one was assembled first for the same pairs (the sections do not depend on k)
+  const unsigned char *rot_geo = nullptr;
   RotLayout rl;
   RotPlan rplan;
   int rplan_world = -1, rplan_rank = -1;
@@ -159,6 +162,7 @@ struct ob_ctx {
   int matvec_variant = 0;
   int operator_mode = 1; // 0 = dense slab (reference layout), 1 = compact pair form (default), 2 = ACA-compressed
   bool keep_matrices = true;
+  bool rot_share = true; // rotated-axial form: the second harmonic reads the geometry sections of the first one's records
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm0 = nullptr, evm1 = nullptr, evt0 = nullptr, evt1 = nullptr;
   // matvec timing without a host sync per apply: a pool of event pairs, read back lazily (flush_matvec_timing)
   std::vector<cudaEvent_t> mv_ev; // 4 per apply: kernel start, kernel end, [trace: after reduce, after Arnoldi step]
@@ -248,6 +252,18 @@ static void allgather_slices(ob_ctx *c, cplx *vec, int blk) {
   }
 }
 
+// The rotated-axial records of harmonic h (0-based) are about to be freed or moved: a harmonic that reads its geometry
+// sections from them must be assembled again.
+static void rot_records_drop(ob_ctx *c, int h) {
+  HarmonicState &H = c->hs[h], &O = c->hs[1 - h];
+  if(H.rot.p && O.rot_geo == H.rot.p) {
+    O.assembled = false;
+    O.rot_geo = nullptr;
+  }
+  H.rot.release();
+  H.rot_geo = nullptr;
+}
+
 static void assemble(ob_ctx *c, int harmonic) {
   check_harmonic(harmonic);
   need(c->nobj > 0, "ob_set_cluster has not been called");
@@ -264,7 +280,7 @@ static void assemble(ob_ctx *c, int harmonic) {
     }
     H.S.release();
     H.aca.release();
-    H.rot.release();
+    rot_records_drop(c, harmonic - 1);
     c->aca_scratch.release();
     if(!H.AB.p && c->spare_AB.p && c->spare_AB.n >= std::max<size_t>(1, pair_storage_elems(H.pplan))) {
       std::swap(H.AB.p, c->spare_AB.p);
@@ -288,14 +304,26 @@ static void assemble(ob_ctx *c, int harmonic) {
       H.rplan_rank = c->rank;
     }
     H.rl = rot_layout(H.nMax);
-    H.rot.alloc(std::max<size_t>(16, (size_t)H.rplan.npairs * H.rl.rec_bytes));
-    launch_assemble_rot(ts, c->xyz.p, H.k, H.rplan.pair_ij, H.rplan.npairs, H.rot.p, H.rl, c->sm_count, c->st);
-    c->launches += 2;
+    const size_t rot_bytes = std::max<size_t>(16, (size_t)H.rplan.npairs * H.rl.rec_bytes);
+    if(rot_bytes > H.rot.n)
+      rot_records_drop(c, harmonic - 1);
+    H.rot.alloc(rot_bytes);
+    // phases and small-d matrices depend on the geometry only: when the other harmonic holds them for the same pairs
+    // (assembled for the current cluster, both resident), this one stores its axial coefficients alone and k_rot_tables
+    // is skipped; the apply fetches the geometry sections from the other harmonic's records
+    HarmonicState &O = c->hs[2 - harmonic];
+    const bool share = c->rot_share && c->keep_matrices && O.assembled && O.mode == 3 && O.rot.p && O.rot_geo == O.rot.p &&
+                       O.nMax == H.nMax && O.rplan.nobj == H.rplan.nobj && O.rplan.I == H.rplan.I &&
+                       O.rplan.npairs == H.rplan.npairs && O.rplan.strip0 == H.rplan.strip0 &&
+                       O.rplan.nstrips == H.rplan.nstrips && O.rplan_world == H.rplan_world && O.rplan_rank == H.rplan_rank;
+    launch_assemble_rot(ts, c->xyz.p, H.k, H.rplan.pair_ij, H.rplan.npairs, H.rot.p, H.rl, c->sm_count, c->st, !share);
+    H.rot_geo = share ? O.rot.p : H.rot.p;
+    c->launches += share ? 1 : 2;
     H.mode = 3;
     H.assembled = true;
     return;
   }
-  H.rot.release();
+  rot_records_drop(c, harmonic - 1);
   if(c->operator_mode == 2) { // Scattering_matrix_ACA_FF / _SH (PreconditionedMatrix.cpp:489-551, 699-759)
     H.S.release();
     aca_build(H.aca, c->aca_scratch, ts, c->xyz.p, c->fac[harmonic == 1 ? 0 : 1].p, H.k, c->nobj, c->first, c->count, c->h_xyz.data(),
@@ -369,11 +397,11 @@ static void matvec(ob_ctx *c, int harmonic, const cplx *x, cplx *y, bool x_stage
     const cplx *T = c->fac[harmonic == 1 ? 0 : 1].p;
     const size_t N = (size_t)c->N(harmonic);
     if(c->world == 1) {
-      launch_matvec_rot(H.rplan, H.rl, H.rot.p, x, T, y, 1, c->st, evm0, evm1);
+      launch_matvec_rot(H.rplan, H.rl, H.rot.p, H.rot_geo, x, T, y, 1, c->st, evm0, evm1);
       c->launches += 2;
     } else {
       need(c->comm != nullptr, "world > 1 but ob_comm_init has not been called");
-      launch_matvec_rot(H.rplan, H.rl, H.rot.p, x, T, H.rplan.acc, 0, c->st, evm0, evm1);
+      launch_matvec_rot(H.rplan, H.rl, H.rot.p, H.rot_geo, x, T, H.rplan.acc, 0, c->st, evm0, evm1);
       OB_NCCL(g_nccl.AllReduce((const void *)H.rplan.acc, (void *)H.rplan.acc, 2 * N, ncclDouble, ncclSum, c->comm,
                                c->st));
       launch_pairs_finalize(x, T, H.rplan.acc, N, y, c->st);
@@ -1208,7 +1236,7 @@ int ob_release_matrix(ob_ctx *ctx, int harmonic) {
   ctx->hs[harmonic - 1].S.release();
   ctx->hs[harmonic - 1].AB.release();
   ctx->hs[harmonic - 1].aca.release();
-  ctx->hs[harmonic - 1].rot.release();
+  rot_records_drop(ctx, harmonic - 1);
   ctx->hs[harmonic - 1].assembled = false;
   OB_END
 }
@@ -1378,7 +1406,7 @@ int ob_matvec_partial(ob_ctx *ctx, int harmonic, const double *x, double *acc) {
     launch_matvec_pairs(H.pplan, H.AB.p, ctx->tmpA.p, T, H.pplan.acc, 0, ctx->st);
     download(ctx, H.pplan.acc, acc, N);
   } else {
-    launch_matvec_rot(H.rplan, H.rl, H.rot.p, ctx->tmpA.p, T, H.rplan.acc, 0, ctx->st);
+    launch_matvec_rot(H.rplan, H.rl, H.rot.p, H.rot_geo, ctx->tmpA.p, T, H.rplan.acc, 0, ctx->st);
     download(ctx, H.rplan.acc, acc, N);
   }
   OB_END
@@ -1521,7 +1549,7 @@ static void release_harmonic(ob_ctx *ctx, int harmonic) {
   }
   H.AB.release();
   H.aca.release();
-  H.rot.release();
+  rot_records_drop(ctx, harmonic - 1);
   H.assembled = false;
 }
 
@@ -1737,6 +1765,9 @@ int ob_set_option(ob_ctx *ctx, const char *name, double value) {
   } else if(n == "assemble_minb") { // tuning: resident CTAs per SM k_assemble_pairs is compiled for (0 auto, 2, 3)
     need(value == 0 || value == 2 || value == 3, "assemble_minb must be 0, 2 or 3");
     assemble_pairs_tuning((int)value);
+  } else if(n == "rot_share") { // 1 (default): one set of phases / small-d matrices serves both harmonics
+    ctx->rot_share = value != 0;
+    ctx->hs[0].assembled = ctx->hs[1].assembled = false;
   } else if(n == "rot_assembly") { // 1 = axial-only recursion (default), 0 = vtac_block at theta = 0 (cross-check path)
     need(value == 0 || value == 1, "rot_assembly must be 0 or 1");
     rot_tuning((int)value, -1, -1);

@@ -126,8 +126,9 @@ void rot_plan_release(RotPlan &p);
 // -1 keeps a setting; assembly: 1 = axial-only recursion (default), 0 = vtac_block-based; rows per block; CTAs per SM
 void rot_tuning(int assembly, int rows, int ctas_per_sm);
 void launch_assemble_rot(VtacTableSet const &ts, const double *xyz, cplx k, const int2 *pair_ij, long npairs,
-                         unsigned char *recs, RotLayout const &L, int sm_count, cudaStream_t st);
-void launch_matvec_rot(RotPlan const &p, RotLayout const &L, const unsigned char *recs, const cplx *x, const cplx *Tdiag,
+                         unsigned char *recs, RotLayout const &L, int sm_count, cudaStream_t st, bool geometry = true);
+// geo: records holding the geometry sections (phases, small-d) of the same pairs; == recs when the harmonic owns them
+void launch_matvec_rot(RotPlan const &p, RotLayout const &L, const unsigned char *recs, const unsigned char *geo, const cplx *x, const cplx *Tdiag,
                        cplx *acc_or_y, int finalize, cudaStream_t st, cudaEvent_t e0 = nullptr, cudaEvent_t e1 = nullptr);
 
 // ---- ob_aca.cu (ACA-compressed operator: U V^T-style low-rank far blocks, dense near blocks) ----

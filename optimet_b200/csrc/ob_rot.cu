@@ -428,6 +428,7 @@ static_assert(rot_ct(OB_MAX_NMAX).nd <= ROT_MAX_UNITS && rot_ct(OB_MAX_NMAX).nc 
 
 struct RotArgs {
   const unsigned char *recs;
+  const unsigned char *geo; // records the phases and small-d sections are fetched from (recs itself, or the other harmonic's)
   const cplx *x;
   const int4 *pinfo;   // per local pair: (i, j, local strip, flags: 1 = last pair of its strip, 2 = last pair of its segment)
   const int *cta_pair; // [grid + 1] local pair ranges
@@ -812,10 +813,22 @@ __global__ void __launch_bounds__(ROT_THREADS, ROT_MIN_CTAS) k_matvec_rot(const 
   uint64_t pol;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
   __syncthreads();
-  if(tid == 0) {
-    r_mbar_expect_tx(&full[0], (uint32_t)L.rec_bytes);
-    r_bulk_g2s(smem, a.recs + (size_t)qbeg * L.rec_bytes, (uint32_t)L.rec_bytes, &full[0], pol);
-  }
+  // one record into a shared-memory slot: a single bulk copy, or three (phases | axial coefficients | small-d) when the
+  // geometry sections live in the other harmonic's records; the mbarrier counts the bytes of all of them
+  auto fetch = [&](int slot, long qq) {
+    unsigned char *dst = smem + (size_t)slot * L.rec_bytes;
+    const size_t o = (size_t)qq * L.rec_bytes;
+    r_mbar_expect_tx(&full[slot], (uint32_t)L.rec_bytes);
+    if(a.geo == a.recs)
+      r_bulk_g2s(dst, a.recs + o, (uint32_t)L.rec_bytes, &full[slot], pol);
+    else {
+      r_bulk_g2s(dst, a.geo + o, (uint32_t)L.offCp, &full[slot], pol);
+      r_bulk_g2s(dst + L.offCp, a.recs + o + L.offCp, (uint32_t)(L.offDs - L.offCp), &full[slot], pol);
+      r_bulk_g2s(dst + L.offDs, a.geo + o + L.offDs, (uint32_t)(L.rec_bytes - L.offDs), &full[slot], pol);
+    }
+  };
+  if(tid == 0)
+    fetch(0, qbeg);
   // x of the pair about to be processed, at m = +pa (TE, TM) and m = -pa (TE, TM): xj = x_j (direction 0), xi = x_i
   cplx xj[4], xi[SPLIT ? 1 : 4]; // SPLIT: xj holds the thread's own direction (x_j or x_i)
   int4 pi = a.pinfo[qbeg], pnext = a.pinfo[qbeg + 1 < qend ? qbeg + 1 : qbeg];
@@ -891,11 +904,8 @@ __global__ void __launch_bounds__(ROT_THREADS, ROT_MIN_CTAS) k_matvec_rot(const 
     }
     __syncthreads(); // B1: T complete; every thread is past P3/P4 of the previous pair -> the other record slot is free
     if(q + 1 < qend) {
-      if(tid == 0) {
-        r_mbar_expect_tx(&full[cur ^ 1], (uint32_t)L.rec_bytes);
-        r_bulk_g2s(smem + (size_t)(cur ^ 1) * L.rec_bytes, a.recs + (size_t)(q + 1) * L.rec_bytes, (uint32_t)L.rec_bytes,
-                   &full[cur ^ 1], pol);
-      }
+      if(tid == 0)
+        fetch(cur ^ 1, q + 1);
       if(p0live) { // next pair's x into registers (L2 hits), consumed by its P0; its (i, j) was fetched a pair ago
         if(SPLIT) {
           if(pdir)
@@ -1139,7 +1149,7 @@ void rot_tuning(int assembly, int rows, int ctas_per_sm) {
     g_rot_ctas = ctas_per_sm;
 }
 void launch_assemble_rot(VtacTableSet const &ts, const double *xyz, cplx k, const int2 *pair_ij, long npairs,
-                         unsigned char *recs, RotLayout const &L, int sm_count, cudaStream_t st) {
+                         unsigned char *recs, RotLayout const &L, int sm_count, cudaStream_t st, bool geometry) {
   if(npairs <= 0)
     return;
   RotDTable const &dt = rot_dtable(L.NM);
@@ -1172,6 +1182,8 @@ void launch_assemble_rot(VtacTableSet const &ts, const double *xyz, cplx k, cons
     k_assemble_axial<<<(unsigned)npairs, OB_VTAC_THREADS, ts.smem, st>>>(ts.tb, xyz, k, pair_ij, recs, L);
   }
   OB_CUDA(cudaGetLastError());
+  if(!geometry) // the apply reads phases and small-d matrices from the other harmonic's records
+    return;
   const long tctas = std::min<long>(npairs, (long)sm_count * 16);
   k_rot_tables<<<(unsigned)tctas, ROT_TAB_THREADS, 0, st>>>(xyz, pair_ij, npairs, recs, L, dt.coef, dt.seed);
   OB_CUDA(cudaGetLastError());
@@ -1187,7 +1199,7 @@ template <int NM> static RotKernel rot_kernel_for(int nMax) {
     throw Error("rotated-axial operator: nMax out of range");
 }
 
-void launch_matvec_rot(RotPlan const &p, RotLayout const &L, const unsigned char *recs, const cplx *x, const cplx *Tdiag,
+void launch_matvec_rot(RotPlan const &p, RotLayout const &L, const unsigned char *recs, const unsigned char *geo, const cplx *x, const cplx *Tdiag,
                        cplx *acc_or_y, int finalize, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1) {
   if(e0)
     cudaEventRecord(e0, st);
@@ -1198,6 +1210,7 @@ void launch_matvec_rot(RotPlan const &p, RotLayout const &L, const unsigned char
                                  cudaSharedmemCarveoutMaxShared));
     RotArgs a;
     a.recs = recs;
+    a.geo = geo ? geo : recs;
     a.x = x;
     a.pinfo = p.pinfo;
     a.cta_pair = p.cta_pair;

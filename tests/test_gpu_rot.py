@@ -124,3 +124,40 @@ def test_rot_plan_geometry(rot_ctx, rows, ctas):
     finally:
         rot_ctx.set_option("rot_rows", 0)
         rot_ctx.set_option("rot_ctas_per_sm", 0)
+
+
+@pytest.mark.parametrize("name", ["random9_n10", "random23_n8", "lossy_bg"])
+def test_rot_geometry_sections_shared_between_harmonics(rot_ctx, name):
+    """Phases and small-d matrices do not depend on k: the harmonic assembled second fetches them from the records of
+    the first ("rot_share" = 1, default) instead of computing and storing its own copy.  Same bits either way, in either
+    assembly order; releasing the records the sections live in sends the other harmonic back to assembly."""
+    spec = CLUSTERS[name]()
+    orc = U.oracle_case(spec)
+    U.configure_ctx(rot_ctx, spec, orc)
+    rng = np.random.RandomState(11)
+    N = orc.matrix(1).shape[1]
+    x = rng.standard_normal(N) + 1j * rng.standard_normal(N)
+    ys = {}
+    try:
+        for share, order in ((0, (1, 2)), (1, (1, 2)), (1, (2, 1))):
+            rot_ctx.set_option("rot_share", share)   # marks both harmonics unassembled
+            for h in order:
+                rot_ctx.assemble(h)
+            ys[(share, order)] = [rot_ctx.matvec(h, x) for h in (1, 2)]
+        for key in ((1, (1, 2)), (1, (2, 1))):
+            for h in (0, 1):
+                assert np.array_equal(ys[key][h], ys[(0, (1, 2))][h]), (key, h)
+        for h in (1, 2):
+            assert U.relerr(ys[(1, (1, 2))][h - 1], O.matvec(orc.matrix(h), x)) < 1e-12
+        # harmonic 1 reads its geometry sections from harmonic 2's records (last order above): drop them
+        rot_ctx.release_matrix(2)
+        with pytest.raises(RuntimeError, match="not assembled"):
+            rot_ctx.matvec(1, x)
+        rot_ctx.assemble(1)
+        assert np.array_equal(rot_ctx.matvec(1, x), ys[(0, (1, 2))][0])
+        # an owner that is assembled again (same cluster) keeps serving the harmonic that shares from it
+        rot_ctx.assemble(2)
+        rot_ctx.assemble(1)
+        assert np.array_equal(rot_ctx.matvec(2, x), ys[(0, (1, 2))][1])
+    finally:
+        rot_ctx.set_option("rot_share", 1)
