@@ -370,21 +370,32 @@ k_rot_tables(const double *__restrict__ xyz, const int2 *__restrict__ pair_ij, l
 #ifndef ROT_WARPS
 #define ROT_WARPS 4
 #endif
-#ifndef ROT_MIN_CTAS
-#define ROT_MIN_CTAS 3 // resident CTAs per SM the kernel is compiled for (168 registers: the natural count is 176 at nMax 10)
+// ROT_SINGLE_SLOT = 1: ONE record slot per CTA, refilled section by section as the phases release it (small-d part and
+// the next phases after P1, axial part after P2): 21 KB less shared memory per CTA and loop-invariant section pointers
+// (3.90 -> 3.78 ms per C5 apply at three CTAs per SM).  0: two whole-record slots.
+// ROT_MIN_CTAS: resident CTAs per SM the kernel is compiled for at nMax <= 10.  With the single slot and three rows per
+// block a FOURTH CTA fits (55 KB, 128 registers, 24 bytes of spills): measured 3.88 ms, slower than three CTAs at 168
+// registers (16 % more instructions under the register cap; the shared-memory pipe is already 60 % busy).
+#ifndef ROT_SINGLE_SLOT
+#define ROT_SINGLE_SLOT 1
 #endif
+#ifndef ROT_MIN_CTAS
+#define ROT_MIN_CTAS 3
+#endif
+__host__ __device__ constexpr inline int rot_min_ctas(int NM) { return NM <= 10 ? ROT_MIN_CTAS : (ROT_MIN_CTAS < 3 ? ROT_MIN_CTAS : 3); }
 #define ROT_THREADS (32 * ROT_WARPS)
 #define ROT_MAX_UNITS 32
 // Static work lists, evaluated at COMPILE TIME per nMax (the kernel is a template on nMax: every offset, stride, K-step
 // count and tail condition below is an immediate; the first DMMA version took them from run-time tables and spent
-// 33 instructions per DMMA on index arithmetic).  d-phase units: degree n, first row m0 of an 8-row tile, the s and the
-// a class together.  P2 units: order a, first row of an 8-row tile, the A + B and the A - B channels together.  Units
-// go to the warps by longest-processing-time (cost = DMMAs).
+// 33 instructions per DMMA on index arithmetic).  d-phase units: degree n, the s and the a class together, every 8-row tile
+// (the tiles of a unit share its B fragments: one load per K step).  P2 units: order a, every 8-row tile, the A + B
+// and the A - B channels together.  Units go to the warps by longest-processing-time (cost = DMMAs).
 struct RotCT {
   int nd, nc;
-  int dn[ROT_MAX_UNITS], dm[ROT_MAX_UNITS], dw[ROT_MAX_UNITS], dc[ROT_MAX_UNITS];
-  int ca[ROT_MAX_UNITS], cm[ROT_MAX_UNITS], cw[ROT_MAX_UNITS], cc[ROT_MAX_UNITS];
+  int dn[ROT_MAX_UNITS], dw[ROT_MAX_UNITS], dc[ROT_MAX_UNITS];
+  int ca[ROT_MAX_UNITS], cw[ROT_MAX_UNITS], cc[ROT_MAX_UNITS];
 };
+__host__ __device__ constexpr inline int rot_tiles(int rows) { return (rows + 7) / 8; } // row tiles of 8 (at most two)
 __host__ __device__ constexpr inline void rot_ct_assign(int count, const int *cost, int *owner) {
   bool done[ROT_MAX_UNITS] = {};
   int load[ROT_WARPS] = {};
@@ -404,26 +415,22 @@ __host__ __device__ constexpr inline void rot_ct_assign(int count, const int *co
 }
 __host__ __device__ constexpr inline RotCT rot_ct(int NM) {
   RotCT T{};
-  for(int n = 1; n <= NM; ++n)
-    for(int m0 = 0; m0 <= n; m0 += 8) {
-      T.dn[T.nd] = n;
-      T.dm[T.nd] = m0;
-      T.dc[T.nd] = (n + 1 + 3) / 4 + (n + 3) / 4;
-      ++T.nd;
-    }
-  for(int a = 0; a <= NM; ++a) {
+  for(int n = 1; n <= NM; ++n) { // one d-phase unit per degree: all row tiles share the B fragments
+    T.dn[T.nd] = n;
+    T.dc[T.nd] = rot_tiles(n + 1) * ((n + 1 + 3) / 4 + (n + 3) / 4);
+    ++T.nd;
+  }
+  for(int a = 0; a <= NM; ++a) { // one P2 unit per order
     const int w = NM - rot_n0(a) + 1;
-    for(int m0 = 0; m0 < w; m0 += 8) {
-      T.ca[T.nc] = a;
-      T.cm[T.nc] = m0;
-      T.cc[T.nc] = ((w + 3) / 4) * (a == 0 ? 2 : 4);
-      ++T.nc;
-    }
+    T.ca[T.nc] = a;
+    T.cc[T.nc] = rot_tiles(w) * ((w + 3) / 4) * (a == 0 ? 2 : 4);
+    ++T.nc;
   }
   rot_ct_assign(T.nd, T.dc, T.dw);
   rot_ct_assign(T.nc, T.cc, T.cw);
   return T;
 }
+static_assert(OB_MAX_NMAX + 1 <= 16, "the unit code handles at most two row tiles");
 static_assert(rot_ct(OB_MAX_NMAX).nd <= ROT_MAX_UNITS && rot_ct(OB_MAX_NMAX).nc <= ROT_MAX_UNITS, "unit tables too small");
 
 struct RotArgs {
@@ -483,10 +490,11 @@ __host__ __device__ constexpr inline int rot_plane_doubles(int LF) { return 4 * 
 __host__ __device__ constexpr inline int rot_acc_tm(int nH) { return nH + ((2 - nH % 8) + 8) % 8; }
 __host__ __device__ constexpr inline int rot_acc_row(int nH) { return (rot_acc_tm(nH) + nH + 7) / 8 * 8; }
 __host__ __device__ constexpr inline int rot_acc_units(int nH, int I) { return (I + 1) * rot_acc_row(nH) + 4; }
-// dynamic shared memory: record[2] | bufX[2 planes] | bufY[2 planes] | acc[I + 1][2n] (rows of the block, then the
-// column sums of the strip) | mbarrier[2]
+// dynamic shared memory: record[2] (single slot: record | second phase slot) | bufX[2 planes] | bufY[2 planes] |
+// acc[I + 1][2n] (rows of the block, then the column sums of the strip) | mbarrier[2]
+static size_t rot_slot_bytes(RotLayout const &L) { return ROT_SINGLE_SLOT ? L.rec_bytes + L.offCp : 2 * L.rec_bytes; }
 static size_t rot_smem_bytes(RotLayout const &L, int I) {
-  return 2 * L.rec_bytes + (size_t)4 * rot_plane_doubles(L.LF) * sizeof(double) + (size_t)rot_acc_units(L.n, I) * sizeof(cplx) +
+  return rot_slot_bytes(L) + (size_t)4 * rot_plane_doubles(L.LF) * sizeof(double) + (size_t)rot_acc_units(L.n, I) * sizeof(cplx) +
          2 * sizeof(uint64_t);
 }
 
@@ -507,21 +515,25 @@ struct RotLane {
 // accumulation chain of KS K-steps over K columns: straight-line loads, then DMMAs; the A fragments of a row tile are
 // consecutive runs in the record (fragment order, ob_rot_axial.cuh): pa = first fragment + 4 fr + fc, stepA = 4 Rt doubles
 // per step; a last step of Kv < 4 valid K entries is compacted to row stride Kv (pt = its address for this lane) and
-// the lane's A entry is zeroed past the K range (compile-time known); B advances 16 doubles per step
+// the lane's A entry is zeroed past the K range (compile-time known).  The B fragments bv[KS] are loaded once per unit
+// (rot_load_b: 16 doubles per step) and serve every row tile of the unit.
 // KEEP: 0 = load the A fragments, 1 = load them and keep them in `keep` (registers), 2 = take them from `keep` (the
 // small-d fragments of P1 serve P3 again: D[a', a] = (-1)^(a' - a) D[a, a'] makes both phases read the same entries)
+template <int KS> __device__ __forceinline__ void rot_load_b(double *bv, const double *__restrict__ pb) {
+#pragma unroll
+  for(int s = 0; s < KS; ++s)
+    bv[s] = pb[16 * s];
+}
 template <int KS, int K, int KEEP = 0>
 __device__ __forceinline__ void rot_chain(double (&acc)[2], const double *__restrict__ pa, int stepA,
-                                          const double *__restrict__ pt, const double *__restrict__ pb, int fc,
-                                          double *keep = nullptr) {
-  double av[KS], bv[KS];
+                                          const double *__restrict__ pt, const double *bv, int fc, double *keep = nullptr) {
+  double av[KS];
 #pragma unroll
   for(int s = 0; s < KS; ++s) {
     if(KEEP == 2)
       av[s] = keep[s];
     else
       av[s] = (4 * KS > K && s == KS - 1) ? pt[0] : pa[s * stepA];
-    bv[s] = pb[16 * s];
   }
   if(KEEP != 2 && 4 * KS > K)
     av[KS - 1] = 4 * (KS - 1) + fc < K ? av[KS - 1] : 0.0;
@@ -537,14 +549,13 @@ __device__ __forceinline__ void rot_chain(double (&acc)[2], const double *__rest
 // two chains on the same B fragments: real and imaginary plane of one complex matrix (planes dI doubles apart)
 template <int KS, int K>
 __device__ __forceinline__ void rot_chain2(double (&accR)[2], double (&accI)[2], const double *__restrict__ pa, int dI,
-                                           int stepA, const double *__restrict__ pt, const double *__restrict__ pb, int fc) {
-  double ar[KS], ai[KS], bv[KS];
+                                           int stepA, const double *__restrict__ pt, const double *bv, int fc) {
+  double ar[KS], ai[KS];
 #pragma unroll
   for(int s = 0; s < KS; ++s) {
     const double *q = (4 * KS > K && s == KS - 1) ? pt : pa + s * stepA;
     ar[s] = q[0];
     ai[s] = q[dI];
-    bv[s] = pb[16 * s];
   }
   if(4 * KS > K) {
     const bool in = 4 * (KS - 1) + fc < K;
@@ -558,21 +569,25 @@ __device__ __forceinline__ void rot_chain2(double (&accR)[2], double (&accI)[2],
   }
 }
 
-// d-phase unit U of nMax NM (P1 and P3): rows a = m0 .. m0 + 7 of degree n, both classes.
-//   accS[(a, col)] = sum_{a' = 0..n} Ds[a' (n + 1) + a] v_s[a'][col],  accA[(a, col)] = sum_{a' = 1..n} Da[(a' - 1) n + (a - 1)] v_a[a'][col]
-// register slots of the kept A fragments: units of the same warp before U (compile time)
+// d-phase unit U of nMax NM (P1 and P3): degree n, both classes, every row tile (rows a = 8 TILE .. 8 TILE + 7).
+//   accS[(a, col)] = sum_{a' = 0..n} Ds[(a', a)] v_s[a'][col],  accA[(a, col)] = sum_{a' = 1..n} Da[(a', a)] v_a[a'][col]
+// register slots of the kept A fragments: units of the same warp before U (compile time), tile by tile
 #ifndef ROT_KEEP_S
 #define ROT_KEEP_S 1 // keep the s-class small-d fragments of P1 in registers for P3
 #endif
 #ifndef ROT_KEEP_A
 #define ROT_KEEP_A 1 // the a-class ones too (168 registers with three CTAs per SM: no spills up to nMax 13)
 #endif
+static_assert(!ROT_SINGLE_SLOT || (ROT_KEEP_S && ROT_KEEP_A), "the single record slot is refilled during P3: P3 must not read the small-d part");
+__host__ __device__ constexpr inline int rot_keep_per_tile(int n) {
+  return (ROT_KEEP_S ? (n + 1 + 3) / 4 : 0) + (ROT_KEEP_A ? (n + 3) / 4 : 0);
+}
 __host__ __device__ constexpr inline int rot_keep_slots(int NM, int W, int U) { // fragments kept by W's units before U
   const RotCT T = rot_ct(NM);
   int k = 0;
   for(int u = 0; u < U; ++u)
     if(T.dw[u] == W)
-      k += (ROT_KEEP_S ? (T.dn[u] + 1 + 3) / 4 : 0) + (ROT_KEEP_A ? (T.dn[u] + 3) / 4 : 0);
+      k += rot_tiles(T.dn[u] + 1) * rot_keep_per_tile(T.dn[u]);
   return k;
 }
 __host__ __device__ constexpr inline int rot_keep_total(int NM) {
@@ -584,34 +599,34 @@ __host__ __device__ constexpr inline int rot_keep_total(int NM) {
   }
   return best;
 }
-// PHASE 1: P1 (fragments loaded and kept), 3: P3 (kept fragments reused)
-template <int NM, int W, int U, int PHASE>
-__device__ __forceinline__ void rot_dchains(RotLane const &c, double (&accS)[2], double (&accA)[2], double *keep) {
+// one row tile of a d-phase unit.  PHASE 1: P1 (fragments loaded and kept), 3: P3 (kept fragments reused); bS / bA: the
+// unit's B fragments (class vectors of degree n), already in registers
+template <int NM, int W, int U, int PHASE, int TILE>
+__device__ __forceinline__ void rot_dchains(RotLane const &c, double (&accS)[2], double (&accA)[2], double *keep,
+                                            const double *bS, const double *bA) {
   constexpr RotCT T = rot_ct(NM);
-  constexpr int n = T.dn[U], m0 = T.dm[U], n1 = n + 1, slot = rot_keep_slots(NM, W, U);
+  constexpr int n = T.dn[U], m0 = 8 * TILE, n1 = n + 1, slot = rot_keep_slots(NM, W, U) + TILE * rot_keep_per_tile(n);
   constexpr int KS = ROT_KEEP_S ? (PHASE == 1 ? 1 : 2) : 0, KA = ROT_KEEP_A ? (PHASE == 1 ? 1 : 2) : 0;
   accS[0] = accS[1] = accA[0] = accA[1] = 0.0;
   // s class: rows a = m0 .. of the (n + 1) x (n + 1) matrix, Rt valid rows in this tile
   constexpr int RtS = n1 - m0 < 8 ? n1 - m0 : 8, ksS = (n1 + 3) / 4, kvS = n1 - 4 * (ksS - 1);
   const double *paS = c.Ds + rot_offDs(n) + m0 * n1;
-  rot_chain<ksS, n1, KS>(accS, paS, 4 * RtS, paS + 4 * RtS * (ksS - 1) - (4 - kvS) * c.fr, c.vb + 4 * rot_offF(n) + 4 * c.fc, c.fc,
-                         keep + slot);
+  rot_chain<ksS, n1, KS>(accS, paS, 4 * RtS, paS + 4 * RtS * (ksS - 1) - (4 - kvS) * c.fr, bS, c.fc, keep + slot);
   // a class: rows a = max(m0, 1) .. of the n x n matrix (tile 0: a phantom row 0 in front of the seven rows a = 1 .. 7)
   constexpr int firstA = m0 ? m0 : 1, lastA = m0 + 7 < n ? m0 + 7 : n, RtA = lastA - firstA + 1, ksA = (n + 3) / 4,
                 kvA = n - 4 * (ksA - 1), radj = m0 ? 0 : -1;
   const double *paA = c.Da + rot_offDa(n) + (firstA - 1) * n + 4 * radj;
-  rot_chain<ksA, n, KA>(accA, paA, 4 * RtA, paA + 4 * RtA * (ksA - 1) - (4 - kvA) * c.fr - (4 - kvA) * radj,
-                        c.vb + 4 * (rot_offF(n) + n + 2) + 4 * c.fc, c.fc, keep + slot + (ROT_KEEP_S ? ksS : 0));
+  rot_chain<ksA, n, KA>(accA, paA, 4 * RtA, paA + 4 * RtA * (ksA - 1) - (4 - kvA) * c.fr - (4 - kvA) * radj, bA, c.fc,
+                        keep + slot + (ROT_KEEP_S ? ksS : 0));
 }
 
-// P1 unit: u = D^T t, channel sums p+- = TE_s +- TM_a (TE lanes), r+- = TM_s +- TE_a (TM lanes)
-template <int NM, int W, int U> __device__ __forceinline__ void rot_p1_unit(RotLane const &c, double *keep) {
+// P1: u = D^T t, channel sums p+- = TE_s +- TM_a (TE lanes), r+- = TM_s +- TE_a (TM lanes)
+template <int NM, int W, int U, int TILE>
+__device__ __forceinline__ void rot_p1_tile(RotLane const &c, double *keep, const double *bS, const double *bA) {
   constexpr RotCT T = rot_ct(NM);
-  constexpr int n = T.dn[U], m0 = T.dm[U], SS = rot_plane_doubles(NM * (NM + 3));
-  if constexpr(T.dw[U] != W)
-    return;
+  constexpr int n = T.dn[U], m0 = 8 * TILE, SS = rot_plane_doubles(NM * (NM + 3));
   double aS[2], aA[2];
-  rot_dchains<NM, W, U, 1>(c, aS, aA, keep);
+  rot_dchains<NM, W, U, 1, TILE>(c, aS, aA, keep, bS, bA);
   const int aa = m0 + c.fr;
   if(m0 == 0 && c.fr == 0) // the a class has no a = 0 row (its fragment row was read from outside the block)
     aA[0] = aA[1] = 0.0;
@@ -625,20 +640,31 @@ template <int NM, int W, int U> __device__ __forceinline__ void rot_p1_unit(RotL
     *(cplx *)(P + SS) = mk(aS[0] - ox, aS[1] - oy);
   }
 }
-
-// P2 unit: q = C p for order a, rows n = n0 + m0 .. + 7 (Re and Im of C as two real DMMAs on one B fragment), back to
-// the class vectors: v_s = (-1)^a (q+ + q-) / 2, v_a = (-1)^a (q+ - q-) / 2
-template <int NM, int W, int U> __device__ __forceinline__ void rot_p2_unit(RotLane const &c, double *) {
+template <int NM, int W, int U> __device__ __forceinline__ void rot_p1_unit(RotLane const &c, double *keep) {
   constexpr RotCT T = rot_ct(NM);
-  constexpr int a = T.ca[U], m0 = T.cm[U], n0 = rot_n0(a), w = NM - n0 + 1, ks = (w + 3) / 4;
-  constexpr int XC = rot_offX(NM, NM + 1), XM = XC - NM * NM, SS = rot_plane_doubles(NM * (NM + 3));
-  if constexpr(T.cw[U] != W)
+  constexpr int n = T.dn[U];
+  if constexpr(T.dw[U] != W)
     return;
+  double bS[(n + 4) / 4], bA[(n + 3) / 4]; // class vectors of degree n: one load per K step for all row tiles
+  rot_load_b<(n + 4) / 4>(bS, c.vb + 4 * rot_offF(n) + 4 * c.fc);
+  rot_load_b<(n + 3) / 4>(bA, c.vb + 4 * (rot_offF(n) + n + 2) + 4 * c.fc);
+  rot_p1_tile<NM, W, U, 0>(c, keep, bS, bA);
+  if constexpr(rot_tiles(n + 1) > 1)
+    rot_p1_tile<NM, W, U, 1>(c, keep, bS, bA);
+}
+
+// P2: q = C p for order a, rows n = n0 + 8 TILE .. + 7 (Re and Im of C as two real DMMAs on one B fragment), back to
+// the class vectors: v_s = (-1)^a (q+ + q-) / 2, v_a = (-1)^a (q+ - q-) / 2.  bP / bM: channel vectors of the A + B and
+// the A - B channel of order a, in registers for every row tile
+template <int NM, int W, int U, int TILE>
+__device__ __forceinline__ void rot_p2_tile(RotLane const &c, const double *bP, const double *bM) {
+  constexpr RotCT T = rot_ct(NM);
+  constexpr int a = T.ca[U], m0 = 8 * TILE, n0 = rot_n0(a), w = NM - n0 + 1, ks = (w + 3) / 4;
+  constexpr int XC = rot_offX(NM, NM + 1), XM = XC - NM * NM;
   double apr[2] = {0, 0}, api[2] = {0, 0};
-  const double *pb = c.pb + 4 * rot_offP(NM, a) + 4 * c.fc;
   constexpr int Rt = w - m0 < 8 ? w - m0 : 8, kv = w - 4 * (ks - 1); // fragment order: tile m0 / 8 of the w x w block of order a
   const int tofs = rot_offX(NM, a) + m0 * w + 4 * Rt * (ks - 1) - (4 - kv) * c.fr;
-  rot_chain2<ks, w>(apr, api, c.Cp + rot_offX(NM, a) + m0 * w, XC, 4 * Rt, c.Cp + tofs, pb, c.fc);
+  rot_chain2<ks, w>(apr, api, c.Cp + rot_offX(NM, a) + m0 * w, XC, 4 * Rt, c.Cp + tofs, bP, c.fc);
   // complex products: (Re C p_re - Im C p_im, Re C p_im + Im C p_re); lane = (row n, channel fc = direction * 2 + family)
   const double qpx = apr[0] - api[1], qpy = apr[1] + api[0];
   const int row = m0 + c.fr, n = n0 + row;
@@ -648,7 +674,7 @@ template <int NM, int W, int U> __device__ __forceinline__ void rot_p2_unit(RotL
       *(cplx *)V = mk(qpx, qpy);
   } else {
     double amr[2] = {0, 0}, ami[2] = {0, 0};
-    rot_chain2<ks, w>(amr, ami, c.Cm + rot_offX(NM, a) + m0 * w, XM, 4 * Rt, c.Cm + tofs, pb + SS, c.fc);
+    rot_chain2<ks, w>(amr, ami, c.Cm + rot_offX(NM, a) + m0 * w, XM, 4 * Rt, c.Cm + tofs, bM, c.fc);
     const double qmx = amr[0] - ami[1], qmy = amr[1] + ami[0];
     constexpr double h = (a & 1) ? -0.5 : 0.5; // (-1)^a of the transposed small-d read, and the 1/2 of the channel split
     if(m0 + 7 < w || row < w) {
@@ -657,15 +683,28 @@ template <int NM, int W, int U> __device__ __forceinline__ void rot_p2_unit(RotL
     }
   }
 }
-
-// P3 + P4 unit: w = D v, flip basis -> m, conjugate phase, parity signs of direction 1, accumulate (owner lanes)
-template <int NM, int W, int U> __device__ __forceinline__ void rot_p3_unit(RotLane const &c, double *keep) {
+template <int NM, int W, int U> __device__ __forceinline__ void rot_p2_unit(RotLane const &c, double *) {
   constexpr RotCT T = rot_ct(NM);
-  constexpr int n = T.dn[U], m0 = T.dm[U];
-  if constexpr(T.dw[U] != W)
+  constexpr int a = T.ca[U], n0 = rot_n0(a), w = NM - n0 + 1, ks = (w + 3) / 4, SS = rot_plane_doubles(NM * (NM + 3));
+  if constexpr(T.cw[U] != W)
     return;
+  double bP[ks], bM[ks];
+  const double *pb = c.pb + 4 * rot_offP(NM, a) + 4 * c.fc;
+  rot_load_b<ks>(bP, pb);
+  if constexpr(a > 0)
+    rot_load_b<ks>(bM, pb + SS);
+  rot_p2_tile<NM, W, U, 0>(c, bP, bM);
+  if constexpr(rot_tiles(w) > 1)
+    rot_p2_tile<NM, W, U, 1>(c, bP, bM);
+}
+
+// P3 + P4: w = D v, flip basis -> m, conjugate phase, parity signs of direction 1, accumulate (owner lanes)
+template <int NM, int W, int U, int TILE>
+__device__ __forceinline__ void rot_p3_tile(RotLane const &c, double *keep, const double *bS, const double *bA) {
+  constexpr RotCT T = rot_ct(NM);
+  constexpr int n = T.dn[U], m0 = 8 * TILE;
   double aS[2], aA[2];
-  rot_dchains<NM, W, U, 3>(c, aS, aA, keep);
+  rot_dchains<NM, W, U, 3, TILE>(c, aS, aA, keep, bS, bA);
   const int ap = m0 + c.fr;
   if(m0 + 7 > n && ap > n)
     return;
@@ -683,6 +722,18 @@ template <int NM, int W, int U> __device__ __forceinline__ void rot_p3_unit(RotL
   const cplx o1 = d[0], o2 = d[2 * ap];
   d[0] = mk(o1.x + (php.x * sx + php.y * sy), o1.y + (php.x * sy - php.y * sx));
   d[2 * ap] = mk(o2.x + (phm.x * dx + phm.y * dy), o2.y + (phm.x * dy - phm.y * dx));
+}
+template <int NM, int W, int U> __device__ __forceinline__ void rot_p3_unit(RotLane const &c, double *keep) {
+  constexpr RotCT T = rot_ct(NM);
+  constexpr int n = T.dn[U];
+  if constexpr(T.dw[U] != W)
+    return;
+  double bS[(n + 4) / 4], bA[(n + 3) / 4];
+  rot_load_b<(n + 4) / 4>(bS, c.vb + 4 * rot_offF(n) + 4 * c.fc);
+  rot_load_b<(n + 3) / 4>(bA, c.vb + 4 * (rot_offF(n) + n + 2) + 4 * c.fc);
+  rot_p3_tile<NM, W, U, 0>(c, keep, bS, bA);
+  if constexpr(rot_tiles(n + 1) > 1)
+    rot_p3_tile<NM, W, U, 1>(c, keep, bS, bA);
 }
 
 // The units of ONE warp, selected at compile time, inlined into one straight-line block: the loads and DMMAs of a warp's
@@ -726,7 +777,7 @@ template <int NM, int W, int... U> __device__ __forceinline__ void rot_p3_warp(R
 static_assert(ROT_WARPS == 4 || ROT_WARPS == 8, "ROT_PER_WARP enumerates up to eight warps (no unit is owned by a warp >= ROT_WARPS)");
 
 template <int NM>
-__global__ void __launch_bounds__(ROT_THREADS, ROT_MIN_CTAS) k_matvec_rot(const __grid_constant__ RotArgs a) {
+__global__ void __launch_bounds__(ROT_THREADS, rot_min_ctas(NM)) k_matvec_rot(const __grid_constant__ RotArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr RotCT T = rot_ct(NM);
   constexpr int nH = NM * (NM + 2), n2 = 2 * nH, LF = NM * (NM + 3), NH = LF / 2;
@@ -734,7 +785,8 @@ __global__ void __launch_bounds__(ROT_THREADS, ROT_MIN_CTAS) k_matvec_rot(const 
   constexpr int PP = PS / 2;                // channel buffers: plane stride (the A+B and A-B halves are PS apart)
   const RotLayout L = a.L;
   const int I = a.I;
-  double *bufX = (double *)(smem + 2 * L.rec_bytes);
+  const uint32_t slot_bytes = ROT_SINGLE_SLOT ? (uint32_t)(L.rec_bytes + L.offCp) : (uint32_t)(2 * L.rec_bytes);
+  double *bufX = (double *)(smem + slot_bytes);
   double *bufY = bufX + 2 * PS;
   constexpr int NHP = rot_acc_tm(nH), RS = rot_acc_row(nH);
   cplx *acc = (cplx *)(bufY + 2 * PS); // column sums of the strip, then (4 units later) the I rows of the block
@@ -750,7 +802,7 @@ __global__ void __launch_bounds__(ROT_THREADS, ROT_MIN_CTAS) k_matvec_rot(const 
   }
   { // everything the fragment loads may touch starts finite
     double *z = (double *)smem;
-    const int nz = (int)((2 * L.rec_bytes) / sizeof(double)) + 4 * PS + 2 * rot_acc_units(nH, I);
+    const int nz = (int)(slot_bytes / sizeof(double)) + 4 * PS + 2 * rot_acc_units(nH, I);
     for(int e = tid; e < nz; e += ROT_THREADS)
       z[e] = 0.0;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy writes before the bulk copies into the slots
@@ -815,6 +867,25 @@ __global__ void __launch_bounds__(ROT_THREADS, ROT_MIN_CTAS) k_matvec_rot(const 
   __syncthreads();
   // one record into a shared-memory slot: a single bulk copy, or three (phases | axial coefficients | small-d) when the
   // geometry sections live in the other harmonic's records; the mbarrier counts the bytes of all of them
+#if ROT_SINGLE_SLOT
+  // single slot: full[0] counts the small-d part + the phases of a pair (phase slots alternate: the record's own at
+  // even local pair numbers, the one behind the record at odd ones), full[1] the axial part; each completes once per pair
+  const uint32_t bytesD = (uint32_t)(L.rec_bytes - L.offDs), bytesC = (uint32_t)(L.offDs - L.offCp), bytesP = (uint32_t)L.offCp;
+  auto fetch_geo = [&](long qq, int kpar) { // small-d sections + phases of pair qq (kpar = parity of its local number)
+    const size_t o = (size_t)qq * L.rec_bytes;
+    r_mbar_expect_tx(&full[0], bytesD + bytesP);
+    r_bulk_g2s(smem + L.offDs, a.geo + o + L.offDs, bytesD, &full[0], pol);
+    r_bulk_g2s(smem + (kpar ? L.rec_bytes : 0), a.geo + o, bytesP, &full[0], pol);
+  };
+  auto fetch_ax = [&](long qq) { // axial coefficients of pair qq
+    r_mbar_expect_tx(&full[1], bytesC);
+    r_bulk_g2s(smem + L.offCp, a.recs + (size_t)qq * L.rec_bytes + L.offCp, bytesC, &full[1], pol);
+  };
+  if(tid == 0) {
+    fetch_geo(qbeg, 0);
+    fetch_ax(qbeg);
+  }
+#else
   auto fetch = [&](int slot, long qq) {
     unsigned char *dst = smem + (size_t)slot * L.rec_bytes;
     const size_t o = (size_t)qq * L.rec_bytes;
@@ -829,6 +900,7 @@ __global__ void __launch_bounds__(ROT_THREADS, ROT_MIN_CTAS) k_matvec_rot(const 
   };
   if(tid == 0)
     fetch(0, qbeg);
+#endif
   // x of the pair about to be processed, at m = +pa (TE, TM) and m = -pa (TE, TM): xj = x_j (direction 0), xi = x_i
   cplx xj[4], xi[SPLIT ? 1 : 4]; // SPLIT: xj holds the thread's own direction (x_j or x_i)
   int4 pi = a.pinfo[qbeg], pnext = a.pinfo[qbeg + 1 < qend ? qbeg + 1 : qbeg];
@@ -852,8 +924,13 @@ __global__ void __launch_bounds__(ROT_THREADS, ROT_MIN_CTAS) k_matvec_rot(const 
   double *bufA = bufX, *bufB = bufY; // class vectors T / V in bufA, channels in bufB; roles swap every pair
   for(int q = qbeg; q < qend; ++q) {
     const int cur = (q - qbeg) & 1;
+#if ROT_SINGLE_SLOT
+    const unsigned char *rec = smem;
+    const cplx *s_ph = (const cplx *)(smem + (cur ? L.rec_bytes : 0));
+#else
     const unsigned char *rec = smem + (size_t)cur * L.rec_bytes;
     const cplx *s_ph = (const cplx *)rec;
+#endif
     c.ph = s_ph + NM;
     c.Cp = (const double *)(rec + L.offCp) + lane;
     c.Cm = (const double *)(rec + L.offCm) - NM * NM + lane;
@@ -864,7 +941,11 @@ __global__ void __launch_bounds__(ROT_THREADS, ROT_MIN_CTAS) k_matvec_rot(const 
     c.pst = bufB + sofsP;
     c.vst = bufA + sofs;
     c.dst = acc + (c.dir1 ? 0 : RS + 4 + (pi.x % I) * RS) + c.cpol * NHP; // direction 1: column sums of particle j
+#if ROT_SINGLE_SLOT
+    r_mbar_wait(&full[0], (uint32_t)cur); // small-d part and phases of this pair have landed
+#else
     r_mbar_wait(&full[cur], (uint32_t)(((q - qbeg) >> 1) & 1));
+#endif
     // ---- P0: phases, parity signs of the reversed direction, flip basis ----
     if(p0live) {
       const cplx pp = s_ph[NM + pa], pm = s_ph[NM - pa];
@@ -904,8 +985,10 @@ __global__ void __launch_bounds__(ROT_THREADS, ROT_MIN_CTAS) k_matvec_rot(const 
     }
     __syncthreads(); // B1: T complete; every thread is past P3/P4 of the previous pair -> the other record slot is free
     if(q + 1 < qend) {
+#if !ROT_SINGLE_SLOT
       if(tid == 0)
         fetch(cur ^ 1, q + 1);
+#endif
       if(p0live) { // next pair's x into registers (L2 hits), consumed by its P0; its (i, j) was fetched a pair ago
         if(SPLIT) {
           if(pdir)
@@ -922,8 +1005,19 @@ __global__ void __launch_bounds__(ROT_THREADS, ROT_MIN_CTAS) k_matvec_rot(const 
     const int4 pnext2 = a.pinfo[q + 2 < qend ? q + 2 : qend - 1]; // (i, j) of the pair after the next one
     ROT_PER_WARP(rot_p1_warp, (std::make_integer_sequence<int, T.nd>{})) // P1: u = D^T t, channel combinations
     __syncthreads();                                                     // B2
+#if ROT_SINGLE_SLOT
+    // every warp has its small-d fragments in registers (P3 reuses them): the small-d part of the slot and the phase slot
+    // of the previous pair are free for the next pair; P2 needs the axial part of this one
+    if(tid == 0 && q + 1 < qend)
+      fetch_geo(q + 1, cur ^ 1);
+    r_mbar_wait(&full[1], (uint32_t)cur);
+#endif
     ROT_PER_WARP(rot_p2_warp, (std::make_integer_sequence<int, T.nc>{})) // P2: q = C p, back to the class vectors
     __syncthreads();                                                     // B3
+#if ROT_SINGLE_SLOT
+    if(tid == 0 && q + 1 < qend) // the axial part is free
+      fetch_ax(q + 1);
+#endif
     ROT_PER_WARP(rot_p3_warp, (std::make_integer_sequence<int, T.nd>{})) // P3: w = D v; P4: accumulate
     if(pi.w & 3) { // last pair of the strip / of the segment: the finished sums go to HBM
       __syncthreads();
@@ -1028,10 +1122,11 @@ void rot_plan_build(RotPlan &p, int nobj, int NM, int world, int rank, int sm_co
   p.threads = ROT_THREADS;
   if(L.nh > ROT_THREADS)
     throw Error("rotated-axial operator: nMax exceeds the kernel's thread bound");
-  // rows per block: as many (<= 4) as keep three CTAs per SM resident (the row sums of a block live in shared memory)
-  int I = g_rot_rows > 0 ? g_rot_rows : 4;
+  // rows per block: as many (<= 8) as keep rot_min_ctas CTAs per SM resident (the row sums of a block live in shared
+  // memory; one column partial per strip of up to I pairs goes to HBM: C5 3.74 ms per apply with 4 rows, 3.69 with 8)
+  int I = g_rot_rows > 0 ? g_rot_rows : 8;
   const size_t sm_total = (size_t)228 * 1024, cta_max = (size_t)227 * 1024;
-  while(I > 1 && ROT_MIN_CTAS * (rot_smem_bytes(L, I) + 1024) > sm_total)
+  while(I > 1 && rot_min_ctas(NM) * (rot_smem_bytes(L, I) + 1024) > sm_total)
     --I;
   if(rot_smem_bytes(L, I) > cta_max)
     throw Error("rotated-axial operator: record does not fit in shared memory");
