@@ -423,7 +423,9 @@ __host__ __device__ constexpr inline RotCT rot_ct(int NM) {
   for(int a = 0; a <= NM; ++a) { // one P2 unit per order
     const int w = NM - rot_n0(a) + 1;
     T.ca[T.nc] = a;
-    T.cc[T.nc] = rot_tiles(w) * ((w + 3) / 4) * (a == 0 ? 2 : 4);
+    // DMMAs: two (Re, Im) per K step, channel and full tile; one for a stacked tile of at most four rows
+    const int full = w / 8, rest = w - 8 * full;
+    T.cc[T.nc] = (2 * full + (rest > 4 ? 2 : rest > 0 ? 1 : 0)) * ((w + 3) / 4) * (a == 0 ? 1 : 2);
     ++T.nc;
   }
   rot_ct_assign(T.nd, T.dc, T.dw);
@@ -661,8 +663,36 @@ __device__ __forceinline__ void rot_p2_tile(RotLane const &c, const double *bP, 
   constexpr RotCT T = rot_ct(NM);
   constexpr int a = T.ca[U], m0 = 8 * TILE, n0 = rot_n0(a), w = NM - n0 + 1, ks = (w + 3) / 4;
   constexpr int XC = rot_offX(NM, NM + 1), XM = XC - NM * NM;
-  double apr[2] = {0, 0}, api[2] = {0, 0};
   constexpr int Rt = w - m0 < 8 ? w - m0 : 8, kv = w - 4 * (ks - 1); // fragment order: tile m0 / 8 of the w x w block of order a
+  constexpr double h = (a & 1) ? -0.5 : 0.5; // (-1)^a of the transposed small-d read, and the 1/2 of the channel split
+  if constexpr(Rt <= 4) {
+    // STACKED tile (at most four rows): lanes fr < 4 take the Re C rows, lanes fr >= 4 the Im C rows fr - 4 of the same
+    // fragment position in the other plane: one DMMA per K step instead of two; the halves meet by one shuffle
+    const int hi = c.fr >> 2, r = c.fr & 3;
+    const int lofs = rot_offX(NM, a) + m0 * w - 16 * hi; // c.Cp carries + lane = + 16 hi + 4 r + fc
+    const int tofs = lofs + 4 * Rt * (ks - 1) - (4 - kv) * r;
+    double ap[2] = {0, 0};
+    rot_chain<ks, w>(ap, c.Cp + hi * XC + lofs, 4 * Rt, c.Cp + hi * XC + tofs, bP, c.fc);
+    const double opx = __shfl_xor_sync(0xffffffffu, ap[0], 16), opy = __shfl_xor_sync(0xffffffffu, ap[1], 16);
+    const double qpx = ap[0] - opy, qpy = ap[1] + opx; // valid in the lanes fr < 4 (Re rows own, Im rows from the partner)
+    const int n = n0 + m0 + r;
+    double *V = c.vst + 4 * ((n - 1) * (n + 2) + a);
+    if(a == 0) {
+      if(c.fr < Rt)
+        *(cplx *)V = mk(qpx, qpy);
+    } else {
+      double am[2] = {0, 0};
+      rot_chain<ks, w>(am, c.Cm + hi * XM + lofs, 4 * Rt, c.Cm + hi * XM + tofs, bM, c.fc);
+      const double omx = __shfl_xor_sync(0xffffffffu, am[0], 16), omy = __shfl_xor_sync(0xffffffffu, am[1], 16);
+      const double qmx = am[0] - omy, qmy = am[1] + omx;
+      if(c.fr < Rt) {
+        *(cplx *)V = mk(h * (qpx + qmx), h * (qpy + qmy));
+        *(cplx *)(V + 4 * (n + 1) + 2 - 4 * c.cpol) = mk(h * (qpx - qmx), h * (qpy - qmy));
+      }
+    }
+    return;
+  }
+  double apr[2] = {0, 0}, api[2] = {0, 0};
   const int tofs = rot_offX(NM, a) + m0 * w + 4 * Rt * (ks - 1) - (4 - kv) * c.fr;
   rot_chain2<ks, w>(apr, api, c.Cp + rot_offX(NM, a) + m0 * w, XC, 4 * Rt, c.Cp + tofs, bP, c.fc);
   // complex products: (Re C p_re - Im C p_im, Re C p_im + Im C p_re); lane = (row n, channel fc = direction * 2 + family)
@@ -676,7 +706,6 @@ __device__ __forceinline__ void rot_p2_tile(RotLane const &c, const double *bP, 
     double amr[2] = {0, 0}, ami[2] = {0, 0};
     rot_chain2<ks, w>(amr, ami, c.Cm + rot_offX(NM, a) + m0 * w, XM, 4 * Rt, c.Cm + tofs, bM, c.fc);
     const double qmx = amr[0] - ami[1], qmy = amr[1] + ami[0];
-    constexpr double h = (a & 1) ? -0.5 : 0.5; // (-1)^a of the transposed small-d read, and the 1/2 of the channel split
     if(m0 + 7 < w || row < w) {
       *(cplx *)V = mk(h * (qpx + qmx), h * (qpy + qmy));                                   // v_s: TE (p) / TM (r)
       *(cplx *)(V + 4 * (n + 1) + 2 - 4 * c.cpol) = mk(h * (qpx - qmx), h * (qpy - qmy)); // v_a: TM (p) / TE (r)
