@@ -379,6 +379,9 @@ k_rot_tables(const double *__restrict__ xyz, const int2 *__restrict__ pair_ij, l
 #ifndef ROT_SINGLE_SLOT
 #define ROT_SINGLE_SLOT 1
 #endif
+#ifndef ROT_SPLIT_CHAINS
+#define ROT_SPLIT_CHAINS 0 // 1: odd and even K steps of a DMMA chain accumulate separately (shorter dependency chains; measured slower: 3.88 against 3.66 ms per C5 apply, the extra accumulators cost registers)
+#endif
 #ifndef ROT_MIN_CTAS
 #define ROT_MIN_CTAS 3
 #endif
@@ -544,6 +547,21 @@ __device__ __forceinline__ void rot_chain(double (&acc)[2], const double *__rest
     for(int s = 0; s < KS; ++s)
       keep[s] = av[s];
   }
+#if ROT_SPLIT_CHAINS
+  if constexpr(KS >= 2) { // two independent accumulation chains (odd / even K steps), added at the end
+    double acc2[2] = {0.0, 0.0};
+#pragma unroll
+    for(int s = 0; s < KS; ++s) {
+      if(s & 1)
+        dmma(acc2, av[s], bv[s]);
+      else
+        dmma(acc, av[s], bv[s]);
+    }
+    acc[0] += acc2[0];
+    acc[1] += acc2[1];
+    return;
+  }
+#endif
 #pragma unroll
   for(int s = 0; s < KS; ++s)
     dmma(acc, av[s], bv[s]);
@@ -564,6 +582,26 @@ __device__ __forceinline__ void rot_chain2(double (&accR)[2], double (&accI)[2],
     ar[KS - 1] = in ? ar[KS - 1] : 0.0;
     ai[KS - 1] = in ? ai[KS - 1] : 0.0;
   }
+#if ROT_SPLIT_CHAINS
+  if constexpr(KS >= 2) {
+    double r2[2] = {0.0, 0.0}, i2[2] = {0.0, 0.0};
+#pragma unroll
+    for(int s = 0; s < KS; ++s) {
+      if(s & 1) {
+        dmma(r2, ar[s], bv[s]);
+        dmma(i2, ai[s], bv[s]);
+      } else {
+        dmma(accR, ar[s], bv[s]);
+        dmma(accI, ai[s], bv[s]);
+      }
+    }
+    accR[0] += r2[0];
+    accR[1] += r2[1];
+    accI[0] += i2[0];
+    accI[1] += i2[1];
+    return;
+  }
+#endif
 #pragma unroll
   for(int s = 0; s < KS; ++s) {
     dmma(accR, ar[s], bv[s]);
