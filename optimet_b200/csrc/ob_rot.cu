@@ -147,14 +147,28 @@ static size_t rot_axial_table_bytes(int NM) {
   return ((size_t)z.nrec * (4 * sizeof(double) + sizeof(int)) + (size_t)z.nem * (8 * sizeof(double) + 2 * sizeof(int)) + 15) &
          ~(size_t)15;
 }
+// TAB_SMEM: the tables are read through pointers the compiler can see are shared memory (LDS with 32-bit addresses).
+// The first version selected between the global and the shared copy at run time: every table read became a generic LD
+// (64-bit address arithmetic, long-scoreboard latency: 40 % of the stall samples, profiles/r4k_assemble_axial_only_full.txt)
+template <bool TAB_SMEM>
 __global__ void __launch_bounds__(ROT_AX_MAX_WARPS * 32)
 k_assemble_axial_only(const double *__restrict__ xyz, cplx k, const int2 *__restrict__ pair_ij, long npairs,
-                      unsigned char *__restrict__ recs, RotLayout L, RotAxTab gtab, int nrec, int nem, int tab_in_smem) {
+                      unsigned char *__restrict__ recs, RotLayout L, RotAxTab gtab, int nrec, int nem) {
   extern __shared__ __align__(16) unsigned char smem_ax[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  RotAxTab tab = gtab;
-  unsigned char *wbuf = smem_ax;
-  if(tab_in_smem) { // doubles first (16-byte aligned), then the three index arrays
+  auto pairs = [&](RotAxTab const &tab, unsigned char *wbuf) {
+    cplx *buf = (cplx *)wbuf + (size_t)warp * rot_axial_fast_entries(L.NM);
+    for(long q = (long)blockIdx.x * nwarps + warp; q < npairs; q += (long)gridDim.x * nwarps) {
+      const int2 ij = pair_ij[q];
+      const double x = xyz[3 * ij.x] - xyz[3 * ij.y], y = xyz[3 * ij.x + 1] - xyz[3 * ij.y + 1],
+                   z = xyz[3 * ij.x + 2] - xyz[3 * ij.y + 2];
+      const double r = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
+      unsigned char *rec = recs + (size_t)q * L.rec_bytes;
+      rot_axial_pair_fast(L.NM, k, r, buf, (double *)(rec + L.offCp), (double *)(rec + L.offCm), lane, 32, tab);
+      __syncwarp();
+    }
+  };
+  if constexpr(TAB_SMEM) { // doubles first (16-byte aligned), then the three index arrays, then the warps' level buffers
     double *s_rec = (double *)smem_ax, *s_emit = s_rec + (size_t)nrec * 4;
     int *s_ridx = (int *)(s_emit + (size_t)nem * 8), *s_eidx = s_ridx + nrec, *s_eout = s_eidx + nem;
     for(int e = threadIdx.x; e < nrec * 4; e += blockDim.x)
@@ -167,25 +181,12 @@ k_assemble_axial_only(const double *__restrict__ xyz, cplx k, const int2 *__rest
       s_eidx[e] = gtab.eidx[e];
       s_eout[e] = gtab.eout[e];
     }
-    tab.rec = s_rec;
-    tab.emit = s_emit;
-    tab.ridx = s_ridx;
-    tab.eidx = s_eidx;
-    tab.eout = s_eout;
-    wbuf = smem_ax + (((size_t)nrec * (4 * sizeof(double) + sizeof(int)) + (size_t)nem * (8 * sizeof(double) + 2 * sizeof(int)) + 15) &
-                      ~(size_t)15);
     __syncthreads();
-  }
-  cplx *buf = (cplx *)wbuf + (size_t)warp * rot_axial_fast_entries(L.NM);
-  for(long q = (long)blockIdx.x * nwarps + warp; q < npairs; q += (long)gridDim.x * nwarps) {
-    const int2 ij = pair_ij[q];
-    const double x = xyz[3 * ij.x] - xyz[3 * ij.y], y = xyz[3 * ij.x + 1] - xyz[3 * ij.y + 1],
-                 z = xyz[3 * ij.x + 2] - xyz[3 * ij.y + 2];
-    const double r = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
-    unsigned char *rec = recs + (size_t)q * L.rec_bytes;
-    rot_axial_pair_fast(L.NM, k, r, buf, (double *)(rec + L.offCp), (double *)(rec + L.offCm), lane, 32, tab);
-    __syncwarp();
-  }
+    const RotAxTab tab = {s_rec, s_emit, s_ridx, s_eidx, s_eout, nrec, nem};
+    pairs(tab, smem_ax + (((size_t)nrec * (4 * sizeof(double) + sizeof(int)) + (size_t)nem * (8 * sizeof(double) + 2 * sizeof(int)) + 15) &
+                          ~(size_t)15));
+  } else
+    pairs(gtab, smem_ax);
 }
 
 // index-only coefficient tables of the axial recursion, one set per (device, nMax)
@@ -1334,9 +1335,9 @@ void launch_assemble_rot(VtacTableSet const &ts, const double *xyz, cplx k, cons
       const long per_sm = std::max<long>(1, std::min<long>(16, (long)(220 * 1024) / (long)(sm + 1024)));
       ctas = std::min<long>((npairs + warps - 1) / warps, (long)sm_count * per_sm);
     }
-    OB_CUDA(cudaFuncSetAttribute((const void *)k_assemble_axial_only, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    k_assemble_axial_only<<<(unsigned)ctas, warps * 32, sm, st>>>(xyz, k, pair_ij, npairs, recs, L, rot_axtab(L.NM), z.nrec, z.nem,
-                                                                 in_smem);
+    auto kern = in_smem ? k_assemble_axial_only<true> : k_assemble_axial_only<false>;
+    OB_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    kern<<<(unsigned)ctas, warps * 32, sm, st>>>(xyz, k, pair_ij, npairs, recs, L, rot_axtab(L.NM), z.nrec, z.nem);
   } else {
     OB_CUDA(cudaFuncSetAttribute((const void *)k_assemble_axial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ts.smem));
     OB_CUDA(cudaFuncSetAttribute((const void *)k_assemble_axial, cudaFuncAttributePreferredSharedMemoryCarveout,

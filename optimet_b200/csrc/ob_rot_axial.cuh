@@ -266,17 +266,24 @@ __host__ __device__ inline void rot_axial_pair(int NM, cplx k, double r, cplx *b
 // n - 1).  buf: [2][NM + 2][2 NM + 3] complex per warp; stale entries are never read (the flags say which terms exist).
 // tests/test_rot_axial_host.py holds it bit-identical to rot_axial_pair on the host.
 __host__ __device__ inline int rot_axial_fast_entries(int NM) { return 2 * (NM + 2) * (2 * NM + 3); }
+// seeds (n = m = 0): sqrt(4 pi) (-1)^l Y_l0(0) h_l = (-1)^l sqrt(2l + 1) h_l(k r), order l kept by lane l mod nlanes
+struct RotAxialSeed {
+  cplx *buf;
+  int LL, lane, nlanes;
+  __host__ __device__ void operator()(int l, cplx h) {
+    if(l <= LL && l % nlanes == lane) {
+      const double f = ((l & 1) ? -1.0 : 1.0) * sqrt(2.0 * l + 1.0);
+      buf[l] = cscale(h, f);
+    }
+  }
+};
 __host__ __device__ inline void rot_axial_pair_fast(int NM, cplx k, double r, cplx *buf, double *Cp, double *Cm, int lane,
                                                     int nlanes, RotAxTab const &tab) {
   const int LL = 2 * NM, W = LL + 3, CH = NM + 2;
   const int X = rot_offX(NM, NM + 1), XM = X - NM * NM;
-  {
-    cplx h[2 * 13 + 2];
-    sph_hankel1(cscale(k, r), LL + 1, h);
-    for(int l = lane; l <= LL; l += nlanes) {
-      const double f = ((l & 1) ? -1.0 : 1.0) * sqrt(2.0 * l + 1.0);
-      buf[l] = cscale(h[l], f); // level 0, chain 0
-    }
+  { // every lane runs the short upward Hankel recurrence in registers and stores the orders it owns (level 0, chain 0)
+    RotAxialSeed seed = {buf, LL, lane, nlanes};
+    sph_hankel1_each(cscale(k, r), LL + 1, seed);
   }
   OB_SYNCWARP();
   int offR = 0, offE = 0;

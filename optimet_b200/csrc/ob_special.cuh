@@ -33,20 +33,30 @@ __host__ __device__ inline void csincos(cplx z, cplx &s, cplx &c) {
 // solution for n > |z|, neutral below): h_{n+1} = (2n+1)/z h_n - h_{n-1}.  Single-valued in z
 // (no branch cut), so h1(-conj(z)) = (-1)^n conj(h1(z)) holds exactly as the reference's
 // AMOS + sqrt(pi/2z) path produces it.
-__host__ __device__ inline void sph_hankel1(cplx z, int L, cplx *out) {
+// f(n, h_n) is called for n = 0 .. L in order (the orders stay in registers: an array indexed by a run-time order
+// lives in local memory on the device)
+template <class F> __host__ __device__ inline void sph_hankel1_each(cplx z, int L, F &f) {
   cplx e = cexp_i(z);
   cplx iz = cdiv(mk(1, 0), z);
   cplx h0 = cmul(mk(e.y, -e.x), iz);                          // -i e^{iz} / z
   cplx h1 = cneg(cmul(cmul(e, cadd(z, mk(0, 1))), cmul(iz, iz))); // -e^{iz} (z + i) / z^2
-  out[0] = h0;
+  f(0, h0);
   if(L >= 1)
-    out[1] = h1;
+    f(1, h1);
   for(int n = 1; n < L; ++n) {
     cplx t = csub(cscale(cmul(iz, h1), (double)(2 * n + 1)), h0);
     h0 = h1;
     h1 = t;
-    out[n + 1] = t;
+    f(n + 1, t);
   }
+}
+struct SphStoreOrders {
+  cplx *out;
+  __host__ __device__ void operator()(int n, cplx h) { out[n] = h; }
+};
+__host__ __device__ inline void sph_hankel1(cplx z, int L, cplx *out) {
+  SphStoreOrders st = {out};
+  sph_hankel1_each(z, L, st);
 }
 
 // spherical Bessel j_0..j_L for complex z != 0: Miller's downward recurrence with rescaling,
