@@ -855,6 +855,24 @@ static void source_sh(ob_ctx *c, const cplx *Xint_conj) {
 }
 
 // Result.cpp:557-794; device vectors; partial sums over local particles, gathered on the host side
+// extinction sum of one particle, Re sum_p conj(Q_local[p]) X_sca[p] (Result.cpp:564-571): one thread per local particle,
+// the terms in the order and with the roundings of the host loop this kernel replaces (no contraction into FMAs), so the
+// 2 x 16 N bytes of coefficients no longer travel to the host for it
+__global__ void k_ext_terms(const cplx *__restrict__ q, const cplx *__restrict__ x, int n, int count, double *__restrict__ out) {
+  const int jl = blockIdx.x * blockDim.x + threadIdx.x;
+  if(jl >= count)
+    return;
+  const cplx *qq = q + (size_t)jl * 2 * n, *xx = x + (size_t)jl * 2 * n;
+  double e = 0.0;
+  for(int p = 0; p < n; ++p) {
+    const cplx q1 = qq[p], x1 = xx[p], q2 = qq[p + n], x2 = xx[p + n];
+    const double r1 = __dadd_rn(__dmul_rn(q1.x, x1.x), __dmul_rn(q1.y, x1.y));
+    const double r2 = __dadd_rn(__dmul_rn(q2.x, x2.x), __dmul_rn(q2.y, x2.y));
+    e = __dadd_rn(e, __dadd_rn(r1, r2));
+  }
+  out[jl] = e;
+}
+
 static void cross_sections(ob_ctx *c, const cplx *Xsca, const cplx *Xint, const cplx *XscaSH, const cplx *XintSH,
                            bool do_sh, double cs[5]) {
   const int n = c->hs[0].n, blk = 2 * n;
@@ -868,12 +886,15 @@ static void cross_sections(ob_ctx *c, const cplx *Xsca, const cplx *Xint, const 
                          c->tmpB.p + (size_t)c->first * blk, c->st);
   launch_sca_sum(ts, c->xyz.p, c->waveK, c->first, c->count, Xsca, c->red_d.p + c->first, c->st);
   c->launches += 2;
-  std::vector<hcd> qloc((size_t)c->count * blk), xs((size_t)c->count * blk);
   std::vector<double> sca(c->nobj, 0.0), scaSH(c->nobj, 0.0), ext(c->nobj, 0.0), absSH(c->nobj, 0.0);
-  OB_CUDA(cudaMemcpyAsync(qloc.data(), c->tmpB.p + (size_t)c->first * blk, qloc.size() * sizeof(cplx),
+  if(c->count > 0) {
+    k_ext_terms<<<(c->count + 127) / 128, 128, 0, c->st>>>(c->tmpB.p + (size_t)c->first * blk, Xsca + (size_t)c->first * blk, n,
+                                                           c->count, c->red_d.p + 2 * (size_t)c->nobj + c->first);
+    OB_CUDA(cudaGetLastError());
+    c->launches += 1;
+  }
+  OB_CUDA(cudaMemcpyAsync(ext.data() + c->first, c->red_d.p + 2 * (size_t)c->nobj + c->first, c->count * sizeof(double),
                           cudaMemcpyDeviceToHost, c->st));
-  OB_CUDA(cudaMemcpyAsync(xs.data(), Xsca + (size_t)c->first * blk, xs.size() * sizeof(cplx), cudaMemcpyDeviceToHost,
-                          c->st));
   OB_CUDA(cudaMemcpyAsync(sca.data() + c->first, c->red_d.p + c->first, c->count * sizeof(double),
                           cudaMemcpyDeviceToHost, c->st));
   if(do_sh) {
@@ -893,11 +914,6 @@ static void cross_sections(ob_ctx *c, const cplx *Xsca, const cplx *Xint, const 
                             cudaMemcpyDeviceToHost, c->st));
   OB_CUDA(cudaStreamSynchronize(c->st));
   for(int jl = 0; jl < c->count; ++jl) {
-    double e = 0;
-    const hcd *q = &qloc[(size_t)jl * blk], *x = &xs[(size_t)jl * blk];
-    for(int p = 0; p < n; ++p)
-      e += std::real(std::conj(q[p]) * x[p] + std::conj(q[p + n]) * x[p + n]);
-    ext[c->first + jl] = e;
     if(do_sh) {
       const double mu0 = 4.0 * 3.14159265358979323846 * 1e-7;
       const double eps0 = 1.0 / (mu0 * 299792458.0 * 299792458.0);
