@@ -25,6 +25,11 @@ CLUSTERS = {
     "random3_n13": lambda: U.random_cluster(3, 13, seed=16),
     "random23_n8": lambda: U.random_cluster(23, 8, seed=31),
     "random9_n10": lambda: U.random_cluster(9, 10, seed=77),          # the headline order (C5), several row blocks
+    "random4_n2": lambda: U.random_cluster(4, 2, seed=102),          # every order 1 .. 13 has its own kernel instantiation
+    "random4_n7": lambda: U.random_cluster(4, 7, seed=107),
+    "random4_n9": lambda: U.random_cluster(4, 9, seed=109),
+    "random4_n11": lambda: U.random_cluster(4, 11, seed=111),
+    "random4_n12": lambda: U.random_cluster(4, 12, seed=112),        # 12 rows = a full tile + a stacked tile of four
     "pair_n1": lambda: U.random_cluster(2, 1, seed=3),
     "single_n4": lambda: U.random_cluster(1, 4, seed=5),
     "two_si_z_axis": lambda: U.two_si(nMax=6),                       # theta = 0 / pi
