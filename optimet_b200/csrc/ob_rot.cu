@@ -48,8 +48,9 @@
 //       channels in the same lanes -> class vectors v without any exchange
 //   P3  w = D v (same arrays and access pattern as P1);  P4  flip basis -> m, conjugate phase, parity signs,
 //       accumulate (owner lanes add into the shared-memory row / column sums and flush them at strip / segment ends)
-// The record of the next pair is fetched into the other shared-memory slot by one cp.async.bulk (TMA bulk copy,
-// mbarrier complete_tx) issued right after P0.  Three barriers per pair, three CTAs per SM at nMax 10.
+// The record of the next pair arrives by cp.async.bulk (TMA bulk copies, mbarrier complete_tx) in ONE shared-memory
+// slot that is refilled section by section: small-d part and next phases after P1 (P3 reuses the fragments P1 kept in
+// registers), axial part after P2 (ROT_SINGLE_SLOT).  Three barriers per pair, three CTAs per SM at nMax 10.
 #include "ob_internal.h"
 #include "ob_vtac.cuh"
 #include "ob_rot_axial.cuh"
